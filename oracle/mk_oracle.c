@@ -1,0 +1,469 @@
+/*
+ * CPU ORACLE (C) — TEST INFRASTRUCTURE ONLY.  Not product code, never linked into libmahakala_b200.so.
+ *
+ * A scalar float64 restatement of the reference's per-ray hot path, parallel over rays with OpenMP.
+ * It follows the reference *literally* (forward-mode derivative of the metric + numerical 4x4 inverse,
+ * O(nmb) meshblock scan, back-to-front transfer), so it doubles as the timed "reference CPU path"
+ * (cpu_baseline.kind = "port"; JAX itself is not installable in this image).
+ * Build:  make -C oracle   (gcc -O2 -ffp-contract=off -fopenmp; no FMA contraction, IEEE semantics)
+ *
+ * Parity pinning: validated against oracle/mahakala_oracle.py (NumPy restatement) which in turn passes
+ * the reference's golden shadow vectors (tests/golden/shadow_golden.npz) — tests/test_oracle_*.py.
+ * Rows with no golden vector in the reference (trajectories, sampling, transfer, images) are
+ * "parity unpinned by the reference's own tests".
+ *
+ * Citations are to /root/reference/mahakala/<file>:<line>.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* constants.py:23-31, electrons.py:23-29 */
+static const double EE = 4.8032e-10, CL = 2.99792458e10, ME = 9.1094e-28, MP = 1.6726e-24,
+                    HPL = 6.6261e-27;
+
+/* ---------- jets: value + 3 spatial tangents (the t tangent of jacfwd is identically zero) ---------- */
+typedef struct { double v, d[3]; } jet;
+
+static inline jet jconst(double c) { jet r = {c, {0, 0, 0}}; return r; }
+static inline jet jvar(double x, int k) { jet r = {x, {0, 0, 0}}; r.d[k] = 1.0; return r; }
+static inline jet jadd(jet a, jet b) { jet r; r.v = a.v + b.v; for (int k = 0; k < 3; k++) r.d[k] = a.d[k] + b.d[k]; return r; }
+static inline jet jsub(jet a, jet b) { jet r; r.v = a.v - b.v; for (int k = 0; k < 3; k++) r.d[k] = a.d[k] - b.d[k]; return r; }
+static inline jet jmul(jet a, jet b) { jet r; r.v = a.v * b.v; for (int k = 0; k < 3; k++) r.d[k] = a.d[k] * b.v + b.d[k] * a.v; return r; }
+static inline jet jdiv(jet a, jet b) { jet r; r.v = a.v / b.v; for (int k = 0; k < 3; k++) r.d[k] = (a.d[k] - b.d[k] * r.v) / b.v; return r; }
+static inline jet jscale(double c, jet a) { jet r; r.v = c * a.v; for (int k = 0; k < 3; k++) r.d[k] = c * a.d[k]; return r; }
+static inline jet jsqrt(jet a) { jet r; r.v = sqrt(a.v); for (int k = 0; k < 3; k++) r.d[k] = a.d[k] / (2.0 * r.v); return r; }
+
+/* geodesics.py:95-103, pushed through jets: f and l_mu with their spatial gradients */
+static void metric_jets(const double x[4], double a, jet *f, jet l[4])
+{
+    jet X = jvar(x[1], 0), Y = jvar(x[2], 1), Z = jvar(x[3], 2);
+    double aa = a * a;
+    jet zz = jmul(Z, Z);
+    jet kk = jscale(0.5, jsub(jadd(jadd(jmul(X, X), jmul(Y, Y)), zz), jconst(aa)));
+    jet rr = jadd(jsqrt(jadd(jmul(kk, kk), jscale(aa, zz))), kk);
+    jet r = jsqrt(rr);
+    *f = jdiv(jmul(jscale(2.0, rr), r), jadd(jmul(rr, rr), jscale(aa, zz)));
+    jet q = jadd(rr, jconst(aa));
+    l[0] = jconst(1.0);
+    l[1] = jdiv(jadd(jmul(r, X), jscale(a, Y)), q);
+    l[2] = jdiv(jsub(jmul(r, Y), jscale(a, X)), q);
+    l[3] = jdiv(Z, r);
+}
+
+/* g = eta + f l l (geodesics.py:104) and optionally jg[i][j][k] = d g_ij / d x^(k+1) */
+static void metric_and_jac(const double x[4], double a, double g[4][4], double jg[4][4][3])
+{
+    jet f, l[4];
+    metric_jets(x, a, &f, l);
+    static const double eta[4] = {-1.0, 1.0, 1.0, 1.0};
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            jet gij = jmul(f, jmul(l[i], l[j]));
+            g[i][j] = (i == j ? eta[i] : 0.0) + gij.v;
+            if (jg) for (int k = 0; k < 3; k++) jg[i][j][k] = gij.d[k];
+        }
+}
+
+/* geodesics.py:339-347: inverse by LU with partial pivoting (Gauss-Jordan on [g | I]) */
+static void inv4(const double gin[4][4], double out[4][4])
+{
+    double m[4][8];
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) { m[i][j] = gin[i][j]; m[i][j + 4] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < 4; c++) {
+        int p = c;
+        for (int r = c + 1; r < 4; r++) if (fabs(m[r][c]) > fabs(m[p][c])) p = r;
+        if (p != c) for (int j = 0; j < 8; j++) { double t = m[c][j]; m[c][j] = m[p][j]; m[p][j] = t; }
+        double piv = m[c][c];
+        for (int j = 0; j < 8; j++) m[c][j] /= piv;
+        for (int r = 0; r < 4; r++) {
+            if (r == c) continue;
+            double fct = m[r][c];
+            for (int j = 0; j < 8; j++) m[r][j] -= fct * m[c][j];
+        }
+    }
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[i][j] = m[i][j + 4];
+}
+
+/* geodesics.py:294-309 */
+static void rhs(const double s[8], double a, double out[8])
+{
+    double g[4][4], jg[4][4][3], ig[4][4];
+    const double *v = s + 4;
+    metric_and_jac(s, a, g, jg);
+    inv4(g, ig);
+    double t1[4], t2[4] = {0, 0, 0, 0}, w[4];
+    for (int i = 0; i < 4; i++) {            /* (jg @ v) @ v : sum_jk d_k g_ij v^k v^j  (k spatial) */
+        double acc = 0;
+        for (int j = 0; j < 4; j++) {
+            double inner = 0;
+            for (int k = 0; k < 3; k++) inner += jg[i][j][k] * v[k + 1];
+            acc += inner * v[j];
+        }
+        t1[i] = acc;
+    }
+    for (int k = 0; k < 3; k++) {            /* v @ (v @ jg) : sum_ij v^i v^j d_k g_ij */
+        double acc = 0;
+        for (int i = 0; i < 4; i++) {
+            double inner = 0;
+            for (int j = 0; j < 4; j++) inner += v[j] * jg[i][j][k];
+            acc += v[i] * inner;
+        }
+        t2[k + 1] = acc;
+    }
+    for (int i = 0; i < 4; i++) w[i] = -t1[i] + 0.5 * t2[i];
+    for (int i = 0; i < 4; i++) {
+        double acc = 0;
+        for (int j = 0; j < 4; j++) acc += ig[i][j] * w[j];
+        out[4 + i] = acc;
+        out[i] = v[i];
+    }
+}
+
+/* geodesics.py:317-336 */
+static void rk4(const double s[8], double dt, double a, double out[8])
+{
+    double k1[8], k2[8], k3[8], k4[8], tmp[8], r[8];
+    rhs(s, a, r);   for (int i = 0; i < 8; i++) { k1[i] = dt * r[i]; tmp[i] = s[i] + 0.5 * k1[i]; }
+    rhs(tmp, a, r); for (int i = 0; i < 8; i++) { k2[i] = dt * r[i]; tmp[i] = s[i] + 0.5 * k2[i]; }
+    rhs(tmp, a, r); for (int i = 0; i < 8; i++) { k3[i] = dt * r[i]; tmp[i] = s[i] + k3[i]; }
+    rhs(tmp, a, r); for (int i = 0; i < 8; i++) { k4[i] = dt * r[i]; }
+    const double sixth = 1.0 / 6;
+    for (int i = 0; i < 8; i++) out[i] = s[i] + sixth * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+}
+
+/* geodesics.py:284-291 */
+static double radius_cal(const double x[4], double a)
+{
+    double R = sqrt(x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    double w = R * R - a * a;
+    return sqrt((w + sqrt(w * w + 4 * (a * a) * (x[3] * x[3]))) / 2);
+}
+
+/* geodesics.py:249-252 */
+static double step_rule(const double s[8], double div, double tol, double a, double rEH, double *r_out)
+{
+    double r = radius_cal(s, a);
+    if (r_out) *r_out = r;
+    double dt = -(r - rEH) / div;
+    if (isnan(dt) || fabs(dt) * div < tol || fabs(dt) * div > 1500) return 0.0;
+    return dt;
+}
+
+/*
+ * One ray of geodesic_integrator (geodesics.py:233-281).  Calls emit(row, state, dt) for every row with
+ * dt != 0 and once more for the frozen row (dt = 0).  Returns n = number of accepted steps.
+ * Also returns the "last point" radius of geodesics.py:370-378 (r[argmax(dt) - 1], negative wrap).
+ */
+typedef void (*emit_fn)(void *ctx, int row, const double s[8], double dt);
+
+static int integrate_ray(int N, const double s0[8], double div, double tol, double a,
+                         double final_state[8], double *r_last, emit_fn emit, void *ctx)
+{
+    double rEH = 1 + sqrt(1 - a * a);     /* geodesics.py:350-351 */
+    double s[8], cand[8];
+    memcpy(s, s0, sizeof s);
+    int n = 0;
+    double r_cur, r_prev = NAN;
+    double best_dt = -INFINITY, r_before_best = NAN; int best_idx = -1;
+    double dt = step_rule(s, div, tol, a, rEH, &r_cur);
+    int terminated = 0;
+    for (int it = 0; it < N; it++) {
+        double r_new = NAN, dtn = 0.0;
+        if (dt != 0.0) {
+            rk4(s, dt, a, cand);
+            dtn = step_rule(cand, div, tol, a, rEH, &r_new);
+        }
+        if (dt == 0.0 || dtn == 0.0) {      /* frozen: this row has dt = 0 (geodesics.py:264-267) */
+            if (emit) emit(ctx, it, s, 0.0);
+            /* first zero row = it ; classifier row = it - 1 (wraps to the last row, a frozen copy, if it = 0) */
+            *r_last = (it >= 1) ? r_prev : r_cur;
+            terminated = 1;
+            break;
+        }
+        if (emit) emit(ctx, it, s, dt);
+        if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
+        r_prev = r_cur; r_cur = r_new;
+        memcpy(s, cand, sizeof s);
+        dt = dtn;
+        n++;
+    }
+    if (!terminated) {
+        /* never froze within N rows: argmax over negative dts (geodesics.py:373); row -1 wraps to row N-1 */
+        *r_last = (best_idx >= 1) ? r_before_best : r_prev;
+    }
+    memcpy(final_state, s, sizeof s);
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* exported: geodesics                                                                                */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { double *S, *dt; int npx, p, nrows; } dump_ctx;
+
+static void dump_emit(void *vctx, int row, const double s[8], double dt)
+{
+    dump_ctx *c = (dump_ctx *)vctx;
+    if (row >= c->nrows) return;
+    memcpy(c->S + ((size_t)row * c->npx + c->p) * 8, s, 8 * sizeof(double));
+    c->dt[(size_t)row * c->npx + c->p] = dt;
+}
+
+/* final states, accepted-step counts and last-point radii; optional padded dump (nrows, npx, 8)/(nrows, npx) */
+int orc_integrate(int N, int npx, const double *s0, double div, double tol, double a,
+                  double *final_state, int32_t *nsteps, double *r_last,
+                  double *S_dump, double *dt_dump, int nrows)
+{
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int p = 0; p < npx; p++) {
+        double fin[8], rl;
+        dump_ctx c = {S_dump, dt_dump, npx, p, nrows};
+        int n = integrate_ray(N, s0 + (size_t)p * 8, div, tol, a, fin, &rl, S_dump ? dump_emit : NULL, &c);
+        if (final_state) memcpy(final_state + (size_t)p * 8, fin, sizeof fin);
+        if (nsteps) nsteps[p] = n;
+        if (r_last) r_last[p] = rl;
+        if (S_dump)                          /* rows after the frozen row repeat it (scan keeps emitting) */
+            for (int row = n + 1; row < nrows; row++) {
+                memcpy(S_dump + ((size_t)row * npx + p) * 8, fin, sizeof fin);
+                dt_dump[(size_t)row * npx + p] = 0.0;
+            }
+    }
+    return 0;
+}
+
+void orc_rhs(int n, const double *s, double a, double *out)
+{
+    for (int p = 0; p < n; p++) rhs(s + (size_t)p * 8, a, out + (size_t)p * 8);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* fluid sampling (athenak.py:639-812), electrons (electrons.py:46-50), synchrotron (transfer.py:56-86) */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int nmb, nk, nj, ni;                 /* interior cells per block */
+    const double *data;                  /* (nmb, 8, nk+2, nj+2, ni+2), reference layout */
+    const double *x1f, *x2f, *x3f;       /* (nmb, n+1) */
+    const double *x1v, *x2v, *x3v;       /* (nmb, n) */
+    double a, fluid_gamma;
+} orc_snapshot;
+
+static int find_block(const orc_snapshot *sn, const double x[4])
+{
+    int mb = -1;                          /* athenak.py:663-670: last match wins */
+    for (int b = 0; b < sn->nmb; b++) {
+        const double *f1 = sn->x1f + (size_t)b * (sn->ni + 1);
+        const double *f2 = sn->x2f + (size_t)b * (sn->nj + 1);
+        const double *f3 = sn->x3f + (size_t)b * (sn->nk + 1);
+        if (f1[0] < x[1] && x[1] <= f1[sn->ni] && f2[0] < x[2] && x[2] <= f2[sn->nj] &&
+            f3[0] < x[3] && x[3] <= f3[sn->nk]) mb = b;
+    }
+    return mb;
+}
+
+static double pymod1(double q) { double m = fmod(q, 1.0); if (m < 0) m += 1.0; return m; }
+
+/* athenak.py:718-757: trilinear interpolation of the 8 primitives; zero outside the domain */
+static int interp_prims(const orc_snapshot *sn, const double x[4], double prims[8])
+{
+    int mb = find_block(sn, x);
+    if (mb < 0) { for (int q = 0; q < 8; q++) prims[q] = 0.0; return mb; }
+    const double *v1 = sn->x1v + (size_t)mb * sn->ni, *v2 = sn->x2v + (size_t)mb * sn->nj,
+                 *v3 = sn->x3v + (size_t)mb * sn->nk;
+    double dx1 = v1[1] - v1[0], dx2 = v2[1] - v2[0], dx3 = v3[1] - v3[0];
+    double xi1 = x[1] - v1[0] + dx1, xi2 = x[2] - v2[0] + dx2, xi3 = x[3] - v3[0] + dx3;
+    double d1 = pymod1(xi1 / dx1), d2 = pymod1(xi2 / dx2), d3 = pymod1(xi3 / dx3);
+    /* Python float floor-division: floor((xi - fmod(xi, dx)) / dx), adjusted like CPython/NumPy do */
+    int i1, i2, i3;
+    {   /* np.floor_divide semantics: computed from the remainder, exact at cell faces */
+        double m;
+        m = fmod(xi1, dx1); if (m != 0 && ((dx1 < 0) != (m < 0))) m += dx1; i1 = (int)floor((xi1 - m) / dx1 + 0.5);
+        m = fmod(xi2, dx2); if (m != 0 && ((dx2 < 0) != (m < 0))) m += dx2; i2 = (int)floor((xi2 - m) / dx2 + 0.5);
+        m = fmod(xi3, dx3); if (m != 0 && ((dx3 < 0) != (m < 0))) m += dx3; i3 = (int)floor((xi3 - m) / dx3 + 0.5);
+    }
+    size_t s1 = 1, s2 = (size_t)(sn->ni + 2), s3 = s2 * (sn->nj + 2), sp = s3 * (sn->nk + 2);
+    const double *base = sn->data + (size_t)mb * 8 * sp;
+    for (int q = 0; q < 8; q++) {
+        const double *d = base + q * sp + i3 * s3 + i2 * s2 + i1 * s1;
+        double aaa = d[0], aab = d[s1], aba = d[s2], abb = d[s2 + s1];
+        double baa = d[s3], bab = d[s3 + s1], bba = d[s3 + s2], bbb = d[s3 + s2 + s1];
+        double aa = aaa + (aab - aaa) * d1, ab = aba + (abb - aba) * d1;
+        double ba = baa + (bab - baa) * d1, bb = bba + (bbb - bba) * d1;
+        double a_ = aa + (ab - aa) * d2, b_ = ba + (bb - ba) * d2;
+        prims[q] = a_ + (b_ - a_) * d3;
+    }
+    return mb;
+}
+
+/* athenak.py:760-794; prims order dens, velx, vely, velz, eint, bcc1..3.  out: dens,u,pitch,kdotu,b */
+static void fluid_scalars(const double s[8], const double prims[8], double a, double fallback, double out[5])
+{
+    double g[4][4], ig[4][4];
+    metric_and_jac(s, a, g, NULL);
+    inv4(g, ig);
+    double alpha = sqrt(1. / (-ig[0][0]));
+    const double *U = prims + 1, *Bp = prims + 5;
+    double q = 0;
+    for (int j = 0; j < 3; j++) { double t = 0; for (int i = 0; i < 3; i++) t += U[i] * g[i + 1][j + 1]; q += t * U[j]; }
+    double gamma = sqrt(1 + q);
+    double ucon[4], ucov[4], bcon[4], bcov[4];
+    ucon[0] = gamma / alpha;
+    for (int i = 0; i < 3; i++) ucon[i + 1] = U[i] - gamma * alpha * ig[0][i + 1];
+    for (int i = 0; i < 4; i++) { double t = 0; for (int j = 0; j < 4; j++) t += g[i][j] * ucon[j]; ucov[i] = t; }
+    bcon[0] = 0; for (int i = 0; i < 3; i++) bcon[0] += Bp[i] * ucov[i + 1];
+    for (int i = 0; i < 3; i++) bcon[i + 1] = (Bp[i] + ucon[i + 1] * bcon[0]) / ucon[0];
+    for (int i = 0; i < 4; i++) { double t = 0; for (int j = 0; j < 4; j++) t += g[i][j] * bcon[j]; bcov[i] = t; }
+    double kdotu = 0, kdotb = 0, bdotb = 0;
+    for (int i = 0; i < 4; i++) { kdotu += s[4 + i] * ucov[i]; kdotb += s[4 + i] * bcov[i]; bdotb += bcon[i] * bcov[i]; }
+    double c = kdotb / (fabs(kdotu) * sqrt(bdotb));
+    if (isnan(c)) c = cos(fallback);
+    if (fabs(c) > 1.0) c = c / fabs(c);
+    out[0] = prims[0]; out[1] = prims[4]; out[2] = acos(c); out[3] = kdotu; out[4] = sqrt(bdotb);
+}
+
+/* transfer.py:56-86 */
+static void synchrotron(double Ne, double Theta_e, double B, double pitch, double nu,
+                        int invariant, double rescale_nu, double *em_out, double *ab_out)
+{
+    double nuc = EE * B / (2. * M_PI * ME * CL);
+    double nus = (2. / 9.) * nuc * (Theta_e * Theta_e) * sin(pitch);
+    double X = nu / nus;
+    double var = exp(-pow(X, 1. / 3));
+    double term = sqrt(X) + pow(2.0, 11. / 12) * pow(X, 1. / 6);
+    double em = Ne * nus * (term * term) / (2. * (Theta_e * Theta_e));
+    em = em * var * sqrt(2) * M_PI * (EE * EE) / (3.0 * CL);
+    if (X > 1.e12) em = 0;
+    if (Theta_e < 0.3) em = 0;
+    double bx = HPL * nu / (ME * CL * CL * Theta_e);
+    double series = bx / 24. * (24. + bx * (12. + bx * (4. + bx)));
+    double den = (bx < 2.e-3) ? series : exp(bx) - 1;
+    double B_nu = (2. * HPL * (nu * nu * nu) / den) / (CL * CL);
+    double ab = em / B_nu;
+    if (invariant) { double rn = nu * rescale_nu; em = em / (rn * rn); ab = ab * rn; }
+    if (isnan(em)) em = 0;
+    if (isnan(ab)) ab = 0;
+    *em_out = em; *ab_out = ab;
+}
+
+/* images.py:87-118 for one sample: invariant j, alpha from the 5 fluid scalars */
+static void sample_coefficients(const double sc[5], double fluid_gamma, double r_high, double Ne_unit,
+                                double B_unit, double nu_obs, double *em, double *ab)
+{
+    double dens = sc[0], u = sc[1], pitch = sc[2], kdotu = sc[3], b = sc[4];
+    double bsq = b * b;
+    double beta = u * (fluid_gamma - 1.) / bsq / 0.5;
+    double sigma = bsq / dens;
+    /* electrons.py:46-50 with r_low = 1, electron_gamma = 4/3, ion_gamma = 5/3 */
+    double eg = 4. / 3, ig = 5. / 3, r_low = 1;
+    double T_ratio = (r_high * (beta * beta) + r_low) / (1 + beta * beta);
+    double t_e = (CL * CL) * (MP * u * (eg - 1.) * (ig - 1.));
+    t_e /= dens * ((ig - 1.) + (eg - 1.) * T_ratio);
+    double Theta_e = t_e / (ME * CL * CL);
+    double Ne = Ne_unit * dens, Bg = B_unit * b, local_nu = -kdotu * nu_obs;
+    synchrotron(Ne, Theta_e, Bg, pitch, local_nu, 1, 1. / nu_obs, em, ab);
+    if (sigma > 100.) { *em = 0; *ab = 0; }      /* images.py:116-118 (NaN > 100 is false) */
+}
+
+/* exported: S (nrows, npx, 8) -> scalars (5, nrows, npx) [dens,u,pitch,kdotu,b] or prims (8, nrows, npx) */
+static orc_snapshot make_snap(int nmb, int nk, int nj, int ni, const double *data,
+                              const double *x1f, const double *x2f, const double *x3f,
+                              const double *x1v, const double *x2v, const double *x3v,
+                              double a, double fluid_gamma)
+{
+    orc_snapshot sn = {nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, fluid_gamma};
+    return sn;
+}
+
+int orc_sample(int mode, long nsamples, const double *S,
+               int nmb, int nk, int nj, int ni, const double *data,
+               const double *x1f, const double *x2f, const double *x3f,
+               const double *x1v, const double *x2v, const double *x3v,
+               double a, double fallback_pitch, double *out)
+{
+    orc_snapshot sn = make_snap(nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long p = 0; p < nsamples; p++) {
+        double prims[8];
+        interp_prims(&sn, S + p * 8, prims);
+        if (mode == 0) {
+            double sc[5];
+            fluid_scalars(S + p * 8, prims, a, fallback_pitch, sc);
+            for (int q = 0; q < 5; q++) out[(size_t)q * nsamples + p] = sc[q];
+        } else {
+            /* dens, u(eint), U1..3, B1..3 */
+            out[0 * nsamples + p] = prims[0]; out[1 * nsamples + p] = prims[4];
+            for (int q = 0; q < 3; q++) { out[(size_t)(2 + q) * nsamples + p] = prims[1 + q]; out[(size_t)(5 + q) * nsamples + p] = prims[5 + q]; }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* exported: whole images.py:56-144 chain per ray (integrate -> sample -> j,alpha -> back-to-front)   */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { double *buf; int cap, n; } traj_ctx;   /* rows of 9 doubles: state, dt */
+
+static void traj_emit(void *vctx, int row, const double s[8], double dt)
+{
+    traj_ctx *c = (traj_ctx *)vctx;
+    if (row >= c->cap) { c->cap *= 2; c->buf = (double *)realloc(c->buf, (size_t)c->cap * 9 * sizeof(double)); }
+    memcpy(c->buf + (size_t)row * 9, s, 8 * sizeof(double));
+    c->buf[(size_t)row * 9 + 8] = dt;
+    c->n = row + 1;
+}
+
+int orc_render(int N, int npx, const double *s0, double div, double tol,
+               int nmb, int nk, int nj, int ni, const double *data,
+               const double *x1f, const double *x2f, const double *x3f,
+               const double *x1v, const double *x2v, const double *x3v,
+               double a, double fluid_gamma, double r_high, double Ne_unit, double B_unit, double L_unit,
+               int nfreq, const double *nu_obs, double *image /* (nfreq, npx) */, int32_t *nsteps,
+               int64_t *n_in_domain)
+{
+    orc_snapshot sn = make_snap(nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, fluid_gamma);
+    int64_t indom = 0;
+#pragma omp parallel reduction(+ : indom)
+    {
+        traj_ctx tc; tc.cap = 4096; tc.buf = (double *)malloc((size_t)tc.cap * 9 * sizeof(double));
+#pragma omp for schedule(dynamic, 16)
+        for (int p = 0; p < npx; p++) {
+            double fin[8], rl;
+            tc.n = 0;
+            int n = integrate_ray(N, s0 + (size_t)p * 8, div, tol, a, fin, &rl, traj_emit, &tc);
+            if (nsteps) nsteps[p] = n;
+            /* rows 0..tc.n-1 exist (tc.n-1 is the frozen row when the ray froze within N rows).  Rows after
+               it repeat the frozen row with dt = 0 and contribute -0*L*(...) = 0 (transfer.py:106-109). */
+            for (int fq = 0; fq < nfreq; fq++) {
+                double I = 0.0;
+                for (int i = tc.n - 1; i >= 1; i--) {
+                    const double *row = tc.buf + (size_t)i * 9;
+                    double dtm = tc.buf[(size_t)(i - 1) * 9 + 8];
+                    double prims[8], sc[5], em, ab;
+                    int mb = interp_prims(&sn, row, prims);
+                    if (fq == 0 && mb >= 0) indom++;
+                    fluid_scalars(row, prims, a, M_PI / 3., sc);
+                    sample_coefficients(sc, fluid_gamma, r_high, Ne_unit, B_unit, nu_obs[fq], &em, &ab);
+                    double dI = -dtm * L_unit * (em - (ab * I));
+                    I += dI;
+                }
+                image[(size_t)fq * npx + p] = I;
+            }
+        }
+        free(tc.buf);
+    }
+    if (n_in_domain) *n_in_domain = indom;
+    return 0;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
