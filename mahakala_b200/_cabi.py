@@ -1,0 +1,82 @@
+"""ctypes binding of libmahakala_b200.so (the C ABI declared in include/mahakala_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or CUDA is unavailable every
+compute entry point raises ``RuntimeError``.  Importing the package (and loading the library to inspect
+its symbols) works without a GPU so that the build can be checked on a CPU-only host.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmahakala_b200.so")
+
+_c = {"d": ctypes.c_double, "l": ctypes.c_long, "i": ctypes.c_int, "p": ctypes.c_void_p}
+
+# name -> argument kinds, in the order of include/mahakala_b200.h
+SIGNATURES = {
+    "mk_abi_version": "",
+    "mk_device_info": "ppppp",
+    "mk_measure_fp64_peak": "ipp",
+    "mk_camera_grid": "ddddddlipp",
+    "mk_camera_points": "ddddpplipp",
+    "mk_initial_condition": "dpplpp",
+    "mk_integrate": "idllpddpppppl" "pp",
+    "mk_fill_frozen_rows": "ppppllp",
+    "mk_radius_cal": "dpllpp",
+    "mk_rhs": "idplpp",
+    "mk_rk4_step": "idpplpp",
+    "mk_metric": "idplppp",
+}
+
+_lib = None
+
+
+class MahakalaB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (no GPU needed).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MahakalaB200Error(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C mahakala_b200/csrc`).  mahakala_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.mk_last_error_string.restype = ctypes.c_char_p
+        for name, sig in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [_c[k] for k in sig]
+        _lib = lib
+    return _lib
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    if hasattr(x, "data_ptr"):            # torch tensor
+        return ctypes.c_void_p(x.data_ptr())
+    if isinstance(x, ctypes._SimpleCData) or isinstance(x, ctypes.Array):
+        return ctypes.cast(ctypes.byref(x), ctypes.c_void_p)
+    raise TypeError(f"cannot pass {type(x)} as a pointer")
+
+
+def call(name, *args):
+    """Invoke ``name`` with Python scalars / torch tensors / None; raise on a non-zero status."""
+    lib = load()
+    sig = SIGNATURES[name]
+    if len(args) != len(sig):
+        raise TypeError(f"{name} takes {len(sig)} arguments, got {len(args)}")
+    conv = []
+    for kind, a in zip(sig, args):
+        conv.append(_ptr(a) if kind == "p" else a)
+    rc = getattr(lib, name)(*conv)
+    if name == "mk_abi_version":
+        return rc
+    if rc != 0:
+        raise MahakalaB200Error(f"{name} failed ({rc}): {lib.mk_last_error_string().decode()}")
+    return rc

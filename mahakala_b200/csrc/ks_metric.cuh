@@ -1,0 +1,137 @@
+// Closed-form Cartesian Kerr-Schild metric plugin.
+//
+// Replaces, for the built-in spacetime, the reference's jacfwd(metric) + linalg.inv(metric) pair
+// (/root/reference/mahakala/geodesics.py:88-104 metric, :294-309 rhs, :339-347 imetric):
+//     g_mn = eta_mn + f l_m l_n ,  g^mn = eta^mn - f l^m l^n ,  l_m = (1, l1, l2, l3), l^m = (-1, l1, l2, l3)
+// so the inverse is analytic and dg needs only grad f and grad l_i.  The geodesic acceleration
+//     a^m = g^mn ( -d_k g_ns v^k v^s + 1/2 d_n g_ks v^k v^s )              (geodesics.py:307)
+// is evaluated with shared sub-expressions; one reciprocal, one sqrt and one sqrt/rsqrt pair per call.
+//
+// Metric-plugin concept (see metric_plugin.cuh): a plugin provides
+//     void   accel(const double x[4], const double v[4], double acc[4]) const;
+//     double radius(const double x[4]) const;        // the step rule's radius (geodesics.py:284-291)
+//     double horizon() const;                        // geodesics.py:350-351
+//     void   metric_cov_con(const double x[4], double g[4][4], double gi[4][4]) const;   // sampling
+#pragma once
+#include "fp64_math.cuh"
+
+namespace mk {
+
+struct KerrSchild {
+    double a;    // spin
+    double aa;   // a^2
+    double rH;   // 1 + sqrt(1 - a^2), computed on the host exactly as geodesics.py:351
+
+    __device__ __forceinline__ double horizon() const { return rH; }
+
+    // radius_cal (geodesics.py:290-291): R^2 - a^2 + sqrt((R^2 - a^2)^2 + 4 a^2 z^2), halved, rooted.
+    __device__ __forceinline__ double radius(const double x[4]) const
+    {
+        double R2 = fma(x[1], x[1], fma(x[2], x[2], x[3] * x[3]));
+        double w = R2 - aa;
+        double az = aa * (x[3] * x[3]);
+        double disc = fma(w, w, 4.0 * az);
+        double s = fast_sqrt(disc);
+        return fast_sqrt(0.5 * (w + s));
+    }
+
+    // f and l_i of geodesics.py:97-103
+    __device__ __forceinline__ void fl(const double x[4], double& f, double& l1, double& l2, double& l3) const
+    {
+        double zz = x[3] * x[3];
+        double kk = 0.5 * (fma(x[1], x[1], fma(x[2], x[2], zz)) - aa);
+        double az2 = aa * zz;
+        double rr = fast_sqrt(fma(kk, kk, az2)) + kk;
+        double r, ri;
+        fast_sqrt_rsqrt(rr, r, ri);
+        double den = fma(rr, rr, az2);
+        double q = rr + aa;
+        double inv = fast_rcp(den * q);
+        double iden = inv * q, iq = inv * den;
+        f = 2.0 * rr * r * iden;
+        l1 = fma(r, x[1], a * x[2]) * iq;
+        l2 = fma(r, x[2], -a * x[1]) * iq;
+        l3 = x[3] * ri;
+    }
+
+    // Geodesic acceleration d v^m / d lambda (geodesics.py:301-309 in closed form).
+    __device__ __forceinline__ void accel(const double x[4], const double v[4], double acc[4]) const
+    {
+        const double X = x[1], Y = x[2], Z = x[3];
+        const double v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3];
+        double zz = Z * Z;
+        double kk = 0.5 * (fma(X, X, fma(Y, Y, zz)) - aa);
+        double az2 = aa * zz;
+        double rr = fast_sqrt(fma(kk, kk, az2)) + kk;       // r^2
+        double r, ri;
+        fast_sqrt_rsqrt(rr, r, ri);                         // r, 1/r
+        double den = fma(rr, rr, az2);                      // r^4 + a^2 z^2
+        double q = rr + aa;
+        double inv = fast_rcp(den * q);
+        double iden = inv * q, iq = inv * den;              // 1/den, 1/q
+        double rid = r * iden;
+        double f = 2.0 * rr * rid;
+        double l1 = fma(r, X, a * Y) * iq;
+        double l2 = fma(r, Y, -a * X) * iq;
+        double l3 = Z * ri;
+        // grad r = (r/den) (x_i r^2 + a^2 z delta_iz)
+        double t = rid * rr;
+        double aaz = aa * Z;
+        double g1 = t * X, g2 = t * Y, g3 = fma(t, Z, rid * aaz);
+        double Dr = fma(v1, g1, fma(v2, g2, v3 * g3));      // v . grad r
+        // d_i l_j = g_i c_j + (constant part);  c = ((x - 2 r l1)/q, (y - 2 r l2)/q, -z/r^2)
+        double r2 = r + r;
+        double c1 = fma(-r2, l1, X) * iq;
+        double c2 = fma(-r2, l2, Y) * iq;
+        double c3 = -(l3 * ri);
+        double cv = fma(c1, v1, fma(c2, v2, c3 * v3));
+        double e1 = fma(r, v1, -a * v2) * iq;               // sum_j (const part of d_i l_j) v^j
+        double e2 = fma(a, v1, r * v2) * iq;
+        double e3 = v3 * ri;
+        double h1 = fma(r, v1, a * v2) * iq;                // v^i (const part of d_i l_j)
+        double h2 = fma(r, v2, -a * v1) * iq;
+        // D l_j = v . grad l_j ;  N_i = sum_j d_i l_j v^j ;  the force only needs N_i - D l_i
+        double Dl1 = fma(Dr, c1, h1), Dl2 = fma(Dr, c2, h2), Dl3 = fma(Dr, c3, e3);
+        double n1 = fma(g1, cv, e1) - Dl1;
+        double n2 = fma(g2, cv, e2) - Dl2;
+        double n3 = fma(g3, cv, e3) - Dl3;
+        double M = fma(Dl1, v1, fma(Dl2, v2, Dl3 * v3));    // sum_j D l_j v^j
+        // grad f = alpha grad r + beta delta_iz
+        double alpha = rr * iden * fma(-4.0 * f, r, 6.0);
+        double beta = -2.0 * f * iden * aaz;
+        double Df = fma(alpha, Dr, beta * v3);
+        double L = fma(l1, v1, fma(l2, v2, fma(l3, v3, v0)));   // l_m v^m
+        double K = fma(Df, L, f * M);
+        double fL = f * L, hL2 = 0.5 * L * L;
+        // lower-index force w_m = -d_k g_ms v^k v^s + 1/2 d_m g_ks v^k v^s ;  w_0 = -K
+        double w1 = fma(-K, l1, fma(fL, n1, hL2 * (alpha * g1)));
+        double w2 = fma(-K, l2, fma(fL, n2, hL2 * (alpha * g2)));
+        double w3 = fma(-K, l3, fma(fL, n3, hL2 * fma(alpha, g3, beta)));
+        // raise with g^mn = eta^mn - f l^m l^n
+        double P = fma(l1, w1, fma(l2, w2, fma(l3, w3, K)));    // l^n w_n
+        double fP = f * P;
+        acc[0] = K + fP;
+        acc[1] = fma(-fP, l1, w1);
+        acc[2] = fma(-fP, l2, w2);
+        acc[3] = fma(-fP, l3, w3);
+    }
+
+    // Covariant and contravariant metric at x (for the fluid-frame algebra, athenak.py:760-762).
+    __device__ __forceinline__ void metric_cov_con(const double x[4], double g[4][4], double gi[4][4]) const
+    {
+        double f, l[4];
+        l[0] = 1.0;
+        fl(x, f, l[1], l[2], l[3]);
+        const double lu[4] = {-1.0, l[1], l[2], l[3]};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double eta = (i == j) ? (i == 0 ? -1.0 : 1.0) : 0.0;
+                g[i][j] = fma(f * l[i], l[j], eta);
+                gi[i][j] = fma(-f * lu[i], lu[j], eta);
+            }
+    }
+};
+
+}  // namespace mk

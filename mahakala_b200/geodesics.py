@@ -1,0 +1,271 @@
+"""Drop-in for ``mahakala.geodesics`` (reference: /root/reference/mahakala/geodesics.py).
+
+Same names, positional order, keyword names and defaults as the reference; the arithmetic runs in
+hand-written sm_100a CUDA kernels behind the C ABI (``include/mahakala_b200.h``).  Arrays returned are
+``DeviceArray`` objects (HBM-resident, NumPy protocol via ``__array__``), the analogue of the
+``jax.Array`` results of the reference.  There is no CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _cabi
+from ._device import DeviceArray, as_device, empty, require_gpu, stream_ptr
+
+KERR_SCHILD = 0
+KERR_SCHILD_DUAL = 1
+
+_METRICS = {"kerr_schild": KERR_SCHILD, "kerr_schild_dual": KERR_SCHILD_DUAL}
+_active_metric = KERR_SCHILD
+
+
+def set_metric(name):
+    """Select the spacetime plugin used by the module-level functions (the reference's equivalent is
+    replacing the module globals ``metric``/``imetric``, geodesics.py:304-305)."""
+    global _active_metric
+    _active_metric = _METRICS[name] if isinstance(name, str) else int(name)
+    return _active_metric
+
+
+def _cos_sin_deg(inclination):
+    i = inclination * np.pi / 180          # geodesics.py:205
+    return float(np.cos(i)), float(np.sin(i))
+
+
+# -------------------------------------------------------------------------------------------------
+# camera
+# -------------------------------------------------------------------------------------------------
+def initialize_geodesics_at_camera(bhspin, inclination, distance, fov_lower, fov_upper, pixels_per_side,
+                                   camera_type='grid'):
+    """geodesics.py:29-55.  Returns s0 (npx, 8) = [t, x, y, z, k^t, k^x, k^y, k^z]."""
+    if camera_type.lower() == 'grid':
+        n = int(pixels_per_side)
+        ci, si = _cos_sin_deg(inclination)
+        s0 = empty((n * n, 8))
+        _cabi.call("mk_camera_grid", float(bhspin), ci, si, float(distance), float(fov_lower),
+                   float(fov_upper), n, 1, s0, stream_ptr())
+        return DeviceArray.wrap(s0)
+    grid = get_initial_grid(inclination, distance, fov_lower, fov_upper, pixels_per_side, camera_type)
+    if grid is None:
+        return None
+    return initial_condition(grid[0], grid[1], bhspin)
+
+
+def get_initial_grid(inclination, distance, fov_lower, fov_upper, spacing, camera_type):
+    """geodesics.py:137-201.  Returns (s0_x, s0_v), each (4, npx); wavevectors not yet null."""
+    if camera_type.lower() == 'grid':
+        n = int(spacing)
+        ci, si = _cos_sin_deg(inclination)
+        raw = empty((n * n, 8))
+        _cabi.call("mk_camera_grid", 0.0, ci, si, float(distance), float(fov_lower), float(fov_upper), n,
+                   0, raw, stream_ptr())
+        return DeviceArray.wrap(raw[:, :4].T.contiguous()), DeviceArray.wrap(raw[:, 4:].T.contiguous())
+    elif camera_type.lower() == 'equator':
+        grid_list = np.linspace(fov_lower, fov_upper, 2 * spacing + 1)[1::2]
+        s0_x = np.zeros((4, len(grid_list)))
+        s0_x[1] = distance
+        s0_x[2] = grid_list
+        s0_v = np.ones((4, len(grid_list)))
+        s0_v[2] = 0
+        s0_v[3] = 0
+        return s0_x, s0_v
+    else:
+        print(f'Unexpected camera type "{camera_type}".')
+        print('Please choose either "grid" or "equator"')
+
+
+def _image_points(radius, angle):
+    size = np.size(radius)
+    x = np.ones(size) * np.cos(angle) * radius     # geodesics.py:117-118
+    y = np.ones(size) * np.sin(angle) * radius
+    return x, y
+
+
+def get_camera_pixel(inclination, distance, radius, angle):
+    """geodesics.py:107-134.  Returns (s0_x, s0_v), each (4, n)."""
+    x, y = _image_points(np.asarray(radius, dtype=np.float64), np.asarray(angle, dtype=np.float64))
+    ci, si = _cos_sin_deg(inclination)
+    raw = empty((x.size, 8))
+    _cabi.call("mk_camera_points", 0.0, ci, si, float(distance), as_device(x), as_device(y), x.size, 0,
+               raw, stream_ptr())
+    return DeviceArray.wrap(raw[:, :4].T.contiguous()), DeviceArray.wrap(raw[:, 4:].T.contiguous())
+
+
+def initial_condition(s0_x, s0_v, bhspin):
+    """geodesics.py:219-230: make the wavevectors null.  (4, n), (4, n) -> (n, 8)."""
+    sx = as_device(s0_x)
+    sv = as_device(s0_v)
+    n = sx.shape[1]
+    s0 = empty((n, 8))
+    _cabi.call("mk_initial_condition", float(bhspin), sx, sv, n, s0, stream_ptr())
+    return DeviceArray.wrap(s0)
+
+
+def _camera_pixels_state(inclination, distance, radius, angle, bhspin):
+    """get_camera_pixel + initial_condition in one kernel launch."""
+    x, y = _image_points(np.asarray(radius, dtype=np.float64), np.asarray(angle, dtype=np.float64))
+    ci, si = _cos_sin_deg(inclination)
+    s0 = empty((x.size, 8))
+    _cabi.call("mk_camera_points", float(bhspin), ci, si, float(distance), as_device(x), as_device(y),
+               x.size, 1, s0, stream_ptr())
+    return s0
+
+
+# -------------------------------------------------------------------------------------------------
+# metric utilities
+# -------------------------------------------------------------------------------------------------
+def _metric_pair(x, bhspin, want):
+    xs = as_device(x)
+    single = xs.dim() == 1
+    pts = xs.reshape(-1, xs.shape[-1])[:, :4].contiguous()
+    n = pts.shape[0]
+    g = empty((n, 4, 4)) if want == 'g' else None
+    gi = empty((n, 4, 4)) if want == 'gi' else None
+    _cabi.call("mk_metric", _active_metric, float(bhspin), pts, n, g, gi, stream_ptr())
+    out = g if want == 'g' else gi
+    out = out[0] if single else out.reshape(tuple(xs.shape[:-1]) + (4, 4))
+    return DeviceArray.wrap(out)
+
+
+def metric(x, bhspin):
+    """geodesics.py:88-104: covariant Cartesian Kerr-Schild metric at x (..., 4) -> (..., 4, 4)."""
+    return _metric_pair(x, bhspin, 'g')
+
+
+def imetric(x, bhspin):
+    """geodesics.py:339-347: contravariant metric (closed form eta - f l l instead of linalg.inv)."""
+    return _metric_pair(x, bhspin, 'gi')
+
+
+def radius_cal(x, bhspin):
+    """geodesics.py:284-291: Kerr-Schild radius of points x (..., >=4)."""
+    xs = as_device(x)
+    stride = xs.shape[-1]
+    flat = xs.reshape(-1, stride)
+    n = flat.shape[0]
+    r = empty((n,))
+    _cabi.call("mk_radius_cal", float(bhspin), flat, n, stride, r, stream_ptr())
+    return DeviceArray.wrap(r.reshape(xs.shape[:-1]))
+
+
+def radius_EH(a_spin):
+    """geodesics.py:350-351."""
+    return 1 + np.sqrt(1 - a_spin**2)
+
+
+def rhs(state1, bhspin):
+    """geodesics.py:294-309: right-hand side of the geodesic equation; (8,) or (n, 8)."""
+    s = as_device(state1)
+    single = s.dim() == 1
+    s2 = s.reshape(-1, 8)
+    out = empty(s2.shape)
+    _cabi.call("mk_rhs", _active_metric, float(bhspin), s2, s2.shape[0], out, stream_ptr())
+    return DeviceArray.wrap(out[0] if single else out)
+
+
+_vectorized_rhs = rhs
+
+
+def RK4_gen(state1, dt, bhspin):
+    """geodesics.py:317-336: one RK4 step of a bundle (n, 8) with per-ray dt (n,)."""
+    s = as_device(state1)
+    d = as_device(dt).reshape(-1)
+    out = empty(s.shape)
+    _cabi.call("mk_rk4_step", _active_metric, float(bhspin), s, d, s.shape[0], out, stream_ptr())
+    return DeviceArray.wrap(out)
+
+
+# -------------------------------------------------------------------------------------------------
+# integrator
+# -------------------------------------------------------------------------------------------------
+def integrate_final(N, s0, div, tol, bhspin, want_total=False):
+    """Final-state mode of the integrate kernel (no trajectory storage).
+
+    Returns ``(final_state (npx, 8), nsteps (npx,) int32, r_last (npx,))`` as device tensors, where
+    ``r_last`` is the reference's last-point radius ``radius_cal(S)[argmax(dt) - 1]`` (geodesics.py:370-378).
+    """
+    s = as_device(s0)
+    npx = s.shape[0]
+    final = empty((npx, 8))
+    nsteps = empty((npx,), dtype=torch.int32)
+    r_last = empty((npx,))
+    total = torch.zeros(1, dtype=torch.int64, device=s.device) if want_total else None
+    _cabi.call("mk_integrate", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
+               final, nsteps, r_last, None, None, 0, total, stream_ptr())
+    if want_total:
+        return final, nsteps, r_last, total
+    return final, nsteps, r_last
+
+
+def dump_rows(N, max_steps):
+    """Row count of the reference's truncated scan output (geodesics.py:275-281): first all-zero row
+    + 2, or N (+2, clipped to N) when there is none or it is row 0."""
+    first_zero = max_steps if (1 <= max_steps <= N - 1) else N
+    return min(first_zero + 2, N)
+
+
+def geodesic_integrator(N, s0, div, tol, bhspin):
+    """geodesics.py:233-281.  Returns ``(S (nrows, npx, 8), final_dt (nrows, npx))`` in HBM.
+
+    Two passes of the persistent integrate kernel: the first counts steps (so the dump can be allocated
+    exactly as the reference truncates it), the second writes the trajectories.  Use the fused
+    ``images.make_image`` path when the trajectories themselves are not needed.
+    """
+    s = as_device(s0)
+    npx = s.shape[0]
+    N = int(N)
+    if npx == 0:
+        return DeviceArray.wrap(empty((min(N, 2 + N), 0, 8))), DeviceArray.wrap(empty((N, 0)))
+    final, nsteps, _ = integrate_final(N, s, div, tol, bhspin)
+    nrows = dump_rows(N, int(nsteps.max().item()))
+    need = nrows * npx * 72
+    free, _total = torch.cuda.mem_get_info()
+    if need > free:
+        raise MemoryError(f"trajectory dump needs {need / 2**30:.1f} GiB for {nrows} rows x {npx} rays but only "
+                          f"{free / 2**30:.1f} GiB are free: integrate the bundle in chunks (s0[lo:hi])")
+    S = empty((nrows, npx, 8))
+    dt = empty((nrows, npx))
+    _cabi.call("mk_integrate", _active_metric, float(bhspin), N, npx, s, float(div), float(tol),
+               None, None, None, S, dt, nrows, None, stream_ptr())
+    _cabi.call("mk_fill_frozen_rows", S, dt, final, nsteps, npx, nrows, stream_ptr())
+    return DeviceArray.wrap(S), DeviceArray.wrap(dt)
+
+
+# -------------------------------------------------------------------------------------------------
+# shadow finder
+# -------------------------------------------------------------------------------------------------
+def select_photons_integrator(inc, angle, radius, bhspin, distance=1000, max_steps=2000):
+    """geodesics.py:354-378: last-point radius of each photon (used to classify captured / escaped)."""
+    s0 = _camera_pixels_state(inc, distance, radius, angle, bhspin)
+    _, _, r_last = integrate_final(max_steps, s0, 40, 1e-2, bhspin)
+    return DeviceArray.wrap(r_last)
+
+
+def find_shadow_bisection(bhspin, inc, num_angles, max_steps=2000, error_allowed=0.001, max_it=40):
+    """geodesics.py:381-402."""
+    angles = np.arange(num_angles) / num_angles * 2. * np.pi
+    radii = find_shadow_bisection_angles(bhspin, inc, angles, max_it=max_it, error_allowed=error_allowed,
+                                         max_steps=max_steps)
+    radii = np.append(radii, radii[0])
+    angles = np.append(angles, angles[0])
+    return angles, radii
+
+
+def find_shadow_bisection_angles(bhspin, inc, angles, max_steps=2000, error_allowed=0.001, max_it=40):
+    """geodesics.py:405-435: bisection on the image-plane radius of the shadow edge, per angle."""
+    require_gpu()
+    angles = np.asarray(angles, dtype=np.float64)
+    inner = np.zeros_like(angles) + 0.5
+    outer = np.zeros_like(angles) + 10
+    error = outer - inner
+    bisection_limit = 100
+    counter = 0
+    while np.max(error) > error_allowed and counter < max_it:
+        final_mid = np.asarray(select_photons_integrator(inc, angles, (outer - inner) / 2 + inner, bhspin,
+                                                         max_steps=max_steps))
+        fell = np.where(final_mid < bisection_limit)
+        got_away = np.where(final_mid >= bisection_limit)
+        inner[fell] = (outer[fell] - inner[fell]) / 2 + inner[fell]
+        outer[got_away] = (outer[got_away] - inner[got_away]) / 2 + inner[got_away]
+        error = outer - inner
+        counter += 1
+    return inner
