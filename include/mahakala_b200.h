@@ -79,6 +79,92 @@ int mk_rk4_step(int metric_id, double bhspin, const double* state, const double*
 /* geodesics.py:88-104 metric and :339-347 imetric at n points x (n, 4): g, gi (n, 4, 4); either may be NULL */
 int mk_metric(int metric_id, double bhspin, const double* x, long n, double* g, double* gi, void* stream);
 
+/* ---- GRMHD snapshot: grmhd/athenak.py AthenakFluidModel ------------------------------------- */
+typedef struct mk_snapshot mk_snapshot;   /* opaque; owns the repacked, device-resident snapshot */
+
+/*
+ * Repack a ghost-padded AthenaK-style snapshot for sampling (replaces the per-call upload of
+ * athenak.py:693).  Inputs are DEVICE arrays:
+ *   meshblocks (nmb, 8, nk+2, nj+2, ni+2)   the reference's self.all_meshblocks (athenak.py:105-158)
+ *   geom (12, nmb)  rows: x1f[0], x2f[0], x3f[0], x1f[-1], x2f[-1], x3f[-1], x1v[0], x2v[0], x3v[0],
+ *                         dx1, dx2, dx3   (dx = x_v[1] - x_v[0], athenak.py:686-691)
+ *   grid (gn[2], gn[1], gn[0]) int32 block-lookup table over the bounding box, or NULL for the
+ *        reference's linear scan (athenak.py:663-670); cell (c0,c1,c2) covers
+ *        g0[d] + c_d / ginv[d] .. in dimension d.
+ * Host arrays: prim_index[8] = index in `meshblocks` of dens, eint, velx, vely, velz, bcc1, bcc2, bcc3
+ * (athenak.py:697-710); gn, g0, ginv, bbox_lo, bbox_hi (3 each).
+ * store_f32 != 0 stores cells as float32 (caller guarantees the values are float32-representable).
+ * The call is synchronous with respect to `stream` on return of the handle (the inputs may be freed).
+ */
+int mk_snapshot_create(long nmb, long nk, long nj, long ni, const double* meshblocks, const int* prim_index,
+                       const double* geom, const int* grid, const int* gn, const double* g0,
+                       const double* ginv, const double* bbox_lo, const double* bbox_hi, int store_f32,
+                       mk_snapshot** out, void* stream);
+int mk_snapshot_destroy(mk_snapshot* snap);
+/* bytes of HBM held by the snapshot */
+long mk_snapshot_bytes(const mk_snapshot* snap);
+/* raw device pointer + byte size of the repacked cell array (for NCCL broadcast of a replicated
+   snapshot across ranks: every rank creates the same-shaped snapshot, rank 0 broadcasts the cells) */
+int mk_snapshot_cells(mk_snapshot* snap, void** cells, long* bytes);
+
+/* athenak.py:639-812 get_fluid_scalars_from_geodesics: S (n, 8) -> out (5, n) rows dens, u,
+   pitch_angle, kdotu, b.  Kerr-Schild spacetime of spin bhspin. */
+int mk_sample_scalars(const mk_snapshot* snap, double bhspin, const double* S, long n,
+                      double fallback_pitch_angle, double* out, void* stream);
+/* athenak.py:527-637 get_prims_from_geodesics: S (n, 8) -> out (8, n) rows dens, u, U1..3, B1..3 */
+int mk_sample_prims(const mk_snapshot* snap, const double* S, long n, double* out, void* stream);
+
+/* ---- thermodynamics and transfer: electrons.py, transfer.py, images.py ----------------------- */
+typedef struct mk_emission_params {
+    double fluid_gamma, r_low, r_high, electron_gamma, ion_gamma;   /* electrons.py:32-33 */
+    double Ne_unit, B_unit, L_unit;                                   /* grmhd/grmhd.py:40-55 */
+    double sigma_cut;                                                 /* images.py:116 */
+    double EE, CL, ME, MP, HPL;                                       /* constants.py:23-31 */
+    double two_11_12;                                                 /* 2**(11/12), transfer.py:65 */
+} mk_emission_params;
+
+/* electrons.py:32-50 rlow_rhigh_model, elementwise over n values */
+int mk_rlow_rhigh(const double* dens, const double* u, const double* beta, long n, double r_low,
+                  double r_high, double electron_gamma, double ion_gamma, double CL, double MP, double ME,
+                  double* theta_e, void* stream);
+/* transfer.py:30-86 synchrotron_coefficients, elementwise over n values; nu may be per-element */
+int mk_synchrotron(const mk_emission_params* constants, const double* Ne, const double* theta_e,
+                   const double* B, const double* pitch_angle, const double* nu, long n, int invariant,
+                   double rescale_nu, double* emissivity, double* absorptivity, void* stream);
+/* transfer.py:89-119 solve_specific_intensity: em, ab (nrows, npx), dt (nrows, npx) -> I (npx,);
+   dIs (nrows-1, npx) optional (dIs=True variant, rows in scan order i = nrows-1 .. 1) */
+int mk_solve_specific_intensity(const double* em, const double* ab, const double* dt, long nrows, long npx,
+                                double L_unit, double* I_nu, double* dIs, void* stream);
+/* transfer.py:122-144 solve_attenuated_emissivity -> out (nrows-1, npx) */
+int mk_solve_attenuated_emissivity(const double* em, const double* ab, const double* dt, long nrows,
+                                   long npx, double L_unit, double* out, void* stream);
+/* images.py:84-118 for one chunk: S (nrows*npx, 8) -> invariant em, ab (nrows*npx) at frequency nu_obs
+   (fluid scalars -> beta, sigma, Theta_e, units -> j, alpha -> sigma cut), one fused elementwise kernel */
+int mk_emission_from_states(const mk_snapshot* snap, const mk_emission_params* params, double bhspin,
+                            const double* S, long n, double nu_obs, double* em, double* ab, void* stream);
+
+/* ---- fused render: images.py:30-144 make_image ------------------------------------------------ */
+/*
+ * One persistent kernel: camera ray -> RK4 geodesic -> snapshot sample -> j, alpha -> intensity, all in
+ * registers; no trajectory is materialised.  Either a grid camera (s0 == NULL: res x res pixels,
+ * pixel index ix*res+iy as images.py:144) or explicit rays s0 (npx, 8).
+ *   image (nfreq, npx)  specific intensity per observing frequency nu_obs[f] (nfreq <= 8)
+ *   nsteps (npx,) optional accepted steps; total_steps / total_samples optional device counters
+ *   (sum of accepted steps; number of in-domain samples)
+ *   queue: optional device counter (zero-initialised by the caller) from which warps pull 32-ray
+ *   patches; it may live in a peer GPU's memory so that several GPUs share one dynamic tile queue.
+ *   patch_begin/patch_end restrict the launch to a range of patches (static sharding); pass 0, -1
+ *   for all.  image may likewise be a peer pointer (tiles are written where the gather would put them).
+ */
+int mk_render(double bhspin, double cos_i, double sin_i, double distance, double fov_lower,
+              double fov_upper, long res, const double* s0, long npx, long N, double div, double tol,
+              const mk_snapshot* snap, const mk_emission_params* params, int nfreq, const double* nu_obs,
+              double* image, int32_t* nsteps, unsigned long long* total_steps,
+              unsigned long long* total_samples, unsigned int* queue, long patch_begin, long patch_end,
+              void* stream);
+/* number of 32-ray patches mk_render splits a job into (grid camera: 4x8 pixel patches) */
+long mk_render_patch_count(long res, const double* s0, long npx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,24 @@ SIGNATURES = {
     "mk_rhs": "idplpp",
     "mk_rk4_step": "idpplpp",
     "mk_metric": "idplppp",
+    "mk_snapshot_create": "llllpppppppppipp",
+    "mk_snapshot_destroy": "p",
+    "mk_snapshot_cells": "ppp",
+    "mk_sample_scalars": "pdpldpp",
+    "mk_sample_prims": "pplpp",
+    "mk_rlow_rhigh": "ppplddddddd" "pp",
+    "mk_synchrotron": "ppppppl" "id" "ppp",
+    "mk_solve_specific_intensity": "pppll" "d" "ppp",
+    "mk_solve_attenuated_emissivity": "pppll" "d" "pp",
+    "mk_emission_from_states": "ppdpl" "d" "ppp",
+    "mk_render": "dddddd" "l" "p" "ll" "dd" "pp" "i" "p" "ppppp" "ll" "p",
+}
+
+# entry points that do not return a status code: name -> (restype, argument kinds)
+OTHER = {
+    "mk_last_error_string": (ctypes.c_char_p, ""),
+    "mk_snapshot_bytes": (ctypes.c_long, "p"),
+    "mk_render_patch_count": (ctypes.c_long, "lpl"),
 }
 
 _lib = None
@@ -44,7 +62,10 @@ def load():
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C mahakala_b200/csrc`).  mahakala_b200 has no CPU fallback.")
         lib = ctypes.CDLL(LIB_PATH)
-        lib.mk_last_error_string.restype = ctypes.c_char_p
+        for name, (res, sig) in OTHER.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = [_c[k] for k in sig]
         for name, sig in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = ctypes.c_int
@@ -60,8 +81,12 @@ def _ptr(x):
         return ctypes.c_void_p(x)
     if hasattr(x, "data_ptr"):            # torch tensor
         return ctypes.c_void_p(x.data_ptr())
-    if isinstance(x, ctypes._SimpleCData) or isinstance(x, ctypes.Array):
-        return ctypes.cast(ctypes.byref(x), ctypes.c_void_p)
+    if isinstance(x, ctypes.c_void_p):
+        return x
+    if isinstance(x, (ctypes._SimpleCData, ctypes.Array, ctypes.Structure)):
+        return ctypes.cast(ctypes.pointer(x), ctypes.c_void_p)
+    if type(x).__name__ == "CArgObject":      # ctypes.byref(...)
+        return x
     raise TypeError(f"cannot pass {type(x)} as a pointer")
 
 

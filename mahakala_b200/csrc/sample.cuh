@@ -1,0 +1,271 @@
+// GRMHD-snapshot sampling and emission physics as device functions (used by the stand-alone sampling
+// / synchrotron kernels and by the fused render kernel).
+//
+// Restates /root/reference/mahakala/
+//   grmhd/athenak.py:663-670   point -> meshblock (left-open / right-closed extents)
+//   grmhd/athenak.py:718-757   ghost-padded trilinear interpolation of the 8 primitives
+//   grmhd/athenak.py:760-794   u^m, b^m, k.u, k.b, b.b, pitch angle
+//   images.py:87-118           beta, sigma, units, local frequency, sigma cut
+//   electrons.py:46-50         R_low / R_high electron temperature
+//   transfer.py:56-86          thermal synchrotron j_nu, alpha_nu (invariant form)
+//
+// HBM layout (repacked once at snapshot creation; the reference re-uploads (nmb, 8, nk+2, nj+2, ni+2)
+// on every call, athenak.py:693):  cells[mb][k][j][i][8]  with the 8 primitives of one cell contiguous
+// (64 B as f64, 32 B as f32) in canonical order  dens, eint, U1, U2, U3, B1, B2, B3.  The two x-adjacent
+// corners of a sample are one 128 B (f64) line; a sample touches 4 such segments instead of 64 sectors.
+#pragma once
+#include "fp64_math.cuh"
+
+namespace mk {
+
+struct SnapshotView {
+    const void* cells;        // AoS cells, f64 or f32
+    int is_f32;
+    int nmb, nk, nj, ni;      // interior cells per block
+    // per-block geometry, each (nmb,): face extents, first cell centre, cell size
+    const double* lo[3];
+    const double* hi[3];
+    const double* v0[3];
+    const double* dx[3];
+    // block lookup grid over the bounding box (regular meshes); grid == nullptr -> linear scan
+    const int* grid;
+    int gn[3];
+    double g0[3], ginv[3];
+    double bbox_lo[3], bbox_hi[3];
+};
+
+__device__ __forceinline__ bool in_block(const SnapshotView& sn, int mb, const double x[4])
+{
+    return sn.lo[0][mb] < x[1] && x[1] <= sn.hi[0][mb] && sn.lo[1][mb] < x[2] && x[2] <= sn.hi[1][mb] &&
+           sn.lo[2][mb] < x[3] && x[3] <= sn.hi[2][mb];
+}
+
+// athenak.py:663-670.  Blocks tile the domain without overlap, so "last match wins" == "the match".
+__device__ __forceinline__ int locate_block(const SnapshotView& sn, const double x[4])
+{
+    // NaN-safe bounding-box rejection (comparisons with NaN are false -> outside)
+    if (!(sn.bbox_lo[0] < x[1] && x[1] <= sn.bbox_hi[0] && sn.bbox_lo[1] < x[2] && x[2] <= sn.bbox_hi[1] &&
+          sn.bbox_lo[2] < x[3] && x[3] <= sn.bbox_hi[2]))
+        return -1;
+    if (sn.grid == nullptr) {
+        int found = -1;
+        for (int mb = 0; mb < sn.nmb; mb++)
+            if (in_block(sn, mb, x)) found = mb;
+        return found;
+    }
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        int q = (int)floor((x[d + 1] - sn.g0[d]) * sn.ginv[d]);
+        c[d] = min(max(q, 0), sn.gn[d] - 1);
+    }
+    int mb = sn.grid[(c[2] * sn.gn[1] + c[1]) * sn.gn[0] + c[0]];
+    if (mb >= 0 && in_block(sn, mb, x)) return mb;
+    // a point within rounding distance of a face may land in the neighbouring grid cell: fix up with the
+    // exact extents (x <= lo -> step down, x > hi -> step up), at most one step per axis
+    int c2[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        int s = 0;
+        if (mb >= 0) s = (x[d + 1] <= sn.lo[d][mb]) ? -1 : ((x[d + 1] > sn.hi[d][mb]) ? 1 : 0);
+        c2[d] = min(max(c[d] + s, 0), sn.gn[d] - 1);
+    }
+    int mb2 = sn.grid[(c2[2] * sn.gn[1] + c2[1]) * sn.gn[0] + c2[0]];
+    if (mb2 >= 0 && in_block(sn, mb2, x)) return mb2;
+    // last resort (holes in the mesh, degenerate geometry): exhaustive neighbourhood
+    for (int dk = -1; dk <= 1; dk++)
+        for (int dj = -1; dj <= 1; dj++)
+            for (int di = -1; di <= 1; di++) {
+                int a = c[0] + di, b = c[1] + dj, e = c[2] + dk;
+                if (a < 0 || b < 0 || e < 0 || a >= sn.gn[0] || b >= sn.gn[1] || e >= sn.gn[2]) continue;
+                int m = sn.grid[(e * sn.gn[1] + b) * sn.gn[0] + a];
+                if (m >= 0 && in_block(sn, m, x)) return m;
+            }
+    return -1;
+}
+
+// athenak.py:718-733: xi = x - x_v[0] + dx ; idx = xi // dx ; delta = (xi / dx) % 1.
+__device__ __forceinline__ void cell_index(double x, double v0, double dx, int& idx, double& delta)
+{
+    double xi = x - v0 + dx;
+    double qd = xi / dx;
+    double q = floor(qd);
+    delta = qd - q;                       // python float % 1. for qd >= 0
+    double rem = fma(-q, dx, xi);         // exact floor division (np.floor_divide works from fmod)
+    if (rem < 0.0) q -= 1.0;
+    else if (rem >= dx) q += 1.0;
+    idx = (int)q;
+}
+
+__device__ __forceinline__ void load_cell_pair(const double* p, double a[8], double b[8])
+{
+    // two x-adjacent cells = 128 contiguous bytes, read as four 256-bit read-only loads
+    double4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(v[i].x), "=d"(v[i].y), "=d"(v[i].z), "=d"(v[i].w) : "l"(p + 4 * i));
+    a[0] = v[0].x; a[1] = v[0].y; a[2] = v[0].z; a[3] = v[0].w; a[4] = v[1].x; a[5] = v[1].y; a[6] = v[1].z; a[7] = v[1].w;
+    b[0] = v[2].x; b[1] = v[2].y; b[2] = v[2].z; b[3] = v[2].w; b[4] = v[3].x; b[5] = v[3].y; b[6] = v[3].z; b[7] = v[3].w;
+}
+
+__device__ __forceinline__ void load_cell_pair(const float* p, double a[8], double b[8])
+{
+    // two x-adjacent f32 cells = 64 contiguous bytes, two 256-bit read-only loads
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(v[8 * i]), "=f"(v[8 * i + 1]), "=f"(v[8 * i + 2]), "=f"(v[8 * i + 3]), "=f"(v[8 * i + 4]),
+              "=f"(v[8 * i + 5]), "=f"(v[8 * i + 6]), "=f"(v[8 * i + 7])
+            : "l"(p + 8 * i));
+#pragma unroll
+    for (int q = 0; q < 8; q++) { a[q] = (double)v[q]; b[q] = (double)v[8 + q]; }
+}
+
+// athenak.py:737-752: 8 corners x 8 primitives, lerp x1 -> x2 -> x3 in a + (b - a) t form
+template <class CellT>
+__device__ __forceinline__ void trilinear(const SnapshotView& sn, int mb, const double x[4], double prims[8])
+{
+    int i1, i2, i3;
+    double d1, d2, d3;
+    cell_index(x[1], sn.v0[0][mb], sn.dx[0][mb], i1, d1);
+    cell_index(x[2], sn.v0[1][mb], sn.dx[1][mb], i2, d2);
+    cell_index(x[3], sn.v0[2][mb], sn.dx[2][mb], i3, d3);
+    // in-block points have indices in [0, n]; clamp defensively so that no load can leave the block
+    i1 = min(max(i1, 0), sn.ni); i2 = min(max(i2, 0), sn.nj); i3 = min(max(i3, 0), sn.nk);
+    const long sj = (long)(sn.ni + 2) * 8, sk = sj * (sn.nj + 2);
+    const CellT* base = reinterpret_cast<const CellT*>(sn.cells) + (long)mb * sk * (sn.nk + 2) + i3 * sk + i2 * sj + (long)i1 * 8;
+    double aaa[8], aab[8], aba[8], abb[8], baa[8], bab[8], bba[8], bbb[8];
+    load_cell_pair(base, aaa, aab);
+    load_cell_pair(base + sj, aba, abb);
+    load_cell_pair(base + sk, baa, bab);
+    load_cell_pair(base + sk + sj, bba, bbb);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        double aa = fma(aab[q] - aaa[q], d1, aaa[q]);
+        double ab = fma(abb[q] - aba[q], d1, aba[q]);
+        double ba = fma(bab[q] - baa[q], d1, baa[q]);
+        double bb = fma(bbb[q] - bba[q], d1, bba[q]);
+        double a = fma(ab - aa, d2, aa);
+        double b = fma(bb - ba, d2, ba);
+        prims[q] = fma(b - a, d3, a);
+    }
+}
+
+// prims in canonical order dens, eint, U1..3, B1..3; returns false (and zeros) outside the domain
+__device__ __forceinline__ bool interp_prims(const SnapshotView& sn, const double x[4], double prims[8])
+{
+    int mb = locate_block(sn, x);
+    if (mb < 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) prims[q] = 0.0;
+        return false;
+    }
+    if (sn.is_f32) trilinear<float>(sn, mb, x, prims);
+    else trilinear<double>(sn, mb, x, prims);
+    return true;
+}
+
+struct FluidScalars {
+    double dens, u, cos_pitch, kdotu, b;     // cos_pitch: clamped cosine; pitch_angle = acos(cos_pitch)
+};
+
+// athenak.py:760-792 with g = eta + f l l, g^-1 = eta - f l^m l^n in closed form (Kerr-Schild family).
+__device__ __forceinline__ FluidScalars fluid_frame(double f, const double l[4], const double s[8],
+                                                    const double prims[8], double cos_fallback)
+{
+    const double* U = prims + 2;
+    const double* Bp = prims + 5;
+    double alpha = sqrt(1.0 / (1.0 + f));                       // 1/sqrt(-g^tt), g^tt = -(1 + f)
+    double lU = l[1] * U[0] + l[2] * U[1] + l[3] * U[2];
+    double gamma = sqrt(1.0 + (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + f * lU * lU);
+    double ucon[4], ucov[4], bcon[4], bcov[4];
+    ucon[0] = gamma / alpha;
+    double ga = gamma * alpha;
+#pragma unroll
+    for (int i = 1; i < 4; i++) ucon[i] = U[i - 1] - ga * (f * l[i]);      // g^{0i} = f l_i
+    double lu = l[0] * ucon[0] + l[1] * ucon[1] + l[2] * ucon[2] + l[3] * ucon[3];
+    ucov[0] = -ucon[0] + f * l[0] * lu;
+#pragma unroll
+    for (int i = 1; i < 4; i++) ucov[i] = ucon[i] + f * l[i] * lu;
+    bcon[0] = Bp[0] * ucov[1] + Bp[1] * ucov[2] + Bp[2] * ucov[3];
+#pragma unroll
+    for (int i = 1; i < 4; i++) bcon[i] = (Bp[i - 1] + ucon[i] * bcon[0]) / ucon[0];
+    double lb = l[0] * bcon[0] + l[1] * bcon[1] + l[2] * bcon[2] + l[3] * bcon[3];
+    bcov[0] = -bcon[0] + f * l[0] * lb;
+#pragma unroll
+    for (int i = 1; i < 4; i++) bcov[i] = bcon[i] + f * l[i] * lb;
+    double kdotu = 0.0, kdotb = 0.0, bdotb = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        kdotu += s[4 + i] * ucov[i];
+        kdotb += s[4 + i] * bcov[i];
+        bdotb += bcon[i] * bcov[i];
+    }
+    double b = sqrt(bdotb);
+    double c = kdotb / (fabs(kdotu) * b);
+    if (c != c) c = cos_fallback;
+    if (fabs(c) > 1.0) c = c / fabs(c);
+    FluidScalars o;
+    o.dens = prims[0]; o.u = prims[1]; o.cos_pitch = c; o.kdotu = kdotu; o.b = b;
+    return o;
+}
+
+struct EmissionParams {
+    double fluid_gamma, r_low, r_high, electron_gamma, ion_gamma;
+    double Ne_unit, B_unit, L_unit;
+    double sigma_cut;
+    // physical constants are passed from the host module (mahakala_b200/constants.py) so that there is
+    // exactly one table of digits
+    double EE, CL, ME, MP, HPL;
+    double two_11_12;           // 2^(11/12)
+};
+
+// transfer.py:56-86.  sin_pitch = sin(pitch_angle).  Returns (emissivity, absorptivity).
+__device__ __forceinline__ void synchrotron(const EmissionParams& P, double Ne, double Theta_e, double B,
+                                            double sin_pitch, double nu, int invariant, double rescale_nu,
+                                            double& em_out, double& ab_out)
+{
+    const double PI = 3.141592653589793;
+    double nuc = P.EE * B / (2. * PI * P.ME * P.CL);
+    double th2 = Theta_e * Theta_e;
+    double nus = (2. / 9.) * nuc * th2 * sin_pitch;
+    double X = nu / nus;
+    double x13 = cbrt(X);
+    double var = exp(-x13);
+    double term = sqrt(X) + P.two_11_12 * sqrt(x13);
+    double em = Ne * nus * (term * term) / (2. * th2);
+    em = em * var * 1.4142135623730951 * PI * (P.EE * P.EE) / (3.0 * P.CL);
+    if (X > 1.e12) em = 0.0;
+    if (Theta_e < 0.3) em = 0.0;
+    double bx = P.HPL * nu / (P.ME * P.CL * P.CL * Theta_e);
+    double den = (bx < 2.e-3) ? bx / 24. * (24. + bx * (12. + bx * (4. + bx))) : exp(bx) - 1.0;
+    double B_nu = (2. * P.HPL * (nu * nu * nu) / den) / (P.CL * P.CL);
+    double ab = em / B_nu;
+    if (invariant) {
+        double rn = nu * rescale_nu;
+        em = em / (rn * rn);
+        ab = ab * rn;
+    }
+    em_out = (em != em) ? 0.0 : em;
+    ab_out = (ab != ab) ? 0.0 : ab;
+}
+
+// images.py:87-102 + electrons.py:46-50: everything between the fluid scalars and (Ne, Theta_e, B)
+__device__ __forceinline__ void plasma_state(const EmissionParams& P, const FluidScalars& fs, double& Ne,
+                                             double& Theta_e, double& Bg, double& sigma)
+{
+    double bsq = fs.b * fs.b;
+    double beta = fs.u * (P.fluid_gamma - 1.) / bsq / 0.5;
+    sigma = bsq / fs.dens;
+    double b2 = beta * beta;
+    double T_ratio = (P.r_high * b2 + P.r_low) / (1. + b2);
+    double t_e = (P.CL * P.CL) * (P.MP * fs.u * (P.electron_gamma - 1.) * (P.ion_gamma - 1.));
+    t_e /= fs.dens * ((P.ion_gamma - 1.) + (P.electron_gamma - 1.) * T_ratio);
+    Theta_e = t_e / (P.ME * P.CL * P.CL);
+    Ne = P.Ne_unit * fs.dens;
+    Bg = P.B_unit * fs.b;
+}
+
+}  // namespace mk

@@ -1,0 +1,130 @@
+"""Drop-in for ``mahakala.images`` (reference: /root/reference/mahakala/images.py:30-144).
+
+``make_image`` keeps the reference signature.  With an ``AthenakFluidModel`` it runs the FUSED kernel
+(camera -> RK4 geodesic -> snapshot sample -> j, alpha -> intensity in registers, no trajectories in
+memory, no pixel chunking).  ``make_image_unfused`` executes the reference's stage-by-stage chain on the
+device (integrate/dump -> sample -> Theta_e -> j, alpha -> sigma cut -> back-to-front transfer) and is
+what any other fluid-model duck type goes through.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import geodesics as geo
+from .constants import Msun
+from .electrons import rlow_rhigh_model
+from .transfer import emission_params, solve_specific_intensity, synchrotron_coefficients
+from ._device import DeviceArray, as_device, empty, require_gpu, stream_ptr
+
+
+def _params_for(fluid_model, M_bh, mass_scale, r_high):
+    units = fluid_model.get_units(M_bh, mass_scale)
+    return emission_params(fluid_gamma=fluid_model.fluid_gamma, r_high=r_high, Ne_unit=units['Ne_unit'],
+                           B_unit=units['B_unit'], L_unit=units['L_unit']), units
+
+
+def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26, M_bh=6.2e9 * Msun,
+           r_high=40, observing_frequencies=(230.e9,), fov=20, resolution=160, max_nsteps=10000, s0=None,
+           div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1), want_counters=False):
+    """Fused multi-frequency render.  Returns ``image (nfreq, npx)`` on the device (plus counters).
+
+    ``s0`` (npx, 8) replaces the grid camera by explicit rays.  ``image_out`` / ``queue`` may be tensors
+    or raw device pointers (possibly in a peer GPU's memory) — see ``mahakala_b200.multigpu``.
+    """
+    dev = require_gpu()
+    snap = fluid_model.snapshot()
+    P, units = _params_for(fluid_model, M_bh, mass_scale, r_high)
+    nus = np.atleast_1d(np.asarray(observing_frequencies, dtype=np.float64))
+    nfreq = nus.size
+    if not 1 <= nfreq <= 8:
+        raise ValueError("1..8 observing frequencies per launch")
+    c_nu = (ctypes.c_double * 8)(*(list(nus) + [nus[-1]] * (8 - nfreq)))
+    if s0 is not None:
+        s0d = as_device(s0)
+        npx = s0d.shape[0]
+        res = 0
+    else:
+        s0d = None
+        res = int(resolution)
+        npx = res * res
+    img = image_out if image_out is not None else empty((nfreq, npx))
+    nsteps = None
+    counters = torch.zeros(2, dtype=torch.int64, device=dev) if want_counters else None
+    i = camera_inclination * np.pi / 180
+    _cabi.call("mk_render", float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
+               -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
+               img, nsteps, counters[0:1] if want_counters else None, counters[1:2] if want_counters else None,
+               queue, int(patch_range[0]), int(patch_range[1]), stream_ptr())
+    if want_counters:
+        return img, counters
+    return img
+
+
+def make_image(fluid_model, camera_inclination=60, camera_distance=1000,
+               mass_scale=1.e26, M_bh=6.2e9 * Msun, r_high=40,
+               observing_frequency=230.e9,
+               fov=20, resolution=160,
+               max_nsteps=10000,
+               max_chunk_bytes=None):
+    """images.py:30-144.  Returns a (resolution, resolution) NumPy array of specific intensities in cgs.
+
+    ``max_chunk_bytes`` is accepted for signature compatibility; the fused kernel stores no trajectories,
+    so there is nothing to chunk (the unfused fallback for foreign fluid models does honour it).
+    """
+    if hasattr(fluid_model, "snapshot"):
+        img = render(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
+                     (observing_frequency,), fov, resolution, max_nsteps)
+        host = torch.empty((resolution * resolution,), dtype=torch.float64, pin_memory=True)
+        host.copy_(img[0], non_blocking=False)
+        return host.numpy().reshape((resolution, resolution))
+    return make_image_unfused(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
+                              observing_frequency, fov, resolution, max_nsteps, max_chunk_bytes)
+
+
+def intensity_from_trajectories(fluid_model, S, final_dt, mass_scale, M_bh, r_high, observing_frequency):
+    """images.py:84-120 for one chunk, stage by stage on the device (reference order of operations)."""
+    fluid_gamma = fluid_model.fluid_gamma
+    fs = fluid_model.get_fluid_scalars_from_geodesics(S)
+    dens, u, b = (as_device(fs[k]) for k in ('dens', 'u', 'b'))
+    bsq = b * b
+    beta = u * (fluid_gamma - 1.) / bsq / 0.5
+    sigma = bsq / dens
+    Theta_e = rlow_rhigh_model(dens, u, beta, r_high=r_high)
+    units = fluid_model.get_units(M_bh, mass_scale)
+    Ne_in_cgs = units['Ne_unit'] * dens
+    B_in_gauss = units['B_unit'] * b
+    local_nu = - as_device(fs['kdotu']) * observing_frequency
+    em, ab = synchrotron_coefficients(Ne_in_cgs, Theta_e, B_in_gauss, fs['pitch_angle'], local_nu,
+                                      invariant=True, rescale_nu=1. / observing_frequency)
+    cut = sigma > 100.
+    em = torch.where(cut, torch.zeros_like(em), em)
+    ab = torch.where(cut, torch.zeros_like(ab), ab)
+    return solve_specific_intensity(em, ab, final_dt, units['L_unit'])
+
+
+def make_image_unfused(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26,
+                       M_bh=6.2e9 * Msun, r_high=40, observing_frequency=230.e9, fov=20, resolution=160,
+                       max_nsteps=10000, max_chunk_bytes=None):
+    """The reference's chunked stage-by-stage pipeline (images.py:56-144) with every stage on the GPU."""
+    bhspin = fluid_model.bhspin
+    s0 = geo.initialize_geodesics_at_camera(bhspin, camera_inclination, camera_distance, -fov / 2., fov / 2.,
+                                            resolution)
+    npx = s0.shape[0]
+    num_pixels_per_chunk = npx + 10
+    if max_chunk_bytes is not None:
+        num_pixels_per_chunk = int(max_chunk_bytes // 4 // 20 // max_nsteps)     # images.py:69
+    else:
+        free, _ = torch.cuda.mem_get_info()
+        # a trajectory row costs 72 B/ray plus ~10 stage arrays of 8 B; keep a chunk under ~40% of free HBM
+        num_pixels_per_chunk = max(1024, min(npx + 10, int(0.4 * free / (160 * 2500))))
+    out = np.zeros((0))
+    lower = 0
+    while lower < npx:
+        S, final_dt = geo.geodesic_integrator(max_nsteps, s0[lower:lower + num_pixels_per_chunk], 40, 1e-4, bhspin)
+        I_nu = intensity_from_trajectories(fluid_model, S, final_dt, mass_scale, M_bh, r_high, observing_frequency)
+        out = np.append(out, np.asarray(I_nu))
+        del S, final_dt, I_nu
+        lower += num_pixels_per_chunk
+    return np.array(out).reshape((resolution, resolution))

@@ -1,0 +1,176 @@
+"""GPU parity of sampling, thermodynamics, synchrotron, transfer and the fused render against the oracle."""
+import numpy as np
+import pytest
+
+from helpers import M_BH, MASS_SCALE, device_model, oracle_model, snapshot_arrays
+
+pytestmark = pytest.mark.gpu
+A = 0.94
+
+
+@pytest.fixture(scope="module")
+def setup(built):
+    from oracle import c_oracle, mahakala_oracle as onp
+    arr = snapshot_arrays(ncells=32, block=16, extent=16.0)
+    om = oracle_model(arr, A)
+    dm = device_model(arr, A)
+    s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 10)
+    S, dt = c_oracle.geodesic_integrator(10000, s0, 40, 1e-4, A)
+    return dict(arr=arr, om=om, dm=dm, s0=s0, S=S, dt=dt)
+
+
+def test_ghost_fill_matches_oracle(setup):
+    assert np.array_equal(setup["dm"].all_meshblocks, setup["om"].all_meshblocks)
+
+
+def test_sample_prims_and_scalars(setup):
+    from oracle import c_oracle
+    om, dm, S = setup["om"], setup["dm"], setup["S"]
+    ref_p = c_oracle.sample(om, S, mode="prims")
+    ref_s = c_oracle.sample(om, S, mode="scalars")
+    got_p = dm.get_prims_from_geodesics(S)
+    got_s = dm.get_fluid_scalars_from_geodesics(S)
+    indom = ref_p["dens"] != 0
+    assert indom.sum() > 1000 and (~indom).sum() > 1000
+    for k in ref_p:
+        g = np.asarray(got_p[k])
+        assert g.shape == S.shape[:2]
+        assert np.array_equal(g == 0, ref_p[k] == 0), k
+        scale = np.abs(ref_p[k]).max()
+        assert np.abs(g - ref_p[k]).max() <= 1e-14 * scale, k
+    for k in ("dens", "u", "kdotu", "b"):
+        g = np.asarray(got_s[k])
+        assert np.abs(g - ref_s[k]).max() <= 1e-11 * np.abs(ref_s[k]).max(), k
+    # pitch angle: acos amplifies rounding near 0 and pi; compare cosines
+    assert np.abs(np.cos(np.asarray(got_s["pitch_angle"])) - np.cos(ref_s["pitch_angle"])).max() < 1e-9
+    # the NumPy oracle agrees with the C oracle on a thin slice (pins the C sampling code)
+    sl = S[40:60]
+    np_s = om.get_fluid_scalars_from_geodesics(sl)
+    for k in ("dens", "u", "kdotu", "b"):
+        assert np.allclose(np_s[k], ref_s[k][40:60], rtol=1e-10, atol=1e-14 * np.abs(ref_s[k]).max()), k
+
+
+def test_lookup_and_storage_variants_identical(setup):
+    arr, S = setup["arr"], setup["S"][::7]
+    base = {k: np.asarray(v) for k, v in setup["dm"].get_prims_from_geodesics(S).items()}
+    assert setup["dm"].storage == "f32" and setup["dm"].lookup == "grid"      # synthetic data are f32-exact
+    for kw in (dict(storage="f64"), dict(lookup="scan"), dict(storage="f64", lookup="scan")):
+        m = device_model(arr, A, **kw)
+        got = m.get_prims_from_geodesics(S)
+        for k in base:
+            assert np.array_equal(np.asarray(got[k]), base[k]), (kw, k)
+        m.release()
+
+
+def test_points_on_faces_outside_and_nan(setup):
+    from oracle import c_oracle
+    om, dm = setup["om"], setup["dm"]
+    f = om.x1f[0]
+    pts = []
+    for x in (f[0], f[1], f[-1], -16.0, 16.0, 0.0, 15.999999999999998, 16.000000000000004, -15.75, 1e300, np.nan):
+        for y in (0.0, -16.0, 16.0, 2.0):
+            pts.append([0.0, x, y, 0.5, 1.0, 0.3, -0.2, 0.1])
+    S = np.array(pts)[None]
+    ref = c_oracle.sample(om, S, mode="prims")
+    got = dm.get_prims_from_geodesics(S)
+    for k in ref:
+        assert np.allclose(np.asarray(got[k]), ref[k], rtol=1e-14, atol=0), k
+
+
+def test_thermo_synchrotron_transfer_elementwise(built):
+    import mahakala_b200 as ma
+    from mahakala_b200.electrons import rlow_rhigh_model
+    from mahakala_b200 import transfer
+    from oracle import mahakala_oracle as onp
+    rng = np.random.default_rng(5)
+    n = 4000
+    dens = np.exp(rng.normal(0, 2, n)); u = dens * np.exp(rng.normal(-1, 1, n)); beta = np.exp(rng.normal(0, 2, n))
+    dens[:5] = 0; beta[5:9] = np.inf; u[9] = np.nan
+    th = np.asarray(rlow_rhigh_model(dens, u, beta, r_high=40))
+    th_ref = onp.rlow_rhigh_model(dens, u, beta, r_high=40)
+    assert np.allclose(th, th_ref, rtol=1e-14, equal_nan=True)
+    Ne = np.exp(rng.normal(10, 2, n)); Th = np.exp(rng.normal(1, 1.5, n)); B = np.exp(rng.normal(1, 1, n))
+    pitch = rng.uniform(0, np.pi, n); nu = 230e9 * np.exp(rng.normal(0, 0.5, n))
+    Th[:20] = 0.1; B[20:25] = 0; Ne[25:28] = np.nan; nu[28:40] *= 1e-7; pitch[40:44] = 0.0
+    for inv, resc in ((True, 1 / 230e9), (True, 1.0), (False, 1.0)):
+        em, ab = transfer.synchrotron_coefficients(Ne, Th, B, pitch, nu, invariant=inv, rescale_nu=resc)
+        em_r, ab_r = onp.synchrotron_coefficients(Ne, Th, B, pitch, nu, invariant=inv, rescale_nu=resc)
+        assert np.array_equal(np.asarray(em) == 0, em_r == 0)
+        assert np.allclose(np.asarray(em), em_r, rtol=1e-12, atol=0)
+        assert np.allclose(np.asarray(ab), ab_r, rtol=1e-12, atol=0)
+    # scalar broadcasting as in the reference's elementwise arithmetic
+    em, ab = ma.synchrotron_coefficients(Ne, 10.0, B, np.pi / 3, 230e9)
+    em_r, ab_r = onp.synchrotron_coefficients(Ne, 10.0, B, np.pi / 3, 230e9)
+    assert np.allclose(np.asarray(em), em_r, rtol=1e-12) and np.allclose(np.asarray(ab), ab_r, rtol=1e-12)
+    # transfer scans
+    nrows, npx = 57, 33
+    emm = np.exp(rng.normal(-3, 1, (nrows, npx))); abb = np.exp(rng.normal(-2, 1, (nrows, npx)))
+    dt = -np.abs(rng.normal(0.3, 0.1, (nrows, npx))); dt[40:, ::3] = 0
+    I = np.asarray(ma.solve_specific_intensity(emm, abb, dt, 2.5))
+    I_r = onp.solve_specific_intensity(emm, abb, dt, 2.5)
+    assert np.array_equal(I, I_r)                       # same operation order -> bit-exact
+    I2, dI = ma.solve_specific_intensity(emm, abb, dt, 2.5, dIs=True)
+    I2_r, dI_r = onp.solve_specific_intensity(emm, abb, dt, 2.5, dIs=True)
+    assert np.array_equal(np.asarray(dI), dI_r) and np.array_equal(np.asarray(I2), I2_r)
+    att = np.asarray(ma.solve_attenuated_emissivity(emm, abb, dt, 2.5))
+    att_r = onp.solve_attenuated_emissivity(emm, abb, dt, 2.5)
+    assert att.shape == att_r.shape == (nrows - 1, npx)
+    assert np.allclose(att, att_r, rtol=1e-13, atol=0)
+    # degenerate shapes
+    assert np.asarray(ma.solve_specific_intensity(emm[:1], abb[:1], dt[:1], 1.0)).tolist() == [0.0] * npx
+
+
+def _image_errors(img, ref):
+    scale = np.abs(ref).max()
+    per_px = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * scale)
+    flux = abs(img.sum() - ref.sum()) / abs(ref.sum())
+    return per_px.max(), flux
+
+
+def test_fused_and_unfused_images_match_oracle(setup):
+    """north_star tolerances: per-pixel intensity 1e-6 relative, total flux 1e-8."""
+    from mahakala_b200 import images
+    from oracle import c_oracle, mahakala_oracle as onp
+    om, dm = setup["om"], setup["dm"]
+    res = 24
+    s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, res)
+    units = om.get_units(M_BH, MASS_SCALE)
+    ref, nsteps, nin = c_oracle.render(om, s0, units, [230e9], r_high=40)
+    ref = ref[0].reshape(res, res)
+    assert ref.max() > 0 and nin > 0
+    img = images.make_image(dm, resolution=res)
+    assert img.shape == (res, res) and isinstance(img, np.ndarray)
+    e_px, e_flux = _image_errors(img, ref)
+    assert e_px < 1e-6 and e_flux < 1e-8, (e_px, e_flux)
+    img_u = images.make_image_unfused(dm, resolution=res)
+    e_px, e_flux = _image_errors(img_u, ref)
+    assert e_px < 1e-6 and e_flux < 1e-8, (e_px, e_flux)
+    # NumPy oracle end to end on a coarser image (pins the C render chain)
+    s0c = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 8)
+    ref_np = onp.make_image(om, resolution=8, integrator=c_oracle.geodesic_integrator)
+    ref_c, _, _ = c_oracle.render(om, s0c, units, [230e9])
+    assert np.allclose(ref_c[0].reshape(8, 8), ref_np, rtol=1e-9, atol=1e-12 * ref_np.max())
+
+
+def test_fused_multifrequency_and_explicit_rays(setup):
+    from mahakala_b200 import images
+    from oracle import c_oracle, mahakala_oracle as onp
+    om, dm = setup["om"], setup["dm"]
+    res = 12
+    nus = [43e9, 86e9, 230e9, 345e9, 690e9]
+    s0 = onp.initialize_geodesics_at_camera(A, 30, 1000, -9, 9, res)
+    units = om.get_units(M_BH, MASS_SCALE)
+    ref, nsteps, nin = c_oracle.render(om, s0, units, nus)
+    img, counters = images.render(dm, camera_inclination=30, fov=18, resolution=res, observing_frequencies=nus,
+                                  want_counters=True)
+    img = np.asarray(img.cpu())
+    assert img.shape == (5, res * res)
+    for f in range(5):
+        e_px, e_flux = _image_errors(img[f], ref[f])
+        assert e_px < 1e-6 and e_flux < 1e-8, (f, e_px, e_flux)
+    assert int(counters[1]) == nin
+    assert abs(int(counters[0]) - int(nsteps.sum())) <= 4 * res * res
+    # explicit rays (ragged count, not a multiple of 32)
+    sub = s0[5:5 + 77]
+    img2 = np.asarray(images.render(dm, s0=sub, observing_frequencies=[230e9]).cpu())
+    assert np.allclose(img2[0], ref[2][5:5 + 77], rtol=1e-6, atol=1e-9 * ref[2].max())
