@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray hot path (BASELINE.json metric: ray-steps/s in FP64 + 1024^2 230 GHz render time).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: the cfg2 bundle of BASELINE.json
+(1024x1024 Kerr-Schild rays, a = 0.94, observer r = 1000 M, i = 60 deg, div = 40, tol = 1e-4, N = 10000),
+integrated by the persistent FP64 kernel with trajectory dump.  Prints ONE JSON line (rank 0).
+
+  value      whole-job ray-steps/s with the bundle resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through the public API with HOST buffers: pinned s0 -> H2D -> integrate -> D2H of
+             final states / step counts / classifier radii (trajectories stay in HBM, as the reference's
+             jax.Arrays stay on its device)
+  render     the second half of the metric: wall time of the fused 1024^2 230 GHz image of the synthetic
+             256^3 AthenaK-shaped snapshot (cfg4), device-timed and end-to-end
+  roofline   dominant kernel = integrate_kernel; FP64 pipe: 859 algorithmic flop per ray-step
+              over the measured DFMA peak of this GPU (mk_measure_fp64_peak)
+  cpu_baseline  the C/OpenMP oracle (literal restatement of the reference's JAX path, oracle/mk_oracle.c)
+             timed on this box's host cores on a bounded sample; kind = "port" (JAX is not installable)
+
+--impl reference times that oracle port as the "reference arm" (the reference itself is pure Python on
+JAX, which is absent from this image and the GPU box).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FLOP_PER_RAY_STEP = 859          # 312 add + 523 mul + 12 div + 12 sqrt
+CFG2 = dict(bhspin=0.94, inclination=60.0, distance=1000.0, fov=20.0, div=40.0, tol=1e-4, N=10000)
+WEAK_INCLINATIONS = [60.0, 17.0, 30.0, 80.0, 45.0, 70.0, 25.0, 52.0]    # one frame per rank (cfg5-style)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--res", type=int, default=1024, help="rays per side of the bundle (default: cfg2)")
+    ap.add_argument("--snapshot-cells", type=int, default=256, help="cells per side of the cfg4 snapshot")
+    ap.add_argument("--no-render", action="store_true", help="skip the cfg4 render leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=341, help="side of the pixel sub-lattice timed on the CPU")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], [], set()
+        allsm = []
+        for t, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            allsm.append(clk)
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                smmax.append(mx)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            sm = allsm[-3:] if allsm else [0.0]
+            smmax = smmax or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smmax)) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port)
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample_rays(res, side, inclination=CFG2["inclination"]):
+    """A side x side sub-lattice of the res x res cfg2 pixel grid (same camera, same rays)."""
+    from oracle import mahakala_oracle as onp
+    s0 = onp.initialize_geodesics_at_camera(CFG2["bhspin"], inclination, CFG2["distance"], -CFG2["fov"] / 2,
+                                            CFG2["fov"] / 2, res)
+    stride = max(res // side, 1)
+    idx = (np.arange(0, res, stride)[:, None] * res + np.arange(0, res, stride)[None, :]).reshape(-1)
+    return np.ascontiguousarray(s0[idx]), stride
+
+
+def time_cpu_oracle(res, side):
+    from oracle import c_oracle
+    s0, stride = cpu_sample_rays(res, side)
+    c_oracle.integrate(200, s0[:64], CFG2["div"], CFG2["tol"], CFG2["bhspin"])       # load + thread warm-up
+    t0 = time.perf_counter()
+    out = c_oracle.integrate(CFG2["N"], s0, CFG2["div"], CFG2["tol"], CFG2["bhspin"], dump=False)
+    dt = time.perf_counter() - t0
+    steps = int(out["nsteps"].sum())
+    return steps / dt, dict(seconds=dt, ray_steps=steps, rays=int(s0.shape[0]), cores=c_oracle.num_threads(),
+                            sample=f"every {stride}th pixel of the {res}x{res} cfg2 grid ({s0.shape[0]} rays, "
+                                   f"{steps} ray-steps, {dt:.1f} s)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    side = 64
+    s0, stride = cpu_sample_rays(args.res, side)
+    times, steps = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        out = c_oracle.integrate(CFG2["N"], s0, CFG2["div"], CFG2["tol"], CFG2["bhspin"], dump=False)
+        t1 = time.perf_counter()
+        if it >= args.warmup:
+            times.append(t1 - t0)
+            steps = int(out["nsteps"].sum())
+    total = float(np.sum(times))
+    # useful (accepted) ray-steps only, early exit per ray and no trajectory stores: this FAVOURS the CPU arm
+    # (the reference's lax.scan runs all N = 10000 iterations for every ray and materialises them)
+    value = steps * args.steps / total
+    cores = c_oracle.num_threads()
+    sample = (f"every {stride}th pixel of the {args.res}x{args.res} cfg2 grid per step ({s0.shape[0]} rays, {steps} "
+              f"ray-steps, final-state mode, early exit); C/OpenMP restatement of the reference's JAX path "
+              f"(jacfwd-style forward derivatives + 4x4 inverse), not JAX itself")
+    line = {"impl": "reference", "metric": "ray_steps_per_sec_fp64", "value": value, "unit": "ray-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, mode="reference-cpu"),
+            "cpu_baseline": {"value": value, "unit": "ray-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "ray-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, mode):
+    return {"workload": f"cfg2: Kerr-Schild geodesic bundle {args.res}x{args.res} rays, a=0.94, observer r=1000 M, "
+                        f"i=60 deg, fov 20 M, div=40, tol=1e-4, N=10000",
+            "mode": mode, "rays": args.res * args.res,
+            "l2_policy": "256 MiB scratch write between timed iterations (L2 flush); the dump itself is >> L2",
+            "multi_gpu": "one full frame per rank at its own inclination (weak scaling, no data-path collective)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import mahakala_b200 as ma
+    from mahakala_b200 import _cabi, geodesics as geo
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    a = CFG2["bhspin"]
+    incl = WEAK_INCLINATIONS[rank % len(WEAK_INCLINATIONS)]
+    res = args.res
+    s0 = ma.initialize_geodesics_at_camera(a, incl, CFG2["distance"], -CFG2["fov"] / 2, CFG2["fov"] / 2, res)
+    npx = s0.shape[0]
+    s0_host = torch.empty((npx, 8), dtype=torch.float64, pin_memory=True)
+    s0_host.copy_(s0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # measured FP64 peak of this GPU (roofline denominator)
+    tf = ctypes.c_double(0)
+    ms = ctypes.c_double(0)
+    _cabi.call("mk_measure_fp64_peak", 20000, tf, ms)
+    fp64_peak = tf.value
+
+    store = geo.TrajectoryStore.allocate(npx, CFG2["N"]) if hasattr(geo, "TrajectoryStore") else None
+    mode = "trajectory dump (paged, single pass)" if store is not None else "final state + classifier radius (no dump)"
+    launches = [0]
+
+    def step_device():
+        if store is not None:
+            store.reset()
+            out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)
+            launches[0] += 1
+            return out.total_steps
+        final, nsteps, r_last, total = geo.integrate_final(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, want_total=True)
+        launches[0] += 1
+        return total
+
+    host_out = {"final": torch.empty((npx, 8), dtype=torch.float64, pin_memory=True),
+                "nsteps": torch.empty((npx,), dtype=torch.int32, pin_memory=True),
+                "r_last": torch.empty((npx,), dtype=torch.float64, pin_memory=True)}
+
+    def step_e2e():
+        d = s0_host.to(dev, non_blocking=True)
+        if store is not None:
+            store.reset()
+            out = geo.integrate_paged(CFG2["N"], d, CFG2["div"], CFG2["tol"], a, store=store)
+            final, nsteps, r_last = out.final, out.nsteps, out.r_last
+        else:
+            final, nsteps, r_last = geo.integrate_final(CFG2["N"], d, CFG2["div"], CFG2["tol"], a)
+        host_out["final"].copy_(final, non_blocking=True)
+        host_out["nsteps"].copy_(nsteps, non_blocking=True)
+        host_out["r_last"].copy_(r_last, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int(host_out["nsteps"].sum())
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        total = step_device()
+        flush.fill_(1)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+
+    # ---- timed: device-resident ----
+    launches[0] = 0
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    totals = []
+    for k in range(args.steps):
+        flush.fill_(k)                      # L2 flush, outside the event pair
+        ev[k][0].record()
+        totals.append(step_device())
+        ev[k][1].record()
+    barrier()
+    t_wall1 = time.time()
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    steps_per_pass = int(totals[-1].item())
+    n_launch = launches[0]
+
+    # ---- timed: end to end through the public API with host buffers ----
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_steps = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # ---- reduce over ranks: time = max, work = sum ----
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    w = torch.tensor([steps_per_pass, e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    work, e2e_work = float(w[0]), float(w[1])
+    value = work * args.steps / (dev_ms_max * 1e-3)
+    e2e_value = e2e_work * args.steps / e2e_s_max
+
+    render = None
+    if not args.no_render:
+        render = render_leg(args, rank, world, dev)
+
+    if rank == 0:
+        kernel_ms = dev_ms / args.steps
+        achieved = steps_per_pass * FLOP_PER_RAY_STEP / (kernel_ms * 1e-3) / 1e12
+        dump_bytes = 72 * (steps_per_pass + npx) if store is not None else 0
+        line = {
+            "metric": "ray_steps_per_sec_fp64", "value": value, "unit": "ray-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, mode),
+            "ray_steps_per_pass_rank0": steps_per_pass,
+            "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": int(npx * 64),
+                    "d2h_bytes_per_step": int(npx * (64 + 4 + 8)), "ms_per_step": 1e3 * e2e_s_max / args.steps},
+            "gpu_launches": n_launch,
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "kernel": "mk::integrate_kernel<KerrSchild>", "achieved": achieved,
+                         "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "peak_source": "measured on this GPU by mk_measure_fp64_peak (DFMA microbenchmark); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flop_per_ray_step": FLOP_PER_RAY_STEP, "traffic": None,
+                         "hbm": {"dump_bytes_per_launch": dump_bytes,
+                                 "achieved_GBps": dump_bytes / (kernel_ms * 1e-3) / 1e9,
+                                 "peak_GBps": hbm_peak()}},
+        }
+        if render is not None:
+            line["render"] = render
+        if not args.no_cpu_baseline:
+            v, info = time_cpu_oracle(args.res, args.cpu_sample)
+            line["cpu_baseline"] = {"value": v, "unit": "ray-steps/s", "cores": info["cores"], "kind": "port",
+                                    "sample": info["sample"] + "; C/OpenMP restatement of the reference's JAX path"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0       # B200_PROFILING.md fallback
+
+
+def render_leg(args, rank, world, dev):
+    """cfg4: fused 1024^2 230 GHz image of the synthetic 256^3 snapshot (one frame per rank when N > 1)."""
+    import torch
+    import torch.distributed as dist
+    from mahakala_b200 import images
+    from mahakala_b200.grmhd import AthenakFluidModel
+    from mahakala_b200.synthetic import make_synthetic_snapshot
+
+    nc = args.snapshot_cells
+    arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
+    model = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
+                                          arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"], CFG2["bhspin"],
+                                          fluid_gamma=arr["fluid_gamma"])
+    model.snapshot()
+    del arr
+    incl = WEAK_INCLINATIONS[rank % len(WEAK_INCLINATIONS)]
+    res = args.res
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    times, e2e_times = [], []
+    counters = None
+    for it in range(2 + 3):
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        img, counters = images.render(model, camera_inclination=incl, resolution=res, observing_frequencies=(230e9,),
+                                      want_counters=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            times.append(e0.elapsed_time(e1))
+    for it in range(3):
+        t0 = time.perf_counter()
+        host_img = images.make_image(model, camera_inclination=incl, resolution=res)
+        e2e_times.append(1e3 * (time.perf_counter() - t0))
+    t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    steps, samples = int(counters[0]), int(counters[1])
+    ms = float(t[0])
+    return {"workload": f"cfg4: synthetic AthenaK-shaped {nc}^3 snapshot ({model.storage} cells, {model.lookup} lookup), "
+                        f"{res}x{res} image at 230 GHz, fused kernel; one frame per rank",
+            "ms": ms, "e2e_ms": float(t[1]), "ray_steps": steps, "in_domain_samples": samples,
+            "ray_steps_per_s": steps / (ms * 1e-3),
+            "sampling_algorithmic_GBps": samples * (256 if model.storage == "f32" else 512) / (ms * 1e-3) / 1e9,
+            "snapshot_bytes": model.snapshot_bytes(), "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
