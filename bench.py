@@ -296,13 +296,16 @@ def run_b200(args):
     e2e_value = e2e_work * args.steps / e2e_s_max
 
     render = None
+    pages_used = store.pages_used if store is not None else 0
+    store = None
+    torch.cuda.empty_cache()
     if not args.no_render:
         render = render_leg(args, rank, world, dev)
 
     if rank == 0:
         kernel_ms = dev_ms / args.steps
         achieved = steps_per_pass * FLOP_PER_RAY_STEP / (kernel_ms * 1e-3) / 1e12
-        dump_bytes = 72 * (steps_per_pass + npx) if store is not None else 0
+        dump_bytes = 72 * (steps_per_pass + npx) if pages_used else 0
         line = {
             "metric": "ray_steps_per_sec_fp64", "value": value, "unit": "ray-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,

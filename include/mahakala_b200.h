@@ -69,6 +69,24 @@ int mk_integrate(int metric_id, double bhspin, long N, long npx, const double* s
                  unsigned long long* total_steps, void* stream);
 int mk_fill_frozen_rows(double* S, double* dt, const double* final_state, const int32_t* nsteps, long npx,
                         long nrows, void* stream);
+/*
+ * Single-pass trajectory dump into a paged (ragged) store: no row count has to be known in advance and no
+ * padding is written.  Page p occupies 288 doubles at pages + 288*p: 32 rows of 8 state doubles followed by
+ * the 32 step sizes (mk_page_rows() == 32).  page_first (npx,) holds each ray's first page, page_next
+ * (max_pages,) links a ray's pages (-1 terminates).  A ray stores rows 0..n (row n = frozen state, dt = 0;
+ * N rows when it never froze).  page_counter (one u32, zeroed by the caller) counts pages handed out (in
+ * slabs of 64 per warp); *overflow becomes 1 if more than max_pages were needed (results other than the
+ * trajectories stay valid).  mk_paged_gather materialises the reference layout S (nrows, nsel, 8),
+ * dt (nrows, nsel) for the rays ray_idx[0..nsel) (NULL = rays 0..nsel-1).
+ */
+int mk_page_rows(void);
+int mk_integrate_paged(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
+                       double tol, double* final_state, int32_t* nsteps, double* r_last, double* pages,
+                       int32_t* page_next, int32_t* page_first, unsigned int* page_counter, long max_pages,
+                       int32_t* overflow, unsigned long long* total_steps, void* stream);
+int mk_paged_gather(const double* pages, const int32_t* page_next, const int32_t* page_first,
+                    const int32_t* nsteps, const long* ray_idx, long nsel, long nrows, long N, double* S,
+                    double* dt, void* stream);
 /* geodesics.py:284-291 radius_cal for n points of stride `stride` doubles (x at offsets 1..3) */
 int mk_radius_cal(double bhspin, const double* x, long n, long stride, double* r, void* stream);
 /* geodesics.py:294-314 rhs on a bundle: state (n, 8) -> (n, 8); metric_id selects the plugin */

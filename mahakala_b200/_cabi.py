@@ -22,6 +22,8 @@ SIGNATURES = {
     "mk_initial_condition": "dpplpp",
     "mk_integrate": "idllpddpppppl" "pp",
     "mk_fill_frozen_rows": "ppppllp",
+    "mk_integrate_paged": "idllpdd" "ppp" "pppp" "l" "pp" "p",
+    "mk_paged_gather": "ppppp" "lll" "ppp",
     "mk_radius_cal": "dpllpp",
     "mk_rhs": "idplpp",
     "mk_rk4_step": "idpplpp",
@@ -43,6 +45,7 @@ SIGNATURES = {
 OTHER = {
     "mk_last_error_string": (ctypes.c_char_p, ""),
     "mk_snapshot_bytes": (ctypes.c_long, "p"),
+    "mk_page_rows": (ctypes.c_int, ""),
     "mk_render_patch_count": (ctypes.c_long, "lpl"),
 }
 

@@ -26,11 +26,26 @@ struct IntegrateArgs {
     long nrows;
     unsigned int* queue;   // zero-initialised ray counter
     unsigned long long* total_steps;  // optional global sum of accepted steps
+    // paged dump (single pass, ragged): page p = [PAGE_ROWS][8] states followed by [PAGE_ROWS] dts
+    double* pages;
+    int* page_next;        // (max_pages,) next page of the same ray or -1
+    int* page_first;       // (npx,) first page of each ray
+    unsigned int* page_counter;
+    unsigned int max_pages;
+    int* overflow;         // set to 1 when the page pool is exhausted
 };
 
-template <class Metric, bool DUMP>
+constexpr int PAGE_ROWS = 32;
+constexpr int PAGE_DOUBLES = PAGE_ROWS * 9;
+constexpr unsigned PAGE_SLAB = 64;       // pages a warp takes from the global pool per atomic
+enum { MODE_FINAL = 0, MODE_PADDED = 1, MODE_PAGED = 2 };
+
+template <class Metric, int MODE>
 __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const IntegrateArgs A)
 {
+    constexpr bool DUMP = (MODE == MODE_PADDED);
+    unsigned slab_next = 0, slab_end = 0;      // warp-uniform page slab (MODE_PAGED)
+    int page = -1;
     const unsigned lane = threadIdx.x & 31u;
     long ray = -1;
     bool drained = false;           // queue exhausted (warp-uniform)
@@ -63,12 +78,43 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
                         dt = A.rule(r_cur);
                         r_prev = r_cur;
                         it = 0; best_idx = -1; best_dt = -1.0e300; r_before_best = r_cur;
+                        page = -1;
                     }
                 }
             }
             if (__ballot_sync(FULL_MASK, ray >= 0) == 0) break;
         }
-        if (ray < 0) continue;
+        const bool act = ray >= 0;
+
+        // ---- paged dump: lanes starting a new page take one from the warp's slab ----
+        if (MODE == MODE_PAGED) {
+            bool need = act && ((it & (PAGE_ROWS - 1)) == 0);
+            unsigned nm = __ballot_sync(FULL_MASK, need);
+            if (nm) {
+                unsigned cnt = (unsigned)__popc(nm);
+                if (slab_next + cnt > slab_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(A.page_counter, PAGE_SLAB);
+                    slab_next = __shfl_sync(FULL_MASK, base, 0);
+                    slab_end = slab_next + PAGE_SLAB;
+                }
+                if (need) {
+                    unsigned np = slab_next + (unsigned)__popc(nm & ((1u << lane) - 1u));
+                    if (np < A.max_pages) {
+                        if (it == 0) A.page_first[ray] = (int)np;
+                        else if (page >= 0) A.page_next[page] = (int)np;
+                        A.page_next[np] = -1;
+                        page = (int)np;
+                    } else {
+                        *A.overflow = 1;
+                        if (it == 0) A.page_first[ray] = -1;
+                        page = -1;
+                    }
+                }
+                slab_next += cnt;
+            }
+        }
+        if (!act) continue;
 
         // ---- one iteration of geodesic_step ----
         double cand[8];
@@ -85,6 +131,16 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
                 p[0] = make_double4(s[0], s[1], s[2], s[3]);
                 p[1] = make_double4(s[4], s[5], s[6], s[7]);
                 A.dt[(long)it * A.npx + ray] = frozen ? 0.0 : dt;
+            }
+        }
+        if (MODE == MODE_PAGED) {
+            if (page >= 0) {
+                double* pg = A.pages + (long)page * PAGE_DOUBLES;
+                int rr = it & (PAGE_ROWS - 1);
+                double4* p = reinterpret_cast<double4*>(pg + rr * 8);
+                p[0] = make_double4(s[0], s[1], s[2], s[3]);
+                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+                pg[PAGE_ROWS * 8 + rr] = frozen ? 0.0 : dt;
             }
         }
         bool done = frozen;
@@ -143,7 +199,8 @@ template <class Metric>
 static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_t stream)
 {
     int per_sm = 0;
-    auto kern = A.S ? integrate_kernel<Metric, true> : integrate_kernel<Metric, false>;
+    auto kern = A.pages ? integrate_kernel<Metric, MODE_PAGED>
+                        : (A.S ? integrate_kernel<Metric, MODE_PADDED> : integrate_kernel<Metric, MODE_FINAL>);
     MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
     if (per_sm < 1) per_sm = 1;
     long warps_needed = (A.npx + 31) / 32;
@@ -159,6 +216,8 @@ static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_
 }  // namespace mk
 
 using namespace mk;
+
+static int dispatch_integrate(int metric_id, double bhspin, IntegrateArgs& A, cudaStream_t stream);
 
 extern "C" int mk_integrate(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
                             double tol, double* final_state, int32_t* nsteps, double* r_last, double* S,
@@ -179,6 +238,13 @@ extern "C" int mk_integrate(int metric_id, double bhspin, long N, long npx, cons
     A.queue = queue_counter(stream, 0);
     if (!A.queue) return 1;
     A.total_steps = total_steps;
+    A.pages = nullptr; A.page_next = nullptr; A.page_first = nullptr; A.page_counter = nullptr;
+    A.max_pages = 0; A.overflow = nullptr;
+    return dispatch_integrate(metric_id, bhspin, A, stream);
+}
+
+static int dispatch_integrate(int metric_id, double bhspin, IntegrateArgs& A, cudaStream_t stream)
+{
     int rc;
     if (metric_id == MK_METRIC_KERR_SCHILD) {
         KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
@@ -205,6 +271,79 @@ extern "C" int mk_fill_frozen_rows(double* S, double* dt, const double* final_st
     long cap = (long)sm_count() * 16;
     if (blocks > cap) blocks = cap;
     fill_frozen_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(S, dt, final_state, nsteps, npx, nrows);
+    MK_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---- paged (single-pass, ragged) trajectory dump ------------------------------------------------------
+extern "C" int mk_page_rows(void) { return PAGE_ROWS; }
+
+extern "C" int mk_integrate_paged(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
+                                  double tol, double* final_state, int32_t* nsteps, double* r_last,
+                                  double* pages, int32_t* page_next, int32_t* page_first,
+                                  unsigned int* page_counter, long max_pages, int32_t* overflow,
+                                  unsigned long long* total_steps, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MK_REQUIRE(npx >= 0 && N >= 0 && N < (1L << 31) - 2, "npx / N out of range");
+    MK_REQUIRE(pages && page_next && page_first && page_counter && overflow, "null page-store pointer");
+    MK_REQUIRE(max_pages > 0 && max_pages < (1L << 31), "max_pages out of range");
+    MK_REQUIRE(npx == 0 || s0 != nullptr, "s0 is null");
+    MK_REQUIRE(div != 0.0, "div must be non-zero");
+    if (npx == 0 || N == 0) return 0;
+    IntegrateArgs A;
+    A.s0 = s0; A.npx = npx; A.N = (int)N;
+    A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol;
+    A.final_state = final_state; A.nsteps = nsteps; A.r_last = r_last;
+    A.S = nullptr; A.dt = nullptr; A.nrows = 0;
+    A.queue = queue_counter(stream, 0);
+    if (!A.queue) return 1;
+    A.total_steps = total_steps;
+    A.pages = pages; A.page_next = page_next; A.page_first = page_first; A.page_counter = page_counter;
+    A.max_pages = (unsigned)max_pages; A.overflow = overflow;
+    return dispatch_integrate(metric_id, bhspin, A, stream);
+}
+
+namespace mk {
+// paged store -> the reference's padded layout for a selection of rays: S (nrows, nsel, 8), dt (nrows, nsel).
+// One thread per selected ray walks its page chain; rows past the ray's last stored row repeat it with dt = 0.
+__global__ void paged_gather_kernel(const double* __restrict__ pages, const int* __restrict__ page_next,
+                                    const int* __restrict__ page_first, const int32_t* __restrict__ nsteps,
+                                    const long* __restrict__ ray_idx, long nsel, long nrows, long N,
+                                    double* __restrict__ S, double* __restrict__ dt)
+{
+    long j = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (j >= nsel) return;
+    long ray = ray_idx ? ray_idx[j] : j;
+    long have = (long)nsteps[ray] + 1;          // rows stored: 0..n (frozen row) or N rows when n == N
+    if (have > N) have = N;
+    int page = page_first[ray];
+    double4 lo = make_double4(0, 0, 0, 0), hi = lo;
+    for (long row = 0; row < nrows; row++) {
+        double d = 0.0;
+        if (row < have && page >= 0) {
+            int rr = (int)(row & (PAGE_ROWS - 1));
+            const double* pg = pages + (long)page * PAGE_DOUBLES;
+            const double4* p = reinterpret_cast<const double4*>(pg + rr * 8);
+            lo = p[0]; hi = p[1];
+            d = pg[PAGE_ROWS * 8 + rr];
+            if (rr == PAGE_ROWS - 1) page = page_next[page];
+        }
+        double4* o = reinterpret_cast<double4*>(S + (row * nsel + j) * 8);
+        o[0] = lo; o[1] = hi;
+        dt[row * nsel + j] = d;
+    }
+}
+}  // namespace mk
+
+extern "C" int mk_paged_gather(const double* pages, const int32_t* page_next, const int32_t* page_first,
+                               const int32_t* nsteps, const long* ray_idx, long nsel, long nrows, long N,
+                               double* S, double* dt, void* stream)
+{
+    if (nsel <= 0 || nrows <= 0) return 0;
+    MK_REQUIRE(pages && page_next && page_first && nsteps && S && dt, "null pointer");
+    paged_gather_kernel<<<(unsigned)((nsel + 63) / 64), 64, 0, (cudaStream_t)stream>>>(pages, page_next, page_first, nsteps,
+                                                                                    ray_idx, nsel, nrows, N, S, dt);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -230,6 +230,84 @@ def geodesic_integrator(N, s0, div, tol, bhspin):
     return DeviceArray.wrap(S), DeviceArray.wrap(dt)
 
 
+class TrajectoryStore:
+    """Paged, ragged trajectory dump held in HBM (single integration pass, no padding).
+
+    The reference materialises ``S (nrows, npx, 8)`` padded to the longest ray (and its scan to all ``N``
+    iterations); at 1024^2 rays that is hundreds of GB.  Here every ray appends rows to 32-row pages taken
+    from a pool, so memory and write traffic are proportional to the steps actually taken (72 B per
+    ray-step).  ``padded()`` materialises the reference layout for any subset of rays on demand.
+    """
+    PAGE_ROWS = 32
+    PAGE_DOUBLES = 32 * 9
+
+    def __init__(self, npx, N, max_pages, device):
+        self.npx, self.N, self.max_pages = int(npx), int(N), int(max_pages)
+        self.pages = torch.empty((self.max_pages, self.PAGE_DOUBLES), dtype=torch.float64, device=device)
+        self.page_next = torch.empty((self.max_pages,), dtype=torch.int32, device=device)
+        self.page_first = torch.empty((self.npx,), dtype=torch.int32, device=device)
+        self.ctrl = torch.zeros(2, dtype=torch.int32, device=device)       # [page counter, overflow flag]
+        self.final = torch.empty((self.npx, 8), dtype=torch.float64, device=device)
+        self.nsteps = torch.empty((self.npx,), dtype=torch.int32, device=device)
+        self.r_last = torch.empty((self.npx,), dtype=torch.float64, device=device)
+        self.total_steps = torch.zeros(1, dtype=torch.int64, device=device)
+
+    @classmethod
+    def allocate(cls, npx, N, max_pages=None, mem_fraction=0.6):
+        dev = require_gpu()
+        worst = int(npx) * (-(-(int(N) + 1) // cls.PAGE_ROWS)) + 64 * 148 * 64
+        if max_pages is None:
+            free, _ = torch.cuda.mem_get_info()
+            max_pages = min(worst, int(mem_fraction * free) // (cls.PAGE_DOUBLES * 8))
+        return cls(npx, N, max(int(max_pages), 1), dev)
+
+    def reset(self):
+        self.ctrl.zero_()
+        self.total_steps.zero_()
+
+    @property
+    def overflowed(self):
+        return bool(self.ctrl[1].item())
+
+    @property
+    def pages_used(self):
+        return int(self.ctrl[0].item())
+
+    def padded(self, rays=None):
+        """Reference layout ``(S (nrows, nsel, 8), final_dt (nrows, nsel))`` for ``rays`` (default: all), with
+        ``nrows`` following geodesics.py:275-281 for that selection."""
+        if self.overflowed:
+            raise MemoryError("the page pool overflowed during integration; allocate more pages")
+        if rays is None:
+            idx = None
+            nsel = self.npx
+            nmax = int(self.nsteps.max().item()) if nsel else 0
+        else:
+            idx = as_device(np.asarray(rays, dtype=np.int64), dtype=torch.int64)
+            nsel = idx.numel()
+            nmax = int(self.nsteps[idx].max().item()) if nsel else 0
+        nrows = dump_rows(self.N, nmax)
+        S = empty((nrows, nsel, 8))
+        dt = empty((nrows, nsel))
+        _cabi.call("mk_paged_gather", self.pages, self.page_next, self.page_first, self.nsteps, idx, nsel, nrows,
+                   self.N, S, dt, stream_ptr())
+        return DeviceArray.wrap(S), DeviceArray.wrap(dt)
+
+
+def integrate_paged(N, s0, div, tol, bhspin, store=None):
+    """Single-pass trajectory dump of a whole bundle into a ``TrajectoryStore`` (see there)."""
+    s = as_device(s0)
+    npx = s.shape[0]
+    if store is None:
+        store = TrajectoryStore.allocate(npx, N)
+    if store.npx != npx or store.N != int(N):
+        raise ValueError("TrajectoryStore was allocated for a different bundle")
+    _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
+               store.final, store.nsteps, store.r_last, store.pages, store.page_next, store.page_first,
+               store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps, stream_ptr())
+    return store
+
+
 # -------------------------------------------------------------------------------------------------
 # shadow finder
 # -------------------------------------------------------------------------------------------------

@@ -117,6 +117,41 @@ def test_dump_mode_matches_oracle(ma):
     assert np.array_equal(np.asarray(dt2) == 0, dtr2 == 0)
 
 
+def test_paged_dump_matches_padded_dump(ma):
+    from oracle import c_oracle, mahakala_oracle as onp
+    from mahakala_b200 import geodesics as geo
+    s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 20)
+    store = geo.integrate_paged(10000, s0, 40, 1e-4, A)
+    assert not store.overflowed
+    S, dt = ma.geodesic_integrator(10000, s0, 40, 1e-4, A)
+    Sp, dtp = store.padded()
+    assert np.array_equal(np.asarray(Sp), np.asarray(S)) and np.array_equal(np.asarray(dtp), np.asarray(dt))
+    f, n, rl = geo.integrate_final(10000, s0, 40, 1e-4, A)
+    assert np.array_equal(np.asarray(store.nsteps.cpu()), np.asarray(n.cpu()))
+    assert np.array_equal(np.asarray(store.final.cpu()), np.asarray(f.cpu()))
+    assert int(store.total_steps.item()) == int(n.sum())
+    rows = int((n + 1).sum())
+    assert rows / 32 <= store.pages_used <= rows / 32 + 400 + 64 * 148 * 16
+    # subset view: nrows follows the selection, values identical to the oracle's dump of those rays
+    sel = [3, 77, 150, 399]
+    Ss, dts = store.padded(sel)
+    Sr, dtr = c_oracle.geodesic_integrator(10000, s0[sel], 40, 1e-4, A)
+    assert np.asarray(Ss).shape == Sr.shape
+    assert np.array_equal(np.asarray(dts) == 0, dtr == 0)
+    # iteration cap: rays that never freeze store exactly N rows
+    st2 = geo.integrate_paged(70, s0, 40, 1e-4, A)
+    S2, dt2 = ma.geodesic_integrator(70, s0, 40, 1e-4, A)
+    Sp2, dtp2 = st2.padded()
+    assert np.array_equal(np.asarray(Sp2), np.asarray(S2)) and np.array_equal(np.asarray(dtp2), np.asarray(dt2))
+    # a pool that is too small is reported, not silently truncated
+    small = geo.TrajectoryStore.allocate(s0.shape[0], 10000, max_pages=128)
+    geo.integrate_paged(10000, s0, 40, 1e-4, A, store=small)
+    assert small.overflowed
+    with pytest.raises(MemoryError):
+        small.padded()
+    assert np.array_equal(np.asarray(small.nsteps.cpu()), np.asarray(n.cpu()))
+
+
 def test_integrator_edge_cases(ma):
     from oracle import c_oracle, mahakala_oracle as onp
     from mahakala_b200 import geodesics as geo
