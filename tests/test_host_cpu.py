@@ -1,0 +1,142 @@
+"""CPU suite: C-ABI surface, host-side logic of the package, loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    inc = os.path.join(ROOT, "include")
+    for fn in sorted(os.listdir(inc)):
+        if fn.endswith(".h"):
+            text = open(os.path.join(inc, fn)).read()
+            text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+            names += re.findall(r"\b(mk_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from mahakala_b200 import _cabi
+    lib = _cabi.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    bound = set(_cabi.SIGNATURES) | set(_cabi.OTHER)
+    assert bound == set(declared), (bound ^ set(declared))
+    assert _cabi.call("mk_abi_version") == 1
+    assert lib.mk_page_rows() == 32
+    # argument-validation paths return an error string without touching the GPU
+    with pytest.raises(_cabi.MahakalaB200Error, match="metric"):
+        _cabi.call("mk_rhs", 99, 0.5, 1, 1, 1, None)       # unknown metric id is rejected before any launch
+    assert lib.mk_render_patch_count(1024, None, 0) == 256 * 128
+    assert lib.mk_render_patch_count(10, None, 0) == 3 * 2
+    assert lib.mk_render_patch_count(0, 8, 77) == 3
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu(built):
+    import mahakala_b200 as ma
+    from mahakala_b200 import _cabi
+    with pytest.raises(_cabi.MahakalaB200Error, match="no CPU fallback"):
+        ma.initialize_geodesics_at_camera(0.9, 60, 1000, -10, 10, 8)
+    with pytest.raises(_cabi.MahakalaB200Error):
+        ma.geodesic_integrator(10, np.zeros((4, 8)), 40, 1e-2, 0.9)
+    with pytest.raises(_cabi.MahakalaB200Error):
+        ma.find_shadow_bisection_angles(0.9, 60, np.array([0.0, 1.0]))
+    with pytest.raises(_cabi.MahakalaB200Error):
+        ma.synchrotron_coefficients(np.ones(3), np.ones(3), np.ones(3), np.ones(3), np.ones(3))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mahakala_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.lower().replace("# oracle", ""), os.path.join(dirpath, fn)
+
+
+def test_api_surface_matches_reference_exports():
+    import inspect
+    import mahakala_b200 as ma
+    from mahakala_b200 import geodesics, images, electrons, transfer
+    assert ma.__all__ == ["find_shadow_bisection", "find_shadow_bisection_angles", "geodesic_integrator",
+                          "initialize_geodesics_at_camera", "synchrotron_coefficients", "solve_specific_intensity",
+                          "solve_attenuated_emissivity"]
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(ma.initialize_geodesics_at_camera) == ["bhspin", "inclination", "distance", "fov_lower", "fov_upper",
+                                                      "pixels_per_side", "camera_type"]
+    assert sig(ma.geodesic_integrator) == ["N", "s0", "div", "tol", "bhspin"]
+    assert sig(ma.find_shadow_bisection_angles) == ["bhspin", "inc", "angles", "max_steps", "error_allowed", "max_it"]
+    assert sig(ma.find_shadow_bisection) == ["bhspin", "inc", "num_angles", "max_steps", "error_allowed", "max_it"]
+    assert sig(geodesics.select_photons_integrator) == ["inc", "angle", "radius", "bhspin", "distance", "max_steps"]
+    assert sig(ma.synchrotron_coefficients) == ["Ne", "Theta_e", "B", "pitch_angle", "nu", "invariant", "rescale_nu"]
+    assert sig(ma.solve_specific_intensity) == ["emissivity", "absorptivity", "dt", "L_unit", "dIs"]
+    assert sig(ma.solve_attenuated_emissivity) == ["emissivity", "absorptivity", "dt", "L_unit"]
+    assert sig(electrons.rlow_rhigh_model) == ["dens", "u", "beta", "r_low", "r_high", "electron_gamma", "ion_gamma"]
+    assert sig(images.make_image) == ["fluid_model", "camera_inclination", "camera_distance", "mass_scale", "M_bh",
+                                      "r_high", "observing_frequency", "fov", "resolution", "max_nsteps", "max_chunk_bytes"]
+    d = inspect.signature(images.make_image).parameters
+    assert (d["camera_inclination"].default, d["camera_distance"].default, d["mass_scale"].default, d["r_high"].default,
+            d["observing_frequency"].default, d["fov"].default, d["resolution"].default, d["max_nsteps"].default) == \
+        (60, 1000, 1.e26, 40, 230.e9, 20, 160, 10000)
+    for name in ("metric", "imetric", "rhs", "RK4_gen", "radius_cal", "radius_EH", "get_camera_pixel",
+                 "get_initial_grid", "initial_condition"):
+        assert callable(getattr(geodesics, name))
+    from mahakala_b200 import constants as c
+    assert (c.EE, c.KB, c.CL, c.ME, c.HPL, c.GNEWT, c.Msun, c.MP) == \
+        (4.8032e-10, 1.3807e-16, 2.99792458e10, 9.1094e-28, 6.6261e-27, 6.6743e-8, 1.989e33, 1.6726e-24)
+    assert geodesics.radius_EH(0.6) == 1.8
+    me = ma.install_as_mahakala()
+    import mahakala
+    from mahakala.images import make_image
+    assert mahakala is me and make_image is images.make_image
+
+
+def test_dump_rows_rule():
+    from mahakala_b200.geodesics import dump_rows
+    assert dump_rows(2000, 1291) == 1293          # first all-zero row 1291 -> +2   (SURVEY cfg1)
+    assert dump_rows(2000, 0) == 2000             # all rays frozen at row 0 -> N rows (geodesics.py:277-279)
+    assert dump_rows(2000, 2000) == 2000          # nobody froze -> N rows
+    assert dump_rows(2000, 1999) == 2000          # clipped to the N rows the scan produced
+    assert dump_rows(2000, 1998) == 2000
+    assert dump_rows(2000, 1997) == 1999
+
+
+def test_units_and_ghost_fill_and_block_grid(built):
+    from helpers import oracle_model, snapshot_arrays
+    from mahakala_b200.grmhd import GRMHDFluidModel
+    from mahakala_b200.grmhd.athenak import build_block_grid, fill_ghost_zones
+    from oracle import mahakala_oracle as onp
+    u = GRMHDFluidModel().get_units(6.2e9 * 1.989e33, 1e26)
+    assert u == onp.GRMHDFluidModel().get_units(6.2e9 * 1.989e33, 1e26)
+    arr = snapshot_arrays(ncells=24, block=8, extent=12.0)
+    amb, index = fill_ghost_zones(arr["uov"], arr["B"], arr["LogicalLocations"], arr["Levels"])
+    om = oracle_model(arr, 0.5)
+    assert np.array_equal(amb, om.all_meshblocks) and index == om.mb_index_map
+    assert np.array_equal(amb.astype(np.float32).astype(np.float64), amb)       # f32 storage is lossless
+    g, gn, g0, ginv = build_block_grid(arr["x1f"], arr["x2f"], arr["x3f"])
+    assert g.shape == (3, 3, 3) and list(gn) == [3, 3, 3] and (g >= 0).all() and len(set(g.ravel())) == 27
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-12, 12, (500, 3))
+    S = np.concatenate([np.zeros((500, 1)), pts, np.zeros((500, 4))], 1)
+    mb_ref = om._meshblock_indices(S)
+    c = np.clip(np.floor((pts - g0) * ginv).astype(int), 0, gn - 1)
+    assert np.array_equal(g[c[:, 2], c[:, 1], c[:, 0]], mb_ref)
+    # irregular mesh (blocks that are not integer multiples of the smallest) -> scan fallback
+    x1f = arr["x1f"].copy(); x1f[0, -1] += 0.37
+    assert build_block_grid(x1f, arr["x2f"], arr["x3f"]) is None
+
+
+def test_device_array_numpy_protocol():
+    from mahakala_b200._device import DeviceArray
+    t = DeviceArray.wrap(torch.arange(6, dtype=torch.float64).reshape(2, 3))
+    assert np.allclose(t, [[0, 1, 2], [3, 4, 5]])
+    assert isinstance(t[0], DeviceArray) and np.asarray(t * t)[1, 2] == 25.0
+    assert np.where(np.asarray(t) > 2)[0].tolist() == [1, 1, 1]

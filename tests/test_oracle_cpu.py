@@ -1,0 +1,120 @@
+"""CPU suite: the oracle against the reference's golden vectors and against itself (no GPU needed)."""
+import numpy as np
+import pytest
+
+from helpers import M_BH, MASS_SCALE, oracle_model, snapshot_arrays
+
+
+@pytest.fixture(scope="module")
+def oracles(built):
+    from oracle import c_oracle, mahakala_oracle as onp
+    return onp, c_oracle
+
+
+def test_golden_shadows_through_the_oracle(oracles, golden_shadows):
+    """Pins the oracle: the reference's own golden vectors (tests/test_shadows.py:28-45, rtol 1e-2)."""
+    onp, oc = oracles
+    for key, c in golden_shadows.items():
+        radii = onp.find_shadow_bisection_angles(c["bhspin"], c["inclination"], c["angles"],
+                                                 integrator=oc.geodesic_integrator)
+        assert np.allclose(radii, c["radii"], rtol=1e-2), key
+        assert np.abs(radii / c["radii"] - 1).max() < 3e-3, key
+
+
+def test_numpy_and_c_integrators_agree(oracles):
+    """The NumPy restatement (LAPACK inverse, jets) and the C restatement (Gauss-Jordan, jets) are two
+    independent codings of geodesics.py:233-351; their spread is the noise floor of the 1e-9 parity target."""
+    onp, oc = oracles
+    a = 0.94
+    s0 = onp.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 6)
+    S1, d1 = onp.geodesic_integrator(2000, s0, 40, 1e-2, a)
+    S2, d2 = oc.geodesic_integrator(2000, s0, 40, 1e-2, a)
+    assert S1.shape == S2.shape and np.array_equal(d1 == 0, d2 == 0)
+    esc = onp.last_point_radius(S1, d1, a) >= 100
+    err = np.abs(S1[:, esc] - S2[:, esc]) / np.abs(S1[:, esc]).max(axis=(0, 2), keepdims=True)
+    assert err.max() < 5e-8
+    o = oc.integrate(2000, s0, 40, 1e-2, a)
+    assert np.array_equal(o["nsteps"], (d2 != 0).sum(axis=0))
+    assert np.array_equal(o["r_last"], onp.last_point_radius(S2, d2, a))
+    assert np.array_equal(o["final"], S2[-1])
+    # truncation rules of geodesics.py:275-281
+    S3, d3 = oc.geodesic_integrator(30, s0, 40, 1e-2, a)
+    S4, d4 = onp.geodesic_integrator(30, s0, 40, 1e-2, a)
+    assert S3.shape == S4.shape == (30, 36, 8) and np.allclose(S3, S4, rtol=1e-10)
+    far = s0 * np.array([1, 3, 3, 3, 1, 1, 1, 1.0])
+    S5, d5 = oc.geodesic_integrator(25, far, 40, 1e-2, a)
+    S6, d6 = onp.geodesic_integrator(25, far, 40, 1e-2, a)
+    assert S5.shape == S6.shape == (25, 36, 8) and not d5.any() and not d6.any()
+
+
+def test_rhs_against_literal_jacfwd_and_mpmath(oracles):
+    """rhs of both oracles vs a torch.func.jacfwd/linalg.inv transliteration of geodesics.py:294-347 and vs
+    a 40-digit evaluation of the metric derivatives."""
+    onp, oc = oracles
+    from oracle import literal_torch
+    rng = np.random.default_rng(1)
+    a = 0.94
+    st = np.concatenate([np.zeros((40, 1)), rng.normal(0, 4, (40, 3)), np.ones((40, 1)), rng.normal(0, 1, (40, 3))], 1)
+    st = st[onp.radius_cal(st, a) > 1.4]
+    r_np, r_c, r_t = onp.rhs(st, a), oc.rhs(st, a), literal_torch.vectorized_rhs(st, a)
+    den = np.abs(r_np).max(axis=1, keepdims=True)
+    assert (np.abs(r_np - r_c) / den).max() < 1e-13
+    assert (np.abs(r_np - r_t) / den).max() < 1e-13
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+
+    def metric_mp(x):
+        aa = mp.mpf(a)**2
+        zz = x[3]**2
+        kk = (x[1]**2 + x[2]**2 + zz - aa) / 2
+        rr = mp.sqrt(kk * kk + aa * zz) + kk
+        r = mp.sqrt(rr)
+        f = 2 * rr * r / (rr * rr + aa * zz)
+        l = [mp.mpf(1), (r * x[1] + a * x[2]) / (rr + aa), (r * x[2] - a * x[1]) / (rr + aa), x[3] / r]
+        return mp.matrix([[(-1 if i == 0 else 1) * (i == j) + f * l[i] * l[j] for j in range(4)] for i in range(4)])
+
+    for s in st[:3]:
+        x = [mp.mpf(float(q)) for q in s[:4]]
+        v = [mp.mpf(float(q)) for q in s[4:]]
+        g = metric_mp(x)
+        h = mp.mpf(10)**-18
+        dg = []
+        for k in range(4):
+            xp = list(x); xm = list(x)
+            xp[k] += h; xm[k] -= h
+            dg.append((metric_mp(xp) - metric_mp(xm)) / (2 * h))
+        w = [-sum(dg[k][i, j] * v[k] * v[j] for j in range(4) for k in range(4))
+             + sum(dg[i][j, k] * v[j] * v[k] for j in range(4) for k in range(4)) / 2 for i in range(4)]
+        acc = mp.inverse(g) * mp.matrix(w)
+        ref = np.array([float(q) for q in acc])
+        got = onp.rhs(s[None], a)[0, 4:]
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_fluid_chain_numpy_vs_c(oracles):
+    onp, oc = oracles
+    a = 0.94
+    arr = snapshot_arrays(ncells=16, block=8, extent=16.0)
+    om = oracle_model(arr, a)
+    s0 = onp.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 6)
+    S, dt = oc.geodesic_integrator(10000, s0, 40, 1e-4, a)
+    sub = S[100:140]
+    ref = om.get_fluid_scalars_from_geodesics(sub)
+    got = oc.sample(om, sub, mode="scalars")
+    for k in ref:
+        assert np.allclose(got[k], ref[k], rtol=1e-9, atol=1e-13 * max(np.abs(ref[k]).max(), 1e-300)), k
+    refp = om.get_prims_from_geodesics(sub)
+    gotp = oc.sample(om, sub, mode="prims")
+    for k in refp:
+        assert np.allclose(gotp[k], refp[k], rtol=1e-12, atol=1e-300), k
+    img_np = onp.make_image(om, resolution=6, integrator=oc.geodesic_integrator)
+    units = om.get_units(M_BH, MASS_SCALE)
+    img_c, nsteps, nin = oc.render(om, s0, units, [230e9])
+    assert img_np.max() > 0
+    assert np.allclose(img_c[0].reshape(6, 6), img_np, rtol=1e-9, atol=1e-12 * img_np.max())
+    # attenuated emissivity integrates to the same intensity when alpha dt is small (consistency of the two scans)
+    em = np.abs(np.random.default_rng(0).normal(1, 0.1, (30, 4))); ab = em * 1e-3
+    d = -np.full((30, 4), 0.01)
+    I = onp.solve_specific_intensity(em, ab, d, 1.0)
+    att = onp.solve_attenuated_emissivity(em, ab, d, 1.0)
+    assert np.allclose(att.sum(axis=0), I, rtol=1e-3)
