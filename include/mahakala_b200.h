@@ -112,6 +112,8 @@ typedef struct mk_snapshot mk_snapshot;   /* opaque; owns the repacked, device-r
  * Host arrays: prim_index[8] = index in `meshblocks` of dens, eint, velx, vely, velz, bcc1, bcc2, bcc3
  * (athenak.py:697-710); gn, g0, ginv, bbox_lo, bbox_hi (3 each).
  * store_f32 != 0 stores cells as float32 (caller guarantees the values are float32-representable).
+ * meshblocks == NULL allocates the snapshot without filling the cells (a replica that receives them from
+ * another rank through mk_snapshot_cells + an NCCL broadcast).
  * The call is synchronous with respect to `stream` on return of the handle (the inputs may be freed).
  */
 int mk_snapshot_create(long nmb, long nk, long nj, long ni, const double* meshblocks, const int* prim_index,
@@ -171,17 +173,26 @@ int mk_emission_from_states(const mk_snapshot* snap, const mk_emission_params* p
  *   (sum of accepted steps; number of in-domain samples)
  *   queue: optional device counter (zero-initialised by the caller) from which warps pull 32-ray
  *   patches; it may live in a peer GPU's memory so that several GPUs share one dynamic tile queue.
- *   patch_begin/patch_end restrict the launch to a range of patches (static sharding); pass 0, -1
- *   for all.  image may likewise be a peer pointer (tiles are written where the gather would put them).
+ *   The launch processes patches patch_begin + k*patch_stride < patch_end (k from the queue): 0, -1, 1
+ *   = everything; rank, -1, world = static interleaved sharding.  image may likewise be a peer pointer
+ *   (tiles are written where the gather would put them).
  */
 int mk_render(double bhspin, double cos_i, double sin_i, double distance, double fov_lower,
               double fov_upper, long res, const double* s0, long npx, long N, double div, double tol,
               const mk_snapshot* snap, const mk_emission_params* params, int nfreq, const double* nu_obs,
               double* image, int32_t* nsteps, unsigned long long* total_steps,
               unsigned long long* total_samples, unsigned int* queue, long patch_begin, long patch_end,
-              void* stream);
+              long patch_stride, void* stream);
 /* number of 32-ray patches mk_render splits a job into (grid camera: 4x8 pixel patches) */
 long mk_render_patch_count(long res, const double* s0, long npx);
+
+/* ---- peer memory for the multi-GPU tile queue and in-kernel gather ----------------------------- */
+/* cudaMalloc'ed, zero-filled buffer that other processes on the node can map: handle receives the 64-byte
+   cudaIpcMemHandle_t to ship to the peers (e.g. with torch.distributed.broadcast_object_list). */
+int mk_ipc_alloc(long bytes, void** ptr, unsigned char* handle64);
+int mk_ipc_open(const unsigned char* handle64, void** ptr);
+int mk_ipc_close(void* ptr);
+int mk_ipc_free(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -239,3 +239,44 @@ extern "C" int mk_metric(int metric_id, double bhspin, const double* x, long n, 
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
+
+// ---- peer memory (CUDA IPC) for the shared tile queue / in-kernel gather -----------------------------
+extern "C" int mk_ipc_alloc(long bytes, void** ptr, unsigned char* handle64)
+{
+    MK_REQUIRE(bytes > 0 && ptr && handle64, "bad arguments");
+    void* p = nullptr;
+    MK_CUDA_CHECK(cudaMalloc(&p, (size_t)bytes));
+    MK_CUDA_CHECK(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return 0;
+}
+
+extern "C" int mk_ipc_open(const unsigned char* handle64, void** ptr)
+{
+    MK_REQUIRE(handle64 && ptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    MK_CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int mk_ipc_close(void* ptr)
+{
+    if (ptr) MK_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+extern "C" int mk_ipc_free(void* ptr)
+{
+    if (ptr) MK_CUDA_CHECK(cudaFree(ptr));
+    return 0;
+}

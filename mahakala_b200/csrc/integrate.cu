@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
     bool drained = false;           // queue exhausted (warp-uniform)
     double s[8];
     double dt = 0.0, r_cur = 0.0, r_prev = 0.0;
+    typename Metric::Cache cache, cache_new;
     double best_dt = 0.0, r_before_best = 0.0;
     int it = 0, best_idx = -1;
     unsigned long long my_steps = 0;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
                         double4 lo = p[0], hi = p[1];
                         s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
                         s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-                        r_cur = g.radius(s);
+                        r_cur = g.radius(s, cache);
                         dt = A.rule(r_cur);
                         r_prev = r_cur;
                         it = 0; best_idx = -1; best_dt = -1.0e300; r_before_best = r_cur;
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
         double cand[8];
         double r_new = 0.0, dtn = 0.0;
         if (dt != 0.0) {
-            rk4_step(g, s, dt, cand);
-            r_new = g.radius(cand);
+            rk4_step(g, s, dt, cand, &cache);
+            r_new = g.radius(cand, cache_new);
             dtn = A.rule(r_new);
         }
         bool frozen = (dt == 0.0) || (dtn == 0.0);
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
         if (!frozen) {
             if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
             r_prev = r_cur; r_cur = r_new;
+            cache = cache_new;
 #pragma unroll
             for (int i = 0; i < 8; i++) s[i] = cand[i];
             dt = dtn;

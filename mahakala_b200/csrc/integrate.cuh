@@ -27,12 +27,13 @@ struct StepRule {
 
 // One classical RK4 step of the 8-vector (x^m, v^m) with the plugin's acceleration.
 template <class Metric>
-__device__ __forceinline__ void rk4_step(const Metric& g, const double s[8], double dt, double out[8])
+__device__ __forceinline__ void rk4_step(const Metric& g, const double s[8], double dt, double out[8],
+                                         const typename Metric::Cache* cache = nullptr)
 {
     double acc[4], sum[8], tmp[8];
     const double hdt = 0.5 * dt;
-    // stage 1
-    g.accel(s, s + 4, acc);
+    // stage 1 (the point cache of s comes from the step rule evaluated when s was accepted)
+    g.accel(s, s + 4, acc, cache);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         sum[i] = s[4 + i];

@@ -24,15 +24,27 @@ struct KerrSchild {
 
     __device__ __forceinline__ double horizon() const { return rH; }
 
-    // radius_cal (geodesics.py:290-291): R^2 - a^2 + sqrt((R^2 - a^2)^2 + 4 a^2 z^2), halved, rooted.
+    // Point cache: the step rule's radius (geodesics.py:290-291, r = sqrt((w + sqrt(w^2 + 4 a^2 z^2))/2) with
+    // w = R^2 - a^2) is the same quantity as the metric's r = sqrt(rr), rr = sqrt(kk^2 + a^2 z^2) + kk with
+    // kk = w/2 (geodesics.py:99-101).  It is computed once per accepted state and reused by the first RK4
+    // stage of the next step.
+    struct Cache {
+        double rr, r, ri;     // r^2, r, 1/r
+    };
+
+    __device__ __forceinline__ double radius(const double x[4], Cache& c) const
+    {
+        double zz = x[3] * x[3];
+        double kk = 0.5 * (fma(x[1], x[1], fma(x[2], x[2], zz)) - aa);
+        c.rr = fast_sqrt(fma(kk, kk, aa * zz)) + kk;
+        fast_sqrt_rsqrt(c.rr, c.r, c.ri);
+        return c.r;
+    }
+
     __device__ __forceinline__ double radius(const double x[4]) const
     {
-        double R2 = fma(x[1], x[1], fma(x[2], x[2], x[3] * x[3]));
-        double w = R2 - aa;
-        double az = aa * (x[3] * x[3]);
-        double disc = fma(w, w, 4.0 * az);
-        double s = fast_sqrt(disc);
-        return fast_sqrt(0.5 * (w + s));
+        Cache c;
+        return radius(x, c);
     }
 
     // f and l_i of geodesics.py:97-103
@@ -54,17 +66,35 @@ struct KerrSchild {
         l3 = x[3] * ri;
     }
 
+    // same, reusing the point cache of x
+    __device__ __forceinline__ void fl(const double x[4], const Cache& c, double& f, double& l1, double& l2, double& l3) const
+    {
+        double den = fma(c.rr, c.rr, aa * (x[3] * x[3]));
+        double q = c.rr + aa;
+        double inv = fast_rcp(den * q);
+        double iden = inv * q, iq = inv * den;
+        f = 2.0 * c.rr * c.r * iden;
+        l1 = fma(c.r, x[1], a * x[2]) * iq;
+        l2 = fma(c.r, x[2], -a * x[1]) * iq;
+        l3 = x[3] * c.ri;
+    }
+
     // Geodesic acceleration d v^m / d lambda (geodesics.py:301-309 in closed form).
-    __device__ __forceinline__ void accel(const double x[4], const double v[4], double acc[4]) const
+    __device__ __forceinline__ void accel(const double x[4], const double v[4], double acc[4],
+                                          const Cache* cache = nullptr) const
     {
         const double X = x[1], Y = x[2], Z = x[3];
         const double v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3];
         double zz = Z * Z;
-        double kk = 0.5 * (fma(X, X, fma(Y, Y, zz)) - aa);
         double az2 = aa * zz;
-        double rr = fast_sqrt(fma(kk, kk, az2)) + kk;       // r^2
-        double r, ri;
-        fast_sqrt_rsqrt(rr, r, ri);                         // r, 1/r
+        double rr, r, ri;                                   // r^2, r, 1/r
+        if (cache) {
+            rr = cache->rr; r = cache->r; ri = cache->ri;
+        } else {
+            double kk = 0.5 * (fma(X, X, fma(Y, Y, zz)) - aa);
+            rr = fast_sqrt(fma(kk, kk, az2)) + kk;
+            fast_sqrt_rsqrt(rr, r, ri);
+        }
         double den = fma(rr, rr, az2);                      // r^4 + a^2 z^2
         double q = rr + aa;
         double inv = fast_rcp(den * q);

@@ -4,8 +4,9 @@
 // derivatives from jax.jacfwd (/root/reference/mahakala/geodesics.py:294-309, :339-347); a user swaps
 // spacetimes by replacing those globals.  Here a spacetime is a C++ type with
 //
-//     void   accel(const double x[4], const double v[4], double acc[4]) const;   // d v^m / d lambda
-//     double radius(const double x[4]) const;                                    // step-rule radius
+//     struct Cache;                                                              // per-point scratch
+//     void   accel(const double x[4], const double v[4], double acc[4], const Cache* = nullptr) const;
+//     double radius(const double x[4]) const;  double radius(const double x[4], Cache&) const;   // step rule
 //     double horizon() const;                                                    // inner cut-off radius
 //     void   metric_cov_con(const double x[4], double g[4][4], double gi[4][4]) const;
 //
@@ -148,8 +149,10 @@ struct DualMetric {
     Fn fn;
     double rH;
 
+    struct Cache {};      // nothing worth carrying between the step rule and the next stage
     __device__ __forceinline__ double horizon() const { return rH; }
     __device__ __forceinline__ double radius(const double x[4]) const { return fn.radius(x); }
+    __device__ __forceinline__ double radius(const double x[4], Cache&) const { return fn.radius(x); }
 
     __device__ __forceinline__ void metric_cov_con(const double x[4], double g[4][4], double gi[4][4]) const
     {
@@ -158,7 +161,8 @@ struct DualMetric {
     }
 
     // a^m = g^mn ( -d_k g_ns v^k v^s + 1/2 d_n g_ks v^k v^s )      (geodesics.py:307)
-    __device__ __forceinline__ void accel(const double x[4], const double v[4], double acc[4]) const
+    __device__ __forceinline__ void accel(const double x[4], const double v[4], double acc[4],
+                                          const Cache* = nullptr) const
     {
         typedef Dual<4> D;
         D xd[4];

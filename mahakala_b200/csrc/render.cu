@@ -37,20 +37,20 @@ struct RenderArgs {
     StepRule rule;
     SnapshotView sn;
     EmissionParams P;
-    double nu_obs[8];
+    EmissionConsts C;
+    double nu_obs[8], inv_nu_obs[8];
     double* image;             // (NF, npx)
     int32_t* nsteps;
     unsigned long long* total_steps;
     unsigned long long* total_samples;
     unsigned int* queue;
-    long patch_begin, patch_end;
+    long patch_begin, patch_end, patch_stride;
 };
 
 template <int NF>
 __global__ void __launch_bounds__(128, 3) render_kernel(const RenderArgs A)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const double cos_fallback = 0.5000000000000001;     // cos(pi/3) (athenak.py:639, :790)
     unsigned long long my_steps = 0, my_samples = 0;
 
     for (;;) {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128, 3) render_kernel(const RenderArgs A)
         unsigned pq = 0;
         if (lane == 0) pq = atomicAdd(A.queue, 1u);
         pq = __shfl_sync(FULL_MASK, pq, 0);
-        long patch = A.patch_begin + (long)pq;
+        long patch = A.patch_begin + (long)pq * A.patch_stride;
         if (patch >= A.patch_end) break;
 
         long ray;
@@ -90,20 +90,22 @@ __global__ void __launch_bounds__(128, 3) render_kernel(const RenderArgs A)
         for (int f = 0; f < NF; f++) { I[f] = 0.0; T[f] = 1.0; }
         int it = 0;
         double dt = 0.0;
-        if (active) dt = A.rule(A.g.radius(s));
+        KerrSchild::Cache cache, cache_new;
+        if (active) dt = A.rule(A.g.radius(s, cache));
         if (dt == 0.0) active = false;          // never moves: n = 0, no row pair contributes
 
         while (__any_sync(FULL_MASK, active)) {
             if (active) {
                 double cand[8];
-                rk4_step(A.g, s, dt, cand);
-                double dtn = A.rule(A.g.radius(cand));
+                rk4_step(A.g, s, dt, cand, &cache);
+                double dtn = A.rule(A.g.radius(cand, cache_new));
                 if (dtn == 0.0) {
                     active = false;             // step rejected; ray frozen at s (geodesics.py:264-267)
                 } else {
                     const double wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0)
 #pragma unroll
                     for (int i = 0; i < 8; i++) s[i] = cand[i];
+                    cache = cache_new;
                     dt = dtn;
                     it++;
                     if (it == A.N) {
@@ -112,21 +114,14 @@ __global__ void __launch_bounds__(128, 3) render_kernel(const RenderArgs A)
                         double prims[8];
                         if (interp_prims(A.sn, s, prims)) {
                             my_samples++;
-                            double f, l[4];
+                            double f, l[4], em[NF], ab[NF];
                             l[0] = 1.0;
-                            A.g.fl(s, f, l[1], l[2], l[3]);
-                            FluidScalars fs = fluid_frame(f, l, s, prims, cos_fallback);
-                            double Ne, Th, Bg, sigma;
-                            plasma_state(A.P, fs, Ne, Th, Bg, sigma);
-                            if (!(sigma > A.P.sigma_cut)) {
-                                double c = fs.cos_pitch;
-                                double sinp = sqrt((1.0 - c) * (1.0 + c));
+                            A.g.fl(s, cache, f, l[1], l[2], l[3]);
+                            if (emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab)) {
 #pragma unroll
                                 for (int fq = 0; fq < NF; fq++) {
-                                    double em, ab;
-                                    synchrotron(A.P, Ne, Th, Bg, sinp, -fs.kdotu * A.nu_obs[fq], 1, 1.0 / A.nu_obs[fq], em, ab);
-                                    I[fq] = fma(T[fq], wdt * em, I[fq]);
-                                    T[fq] = T[fq] * (1.0 - wdt * ab);
+                                    I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
+                                    T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
                                 }
                             }
                         }
@@ -181,7 +176,8 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
                          double tol, const mk_snapshot* snap, const mk_emission_params* params, int nfreq,
                          const double* nu_obs, double* image, int32_t* nsteps,
                          unsigned long long* total_steps, unsigned long long* total_samples,
-                         unsigned int* queue, long patch_begin, long patch_end, void* stream_)
+                         unsigned int* queue, long patch_begin, long patch_end, long patch_stride,
+                         void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MK_REQUIRE(snap && params && nu_obs && image, "null pointer");
@@ -201,15 +197,20 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
     A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol; A.rule.rH = A.g.rH;
     A.sn = snap->view;
     memcpy(&A.P, params, sizeof A.P);
-    for (int f = 0; f < 8; f++) A.nu_obs[f] = nu_obs[f < nfreq ? f : nfreq - 1];
+    A.C = make_emission_consts(A.P);
+    for (int f = 0; f < 8; f++) {
+        A.nu_obs[f] = nu_obs[f < nfreq ? f : nfreq - 1];
+        A.inv_nu_obs[f] = 1.0 / A.nu_obs[f];
+    }
     A.image = image; A.nsteps = nsteps; A.total_steps = total_steps; A.total_samples = total_samples;
     long npatches = mk_render_patch_count(res, s0, npx);
     A.patch_begin = patch_begin < 0 ? 0 : patch_begin;
     A.patch_end = (patch_end < 0 || patch_end > npatches) ? npatches : patch_end;
+    A.patch_stride = patch_stride < 1 ? 1 : patch_stride;
     if (A.patch_begin >= A.patch_end) return 0;
     A.queue = queue ? queue : queue_counter(stream, 1);
     if (!A.queue) return 1;
-    long span = A.patch_end - A.patch_begin;
+    long span = (A.patch_end - A.patch_begin + A.patch_stride - 1) / A.patch_stride;
     if (nfreq == 1) return launch_render<1>(A, span, stream);
     if (nfreq == 2) return launch_render<2>(A, span, stream);
     if (nfreq == 3) return launch_render<3>(A, span, stream);

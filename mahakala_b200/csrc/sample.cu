@@ -76,7 +76,7 @@ extern "C" int mk_snapshot_create(long nmb, long nk, long nj, long ni, const dou
     cudaStream_t stream = (cudaStream_t)stream_;
     MK_REQUIRE(out != nullptr, "out is null");
     MK_REQUIRE(nmb > 0 && nk > 0 && nj > 0 && ni > 0, "empty snapshot");
-    MK_REQUIRE(meshblocks && prim_index && geom && bbox_lo && bbox_hi, "null pointer");
+    MK_REQUIRE(prim_index && geom && bbox_lo && bbox_hi, "null pointer");
     MK_REQUIRE(nmb < (1L << 31) && nk < 32768 && nj < 32768 && ni < 32768, "snapshot dimensions too large");
     PrimIndex pi;
     for (int q = 0; q < 8; q++) {
@@ -101,7 +101,9 @@ extern "C" int mk_snapshot_create(long nmb, long nk, long nj, long ni, const dou
     }
     cudaMemcpyAsync(s->geom, geom, geom_bytes, cudaMemcpyDeviceToDevice, stream);
     if (grid) cudaMemcpyAsync(s->grid, grid, grid_bytes, cudaMemcpyDeviceToDevice, stream);
-    if (store_f32)
+    if (!meshblocks) {
+        // cells left uninitialised: the caller fills them (NCCL broadcast of a replicated snapshot)
+    } else if (store_f32)
         repack_kernel<float><<<grid_for(nmb * cpb, 256), 256, 0, stream>>>(meshblocks, (float*)s->cells, nmb, cpb, pi);
     else
         repack_kernel<double><<<grid_for(nmb * cpb, 256), 256, 0, stream>>>(meshblocks, (double*)s->cells, nmb, cpb, pi);

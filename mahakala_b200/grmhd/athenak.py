@@ -221,8 +221,9 @@ class AthenakFluidModel(GRMHDFluidModel):
             raise ValueError(f"snapshot lacks one of the primitives {CANONICAL_PRIMS}")
         return idx
 
-    def snapshot(self):
-        """The device-resident repacked snapshot handle (created on first use, reused afterwards)."""
+    def snapshot(self, fill=True):
+        """The device-resident repacked snapshot handle (created on first use, reused afterwards).
+        ``fill=False`` allocates the cells without uploading them (a replica filled by a broadcast)."""
         dev = require_gpu()
         if self._snap is not None and self._snap_device == dev:
             return self._snap
@@ -245,7 +246,7 @@ class AthenakFluidModel(GRMHDFluidModel):
                 raise ValueError("mesh is not regular enough for the block-grid lookup; use lookup='scan'")
         pidx = (ctypes.c_int * 8)(*self._prim_index())
         handle = ctypes.c_void_p()
-        d_mb = as_device(amb)
+        d_mb = as_device(amb) if fill else None
         d_geom = as_device(geom)
         if grid is not None:
             g, gn, g0, ginv = grid

@@ -27,7 +27,7 @@ def _params_for(fluid_model, M_bh, mass_scale, r_high):
 
 def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26, M_bh=6.2e9 * Msun,
            r_high=40, observing_frequencies=(230.e9,), fov=20, resolution=160, max_nsteps=10000, s0=None,
-           div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1), want_counters=False):
+           div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1, 1), want_counters=False):
     """Fused multi-frequency render.  Returns ``image (nfreq, npx)`` on the device (plus counters).
 
     ``s0`` (npx, 8) replaces the grid camera by explicit rays.  ``image_out`` / ``queue`` may be tensors
@@ -49,14 +49,20 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
         s0d = None
         res = int(resolution)
         npx = res * res
-    img = image_out if image_out is not None else empty((nfreq, npx))
+    if image_out is not None:
+        img = image_out
+    elif tuple(patch_range[:2]) == (0, -1) and (len(patch_range) < 3 or patch_range[2] == 1):
+        img = empty((nfreq, npx))
+    else:
+        img = torch.zeros((nfreq, npx), dtype=torch.float64, device=dev)    # partial render: others stay 0
     nsteps = None
     counters = torch.zeros(2, dtype=torch.int64, device=dev) if want_counters else None
     i = camera_inclination * np.pi / 180
     _cabi.call("mk_render", float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
                -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
                img, nsteps, counters[0:1] if want_counters else None, counters[1:2] if want_counters else None,
-               queue, int(patch_range[0]), int(patch_range[1]), stream_ptr())
+               queue, int(patch_range[0]), int(patch_range[1]), int(patch_range[2]) if len(patch_range) > 2 else 1,
+               stream_ptr())
     if want_counters:
         return img, counters
     return img
