@@ -1,0 +1,68 @@
+"""Host logic of the multi-GPU tile sharding, run with the gloo backend on CPU (world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, res, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mahakala_b200 import multigpu
+    assert multigpu.world() == (rank, world)
+    npatch = multigpu.patch_count(res)
+    begin, end, stride = multigpu.static_assignment(npatch, rank, world)
+    img = torch.zeros((2, res * res), dtype=torch.float64)
+    mine = 0
+    for p in range(begin, end, stride):
+        pix = multigpu.patch_pixels(p, res)
+        img[0, pix] = torch.from_numpy(pix + 1.0)
+        img[1, pix] = float(rank + 1)
+        mine += len(pix)
+    multigpu.combine_static(img, dst=0)
+    counts = torch.tensor([mine], dtype=torch.int64)
+    dist.all_reduce(counts)
+    if rank == 0:
+        ok = bool(torch.equal(img[0], torch.arange(1, res * res + 1, dtype=torch.float64)))
+        owners = set(img[1].tolist())
+        out.put((ok, int(counts.item()), sorted(owners)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_static_sharding_covers_image_once_gloo(built):
+    res = 20                       # not a multiple of the 4x8 patch: edge patches are partial
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, res, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, total, owners = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and total == res * res and owners == [1.0, 2.0]
+
+
+def test_patch_geometry_matches_library(built):
+    from mahakala_b200 import _cabi, multigpu
+    lib = _cabi.load()
+    for res in (8, 20, 33, 1024):
+        n = multigpu.patch_count(res)
+        assert n == lib.mk_render_patch_count(res, None, 0)
+        if res <= 33:
+            seen = np.concatenate([multigpu.patch_pixels(p, res) for p in range(n)])
+            assert np.array_equal(np.sort(seen), np.arange(res * res))
+    assert multigpu.static_assignment(10, 1, 4) == (1, 10, 4)
