@@ -345,20 +345,34 @@ def hbm_peak():
 
 
 def render_leg(args, rank, world, dev):
-    """cfg4: fused 1024^2 230 GHz image of the synthetic 256^3 snapshot (one frame per rank when N > 1)."""
+    """cfg4: fused 1024^2 230 GHz image of the synthetic 256^3 snapshot.
+
+    N = 1: one image.  N > 1: (weak) one frame per rank at its own inclination, and (strong) ONE image whose
+    32-ray patches all ranks pull from a single queue in rank 0's memory over NVLink, pixels stored straight
+    into rank 0's image (mahakala_b200.multigpu).  The snapshot is replicated with one NCCL broadcast.
+    """
     import torch
     import torch.distributed as dist
-    from mahakala_b200 import images
+    from mahakala_b200 import images, multigpu
     from mahakala_b200.grmhd import AthenakFluidModel
     from mahakala_b200.synthetic import make_synthetic_snapshot
 
     nc = args.snapshot_cells
     arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
+    if rank != 0:       # replicas keep only the geometry; the cells arrive by broadcast
+        arr["uov"] = np.zeros_like(arr["uov"])
+        arr["B"] = np.zeros_like(arr["B"])
     model = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
                                           arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"], CFG2["bhspin"],
-                                          fluid_gamma=arr["fluid_gamma"])
-    model.snapshot()
+                                          fluid_gamma=arr["fluid_gamma"], storage="f32")
     del arr
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    b0.record()
+    multigpu.replicate_snapshot(model)
+    b1.record()
+    torch.cuda.synchronize()
+    bcast_ms = b0.elapsed_time(b1)
     incl = WEAK_INCLINATIONS[rank % len(WEAK_INCLINATIONS)]
     res = args.res
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -378,17 +392,48 @@ def render_leg(args, rank, world, dev):
         t0 = time.perf_counter()
         host_img = images.make_image(model, camera_inclination=incl, resolution=res)
         e2e_times.append(1e3 * (time.perf_counter() - t0))
-    t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times))], dtype=torch.float64, device=dev)
+    strong = None
+    if world > 1:
+        shared = multigpu.SharedImage(1, res * res)
+        st = []
+        for it in range(2 + 3):
+            shared.reset()
+            flush.fill_(it)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            images.render(model, camera_inclination=CFG2["inclination"], resolution=res, observing_frequencies=(230e9,),
+                          image_out=shared.image_ptr, queue=shared.queue_ptr)
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            if it >= 2:
+                st.append(e0.elapsed_time(e1))
+        strong = float(np.mean(st))
+        flux = float(shared.local_view()[1].sum()) if rank == 0 else 0.0
+        dist.barrier()
+        shared.close()
+    t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong or 0.0, bcast_ms], dtype=torch.float64, device=dev)
+    w = torch.tensor([float(counters[0]), float(counters[1])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    steps, samples = int(counters[0]), int(counters[1])
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    steps, samples = int(w[0]), int(w[1])
     ms = float(t[0])
-    return {"workload": f"cfg4: synthetic AthenaK-shaped {nc}^3 snapshot ({model.storage} cells, {model.lookup} lookup), "
-                        f"{res}x{res} image at 230 GHz, fused kernel; one frame per rank",
-            "ms": ms, "e2e_ms": float(t[1]), "ray_steps": steps, "in_domain_samples": samples,
-            "ray_steps_per_s": steps / (ms * 1e-3),
-            "sampling_algorithmic_GBps": samples * (256 if model.storage == "f32" else 512) / (ms * 1e-3) / 1e9,
-            "snapshot_bytes": model.snapshot_bytes(), "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
+    out = {"workload": f"cfg4: synthetic AthenaK-shaped {nc}^3 snapshot ({model.storage} cells, {model.lookup} lookup), "
+                       f"{res}x{res} image at 230 GHz, fused kernel; one frame per rank",
+           "ms": ms, "e2e_ms": float(t[1]), "ray_steps": steps, "in_domain_samples": samples,
+           "ray_steps_per_s": steps / (ms * 1e-3),
+           "sampling_algorithmic_GBps": samples * (256 if model.storage == "f32" else 512) / (ms * 1e-3) / 1e9,
+           "snapshot_bytes": model.snapshot_bytes(), "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
+    if world > 1:
+        out["strong_scaling_single_image_ms"] = float(t[2])
+        out["strong_scaling_note"] = ("one i=60 deg image split over all ranks: shared atomic tile queue + in-kernel "
+                                      "gather into rank 0 over NVLink (CUDA IPC), device-timed, max over ranks")
+        out["strong_image_sum"] = flux
+        out["snapshot_broadcast_ms"] = float(t[3])
+    return out
 
 
 if __name__ == "__main__":

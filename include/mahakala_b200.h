@@ -174,7 +174,9 @@ int mk_emission_from_states(const mk_snapshot* snap, const mk_emission_params* p
  *   queue: optional device counter (zero-initialised by the caller) from which warps pull 32-ray
  *   patches; it may live in a peer GPU's memory so that several GPUs share one dynamic tile queue.
  *   The launch processes patches patch_begin + k*patch_stride < patch_end (k from the queue): 0, -1, 1
- *   = everything; rank, -1, world = static interleaved sharding.  image may likewise be a peer pointer
+ *   = everything; rank, -1, world = static interleaved sharding.  patch_order (device int32, one entry per
+ *   patch, or NULL) permutes the order in which patches are handed out: putting the long rays near the
+ *   photon ring first shortens the tail of the dynamic queue (longest-processing-time-first).  image may likewise be a peer pointer
  *   (tiles are written where the gather would put them).
  */
 int mk_render(double bhspin, double cos_i, double sin_i, double distance, double fov_lower,
@@ -182,7 +184,7 @@ int mk_render(double bhspin, double cos_i, double sin_i, double distance, double
               const mk_snapshot* snap, const mk_emission_params* params, int nfreq, const double* nu_obs,
               double* image, int32_t* nsteps, unsigned long long* total_steps,
               unsigned long long* total_samples, unsigned int* queue, long patch_begin, long patch_end,
-              long patch_stride, void* stream);
+              long patch_stride, const int* patch_order, void* stream);
 /* number of 32-ray patches mk_render splits a job into (grid camera: 4x8 pixel patches) */
 long mk_render_patch_count(long res, const double* s0, long npx);
 

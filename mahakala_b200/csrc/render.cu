@@ -45,6 +45,7 @@ struct RenderArgs {
     unsigned long long* total_samples;
     unsigned int* queue;
     long patch_begin, patch_end, patch_stride;
+    const int* patch_order;    // optional permutation of the patch indices (scheduling order)
 };
 
 template <int NF>
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(128, 3) render_kernel(const RenderArgs A)
         pq = __shfl_sync(FULL_MASK, pq, 0);
         long patch = A.patch_begin + (long)pq * A.patch_stride;
         if (patch >= A.patch_end) break;
+        if (A.patch_order) patch = A.patch_order[patch];
 
         long ray;
         double s[8];
@@ -177,7 +179,7 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
                          const double* nu_obs, double* image, int32_t* nsteps,
                          unsigned long long* total_steps, unsigned long long* total_samples,
                          unsigned int* queue, long patch_begin, long patch_end, long patch_stride,
-                         void* stream_)
+                         const int* patch_order, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MK_REQUIRE(snap && params && nu_obs && image, "null pointer");
@@ -207,6 +209,7 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
     A.patch_begin = patch_begin < 0 ? 0 : patch_begin;
     A.patch_end = (patch_end < 0 || patch_end > npatches) ? npatches : patch_end;
     A.patch_stride = patch_stride < 1 ? 1 : patch_stride;
+    A.patch_order = patch_order;
     if (A.patch_begin >= A.patch_end) return 0;
     A.queue = queue ? queue : queue_counter(stream, 1);
     if (!A.queue) return 1;

@@ -25,9 +25,28 @@ def _params_for(fluid_model, M_bh, mass_scale, r_high):
                            B_unit=units['B_unit'], L_unit=units['L_unit']), units
 
 
+_order_cache = {}
+
+
+def centre_out_patch_order(res, device):
+    """Scheduling order of the 4x8-pixel patches of a res x res grid camera: by distance of the patch centre
+    from the image centre.  The long rays (photon ring, a few M from the centre for any spin/inclination) are
+    then handed out early and the short outer rays fill the tail of the dynamic queue."""
+    key = (int(res), str(device))
+    if key not in _order_cache:
+        px_n, py_n = -(-res // 4), -(-res // 8)
+        cx = (np.arange(px_n) * 4 + 2.0) - res / 2.0
+        cy = (np.arange(py_n) * 8 + 4.0) - res / 2.0
+        rho = np.hypot(cx[:, None], cy[None, :]).reshape(-1)          # patch index = px * py_n + py
+        order = np.argsort(rho, kind="stable").astype(np.int32)
+        _order_cache[key] = torch.from_numpy(order).to(device)
+    return _order_cache[key]
+
+
 def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26, M_bh=6.2e9 * Msun,
            r_high=40, observing_frequencies=(230.e9,), fov=20, resolution=160, max_nsteps=10000, s0=None,
-           div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1, 1), want_counters=False):
+           div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1, 1), want_counters=False,
+           patch_order="centre_out"):
     """Fused multi-frequency render.  Returns ``image (nfreq, npx)`` on the device (plus counters).
 
     ``s0`` (npx, 8) replaces the grid camera by explicit rays.  ``image_out`` / ``queue`` may be tensors
@@ -62,6 +81,7 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
                -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
                img, nsteps, counters[0:1] if want_counters else None, counters[1:2] if want_counters else None,
                queue, int(patch_range[0]), int(patch_range[1]), int(patch_range[2]) if len(patch_range) > 2 else 1,
+               centre_out_patch_order(res, dev) if (s0d is None and patch_order == "centre_out") else None,
                stream_ptr())
     if want_counters:
         return img, counters
