@@ -120,6 +120,10 @@ int mk_snapshot_create(long nmb, long nk, long nj, long ni, const double* meshbl
                        const double* geom, const int* grid, const int* gn, const double* g0,
                        const double* ginv, const double* bbox_lo, const double* bbox_hi, int store_f32,
                        mk_snapshot** out, void* stream);
+/* Analytic fluid source instead of snapshot cells (BASELINE cfg3: Keplerian thin torus, power-law density,
+   toroidal field at fixed beta; not in the reference).  params9 (host) = {fluid_gamma, R0,
+   R_in, p, h, u0, beta0, dens_scale, r_out}.  The handle works with every mk_sample_* / mk_render call. */
+int mk_snapshot_create_torus(const double* params9, mk_snapshot** out);
 int mk_snapshot_destroy(mk_snapshot* snap);
 /* bytes of HBM held by the snapshot */
 long mk_snapshot_bytes(const mk_snapshot* snap);

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mk_rk4_step": "idpplpp",
     "mk_metric": "idplppp",
     "mk_snapshot_create": "llllpppppppppipp",
+    "mk_snapshot_create_torus": "pp",
     "mk_snapshot_destroy": "p",
     "mk_snapshot_cells": "ppp",
     "mk_sample_scalars": "pdpldpp",

@@ -115,6 +115,7 @@ extern "C" int mk_snapshot_create(long nmb, long nk, long nj, long ni, const dou
         return 1;
     }
     SnapshotView& v = s->view;
+    v.source = 0;
     v.cells = s->cells; v.is_f32 = store_f32 ? 1 : 0;
     v.nmb = (int)nmb; v.nk = (int)nk; v.nj = (int)nj; v.ni = (int)ni;
     for (int d = 0; d < 3; d++) {
@@ -128,6 +129,20 @@ extern "C" int mk_snapshot_create(long nmb, long nk, long nj, long ni, const dou
         v.ginv[d] = grid ? ginv[d] : 0.0;
     }
     v.grid = s->grid;
+    *out = s;
+    return 0;
+}
+
+extern "C" int mk_snapshot_create_torus(const double* params9, mk_snapshot** out)
+{
+    MK_REQUIRE(params9 && out, "null pointer");
+    mk_snapshot* s = new mk_snapshot();
+    memset(s, 0, sizeof *s);
+    cudaGetDevice(&s->device);
+    s->view.source = 1;
+    TorusParams& t = s->view.torus;
+    t.fluid_gamma = params9[0]; t.R0 = params9[1]; t.R_in = params9[2]; t.p = params9[3]; t.h = params9[4];
+    t.u0 = params9[5]; t.beta0 = params9[6]; t.dens_scale = params9[7]; t.r_out = params9[8];
     *out = s;
     return 0;
 }

@@ -18,7 +18,14 @@
 
 namespace mk {
 
+// cfg3 analytic thin torus: primitives are closed-form functions of position.
+struct TorusParams {
+    double fluid_gamma, R0, R_in, p, h, u0, beta0, dens_scale, r_out;
+};
+
 struct SnapshotView {
+    int source;               // 0 = AthenaK-style snapshot cells, 1 = analytic torus
+    TorusParams torus;
     const void* cells;        // AoS cells, f64 or f32
     int is_f32;
     int nmb, nk, nj, ni;      // interior cells per block
@@ -153,9 +160,34 @@ __device__ __forceinline__ void trilinear(const SnapshotView& sn, int mb, const 
     }
 }
 
+// Analytic torus primitives in canonical order; zero outside r <= r_out (the model's "domain").
+__device__ __forceinline__ bool torus_prims(const TorusParams& t, const double x[4], double prims[8])
+{
+    double R2 = x[1] * x[1] + x[2] * x[2];
+    double R = sqrt(R2) + 1e-12, r = sqrt(R2 + x[3] * x[3]) + 1e-12;
+    if (!(r <= t.r_out)) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) prims[q] = 0.0;
+        return false;
+    }
+    double H = t.h * R;
+    double q4 = t.R_in / R;
+    q4 = q4 * q4;
+    double taper = exp(-(q4 * q4));
+    double dens = t.dens_scale * pow(R / t.R0, -t.p) * exp(-x[3] * x[3] / (2. * H * H)) * taper;
+    double eint = t.u0 * dens * (t.R0 / r);
+    double vphi = 0.5 / sqrt(1. + R);
+    double bmag = sqrt(2. * eint * (t.fluid_gamma - 1.) / t.beta0);
+    prims[0] = dens; prims[1] = eint;
+    prims[2] = -vphi * x[2] / R; prims[3] = vphi * x[1] / R; prims[4] = 0.02 * x[3] / (1. + r);
+    prims[5] = -bmag * x[2] / R; prims[6] = bmag * x[1] / R; prims[7] = 0.1 * bmag;
+    return true;
+}
+
 // prims in canonical order dens, eint, U1..3, B1..3; returns false (and zeros) outside the domain
 __device__ __forceinline__ bool interp_prims(const SnapshotView& sn, const double x[4], double prims[8])
 {
+    if (sn.source == 1) return torus_prims(sn.torus, x, prims);
     int mb = locate_block(sn, x);
     if (mb < 0) {
 #pragma unroll

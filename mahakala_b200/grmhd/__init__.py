@@ -1,4 +1,4 @@
 from .grmhd import GRMHDFluidModel
-from .athenak import AthenakFluidModel
+from .athenak import AnalyticTorusFluidModel, AthenakFluidModel
 
-__all__ = ["GRMHDFluidModel", "AthenakFluidModel"]
+__all__ = ["GRMHDFluidModel", "AthenakFluidModel", "AnalyticTorusFluidModel"]

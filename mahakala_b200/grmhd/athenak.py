@@ -150,7 +150,85 @@ def build_block_grid(x1f, x2f, x3f, max_entries=1 << 26):
     return grid, gn.astype(np.int32), g0.astype(np.float64), (1.0 / bw).astype(np.float64)
 
 
-class AthenakFluidModel(GRMHDFluidModel):
+class DeviceSampledFluidModel(GRMHDFluidModel):
+    """Fluid models whose sampling runs in the CUDA kernels: subclasses provide ``snapshot()`` (an
+    ``mk_snapshot`` handle) plus ``bhspin`` / ``fluid_gamma``."""
+
+    _snap = None
+
+    def snapshot(self, fill=True):
+        raise NotImplementedError
+
+    def release(self):
+        if self._snap is not None:
+            _cabi.call("mk_snapshot_destroy", self._snap)
+            self._snap = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def get_prims_from_geodesics(self, S, profile=False):
+        """athenak.py:527-637: interpolated primitives at S[..., :4]; zero outside the domain."""
+        t0 = time.time()
+        Sd = as_device(S)
+        shape = tuple(Sd.shape[:-1])
+        n = int(np.prod(shape)) if shape else 1
+        out = empty((8, n))
+        _cabi.call("mk_sample_prims", self.snapshot(), Sd.reshape(-1, 8), n, out, stream_ptr())
+        names = ('dens', 'u', 'U1', 'U2', 'U3', 'B1', 'B2', 'B3')
+        res = {k: DeviceArray.wrap(out[i].reshape(shape)) for i, k in enumerate(names)}
+        if profile:
+            __import__('torch').cuda.synchronize()
+            print(f"Time to compute meshblock indices and primitives (one kernel): {time.time() - t0}")
+        return res
+
+    def get_fluid_scalars_from_geodesics(self, S, fallback_pitch_angle=np.pi / 3., profile=False):
+        """athenak.py:639-812: dens, u, pitch_angle, kdotu, b at the points of S (nsteps, npx, 8)."""
+        t0 = time.time()
+        Sd = as_device(S)
+        shape = tuple(Sd.shape[:-1])
+        n = int(np.prod(shape)) if shape else 1
+        out = empty((5, n))
+        _cabi.call("mk_sample_scalars", self.snapshot(), float(self.bhspin), Sd.reshape(-1, 8), n,
+                   float(fallback_pitch_angle), out, stream_ptr())
+        names = ('dens', 'u', 'pitch_angle', 'kdotu', 'b')
+        res = {k: DeviceArray.wrap(out[i].reshape(shape)) for i, k in enumerate(names)}
+        if profile:
+            __import__('torch').cuda.synchronize()
+            print(f"Time to compute meshblock indices and scalar data (one kernel): {time.time() - t0}")
+        return res
+
+
+class AnalyticTorusFluidModel(DeviceSampledFluidModel):
+    """BASELINE cfg3: analytic Keplerian thin torus (power-law density, toroidal field at fixed plasma beta),
+    evaluated in closed form at every sample point instead of interpolating snapshot cells.  The reference
+    ships no analytic model; this is a ``GRMHDFluidModel`` duck type pushed through the same fluid-frame,
+    thermodynamics and transfer code.  Zero outside the sphere ``r <= r_out``."""
+
+    def __init__(self, bhspin, fluid_gamma=13. / 9, R0=8.0, R_in=2.5, p=1.5, h=0.3, u0=0.25, beta0=3.0,
+                 dens_scale=1.0, r_out=40.0):
+        self.bhspin, self.fluid_gamma = bhspin, fluid_gamma
+        self.params = (fluid_gamma, R0, R_in, p, h, u0, beta0, dens_scale, r_out)
+        self._snap = None
+        self.storage, self.lookup = "analytic", "analytic"
+
+    def snapshot(self, fill=True):
+        require_gpu()
+        if self._snap is None:
+            handle = ctypes.c_void_p()
+            _cabi.call("mk_snapshot_create_torus", (ctypes.c_double * 9)(*[float(q) for q in self.params]),
+                       ctypes.byref(handle))
+            self._snap = handle
+        return self._snap
+
+    def snapshot_bytes(self):
+        return 0
+
+
+class AthenakFluidModel(DeviceSampledFluidModel):
 
     def __init__(self, grmhd_filename, bhspin, fluid_gamma=None):
         """athenak.py:50-53.  Reads an AthenaK ``.athdf`` dump (h5py required, imported lazily)."""
@@ -267,46 +345,3 @@ class AthenakFluidModel(GRMHDFluidModel):
 
     def snapshot_bytes(self):
         return int(_cabi.load().mk_snapshot_bytes(self.snapshot()))
-
-    def release(self):
-        if self._snap is not None:
-            _cabi.call("mk_snapshot_destroy", self._snap)
-            self._snap = None
-
-    def __del__(self):
-        try:
-            self.release()
-        except Exception:
-            pass
-
-    # ---- sampling ----------------------------------------------------------------------------
-    def get_prims_from_geodesics(self, S, profile=False):
-        """athenak.py:527-637: interpolated primitives at S[..., :4]; zero outside the domain."""
-        t0 = time.time()
-        Sd = as_device(S)
-        shape = tuple(Sd.shape[:-1])
-        n = int(np.prod(shape)) if shape else 1
-        out = empty((8, n))
-        _cabi.call("mk_sample_prims", self.snapshot(), Sd.reshape(-1, 8), n, out, stream_ptr())
-        names = ('dens', 'u', 'U1', 'U2', 'U3', 'B1', 'B2', 'B3')
-        res = {k: DeviceArray.wrap(out[i].reshape(shape)) for i, k in enumerate(names)}
-        if profile:
-            __import__('torch').cuda.synchronize()
-            print(f"Time to compute meshblock indices and primitives (one kernel): {time.time() - t0}")
-        return res
-
-    def get_fluid_scalars_from_geodesics(self, S, fallback_pitch_angle=np.pi / 3., profile=False):
-        """athenak.py:639-812: dens, u, pitch_angle, kdotu, b at the points of S (nsteps, npx, 8)."""
-        t0 = time.time()
-        Sd = as_device(S)
-        shape = tuple(Sd.shape[:-1])
-        n = int(np.prod(shape)) if shape else 1
-        out = empty((5, n))
-        _cabi.call("mk_sample_scalars", self.snapshot(), float(self.bhspin), Sd.reshape(-1, 8), n,
-                   float(fallback_pitch_angle), out, stream_ptr())
-        names = ('dens', 'u', 'pitch_angle', 'kdotu', 'b')
-        res = {k: DeviceArray.wrap(out[i].reshape(shape)) for i, k in enumerate(names)}
-        if profile:
-            __import__('torch').cuda.synchronize()
-            print(f"Time to compute meshblock indices and scalar data (one kernel): {time.time() - t0}")
-        return res

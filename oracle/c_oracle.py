@@ -77,8 +77,18 @@ def rhs(state, bhspin):
     return out
 
 
+def _torus_args(model):
+    tp = np.ascontiguousarray(model.params_array(), dtype=np.float64)
+    z = np.zeros(4)
+    args = [ctypes.c_int(0)] * 4 + [_d(z)] * 7
+    return args, [tp, z], tp
+
+
 def _snap_args(model):
     """model: oracle AthenakFluidModel (reference layout arrays)."""
+    if hasattr(model, "params_array"):
+        args, keep, tp = _torus_args(model)
+        return args, keep
     d = np.ascontiguousarray(model.all_meshblocks, dtype=np.float64)
     nmb, _, nk2, nj2, ni2 = d.shape
     arrs = [np.ascontiguousarray(q, dtype=np.float64) for q in
@@ -96,8 +106,9 @@ def sample(model, S, mode="scalars", fallback_pitch_angle=np.pi / 3.):
     nout = 5 if mode == "scalars" else 8
     out = np.empty((nout, n))
     args, keep = _snap_args(model)
+    torus = _d(keep[0]) if hasattr(model, "params_array") else None
     lib().orc_sample(ctypes.c_int(0 if mode == "scalars" else 1), ctypes.c_long(n), _d(S), *args,
-                     ctypes.c_double(model.bhspin), ctypes.c_double(fallback_pitch_angle), _d(out))
+                     ctypes.c_double(model.bhspin), ctypes.c_double(fallback_pitch_angle), torus, _d(out))
     names = (("dens", "u", "pitch_angle", "kdotu", "b") if mode == "scalars"
              else ("dens", "u", "U1", "U2", "U3", "B1", "B2", "B3"))
     return {k: out[i].reshape(shape) for i, k in enumerate(names)}
@@ -116,5 +127,6 @@ def render(model, s0, units, nu_obs, r_high=40., N=10000, div=40., tol=1e-4):
                      *args, ctypes.c_double(model.bhspin), ctypes.c_double(model.fluid_gamma),
                      ctypes.c_double(r_high), ctypes.c_double(units["Ne_unit"]),
                      ctypes.c_double(units["B_unit"]), ctypes.c_double(units["L_unit"]),
-                     ctypes.c_int(nu.size), _d(nu), _d(img), nsteps.ctypes.data_as(_ip), ctypes.byref(nin))
+                     ctypes.c_int(nu.size), _d(nu), _d(keep[0]) if hasattr(model, "params_array") else None,
+                     _d(img), nsteps.ctypes.data_as(_ip), ctypes.byref(nin))
     return img, nsteps, int(nin.value)

@@ -619,6 +619,53 @@ class AthenakFluidModel(GRMHDFluidModel):
                     b=out[:, :, 4])
 
 
+class AnalyticTorusFluidModel(GRMHDFluidModel):
+    """cfg3: analytic Keplerian thin torus, power-law density and toroidal field at fixed
+    plasma beta.  NOT in the reference (which only ships AthenakFluidModel); it is a GRMHDFluidModel duck type
+    whose primitives are closed-form functions of position, pushed through the identical fluid-frame algebra
+    of athenak.py:760-794.  Zero outside the sphere r <= r_out (plays the role of "outside the domain")."""
+
+    def __init__(self, bhspin, fluid_gamma=13. / 9, R0=8.0, R_in=2.5, p=1.5, h=0.3, u0=0.25, beta0=3.0,
+                 dens_scale=1.0, r_out=40.0):
+        self.bhspin, self.fluid_gamma = bhspin, fluid_gamma
+        self.R0, self.R_in, self.p, self.h, self.u0, self.beta0 = R0, R_in, p, h, u0, beta0
+        self.dens_scale, self.r_out = dens_scale, r_out
+
+    def params_array(self):
+        return np.array([self.fluid_gamma, self.R0, self.R_in, self.p, self.h, self.u0, self.beta0,
+                         self.dens_scale, self.r_out])
+
+    def prims(self, X):
+        """X (..., 4+) -> prims (..., 8) in the AthenaK order dens, velx, vely, velz, eint, bcc1..3."""
+        x, y, z = X[..., 1], X[..., 2], X[..., 3]
+        with np.errstate(all='ignore'):
+            R2 = x * x + y * y
+            R = np.sqrt(R2) + 1e-12
+            r = np.sqrt(R2 + z * z) + 1e-12
+            H = self.h * R
+            taper = np.exp(-(self.R_in / R)**4)
+            dens = self.dens_scale * (R / self.R0)**(-self.p) * np.exp(-z * z / (2. * H * H)) * taper
+            eint = self.u0 * dens * (self.R0 / r)
+            vphi = 0.5 / np.sqrt(1. + R)
+            bmag = np.sqrt(2. * eint * (self.fluid_gamma - 1.) / self.beta0)
+            out = np.stack([dens, -vphi * y / R, vphi * x / R, 0.02 * z / (1. + r), eint,
+                            -bmag * y / R, bmag * x / R, 0.1 * bmag], axis=-1)
+        return np.where((r <= self.r_out)[..., None], out, 0.0)
+
+    def get_prims_from_geodesics(self, S):
+        P = self.prims(np.asarray(S, dtype=np.float64))
+        return dict(dens=P[..., 0], u=P[..., 4], U1=P[..., 1], U2=P[..., 2], U3=P[..., 3],
+                    B1=P[..., 5], B2=P[..., 6], B3=P[..., 7])
+
+    def get_fluid_scalars_from_geodesics(self, S, fallback_pitch_angle=np.pi / 3.):
+        S = np.asarray(S, dtype=np.float64)
+        out = np.zeros(S.shape[:2] + (5,))
+        for i in range(S.shape[0]):
+            out[i] = fluid_frame_scalars(S[i], self.prims(S[i]), self.bhspin, 0, 4, 1, 5, fallback_pitch_angle)
+        return dict(dens=out[:, :, 0], u=out[:, :, 1], pitch_angle=out[:, :, 2], kdotu=out[:, :, 3],
+                    b=out[:, :, 4])
+
+
 def fluid_frame_scalars(S0, prims, bhspin, irho=0, iu=4, iU1=1, iB1=5, fallback_pitch_angle=np.pi / 3.):
     """athenak.py:760-794: metric, four-velocity, magnetic four-vector, k.u, pitch angle, |b|."""
     with np.errstate(all='ignore'):

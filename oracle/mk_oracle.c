@@ -245,6 +245,7 @@ void orc_rhs(int n, const double *s, double a, double *out)
 /* fluid sampling (athenak.py:639-812), electrons (electrons.py:46-50), synchrotron (transfer.py:56-86) */
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct {
+    const double *torus;                 /* NULL, or the analytic thin-torus parameters (cfg3, see below) */
     int nmb, nk, nj, ni;                 /* interior cells per block */
     const double *data;                  /* (nmb, 8, nk+2, nj+2, ni+2), reference layout */
     const double *x1f, *x2f, *x3f;       /* (nmb, n+1) */
@@ -268,8 +269,33 @@ static int find_block(const orc_snapshot *sn, const double x[4])
 static double pymod1(double q) { double m = fmod(q, 1.0); if (m < 0) m += 1.0; return m; }
 
 /* athenak.py:718-757: trilinear interpolation of the 8 primitives; zero outside the domain */
+/*
+ * cfg3 analytic thin torus (not part of the reference, which only ships AthenakFluidModel):
+ * a GRMHDFluidModel whose primitives are closed-form functions of position, pushed through the identical
+ * fluid-frame algebra.  params = {fluid_gamma, R0, R_in, p, h, u0, beta0, dens_scale, r_out}.
+ * Same formulas as mahakala_oracle.AnalyticTorusFluidModel.  Order: dens, velx, vely, velz, eint, b1, b2, b3.
+ */
+static int torus_prims(const double *tp, const double x[4], double prims[8])
+{
+    double fluid_gamma = tp[0], R0 = tp[1], R_in = tp[2], p = tp[3], h = tp[4], u0 = tp[5], beta0 = tp[6],
+           dens_scale = tp[7], r_out = tp[8];
+    double R2 = x[1] * x[1] + x[2] * x[2];
+    double R = sqrt(R2) + 1e-12, r = sqrt(R2 + x[3] * x[3]) + 1e-12;
+    if (!(r <= r_out)) { for (int q = 0; q < 8; q++) prims[q] = 0.0; return -1; }
+    double H = h * R;
+    double taper = exp(-pow(R_in / R, 4));
+    double dens = dens_scale * pow(R / R0, -p) * exp(-x[3] * x[3] / (2. * H * H)) * taper;
+    double eint = u0 * dens * (R0 / r);
+    double vphi = 0.5 / sqrt(1. + R);
+    double bmag = sqrt(2. * eint * (fluid_gamma - 1.) / beta0);
+    prims[0] = dens; prims[1] = -vphi * x[2] / R; prims[2] = vphi * x[1] / R; prims[3] = 0.02 * x[3] / (1. + r);
+    prims[4] = eint; prims[5] = -bmag * x[2] / R; prims[6] = bmag * x[1] / R; prims[7] = 0.1 * bmag;
+    return 0;
+}
+
 static int interp_prims(const orc_snapshot *sn, const double x[4], double prims[8])
 {
+    if (sn->torus) return torus_prims(sn->torus, x, prims);
     int mb = find_block(sn, x);
     if (mb < 0) { for (int q = 0; q < 8; q++) prims[q] = 0.0; return mb; }
     const double *v1 = sn->x1v + (size_t)mb * sn->ni, *v2 = sn->x2v + (size_t)mb * sn->nj,
@@ -374,7 +400,7 @@ static orc_snapshot make_snap(int nmb, int nk, int nj, int ni, const double *dat
                               const double *x1v, const double *x2v, const double *x3v,
                               double a, double fluid_gamma)
 {
-    orc_snapshot sn = {nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, fluid_gamma};
+    orc_snapshot sn = {NULL, nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, fluid_gamma};
     return sn;
 }
 
@@ -382,9 +408,10 @@ int orc_sample(int mode, long nsamples, const double *S,
                int nmb, int nk, int nj, int ni, const double *data,
                const double *x1f, const double *x2f, const double *x3f,
                const double *x1v, const double *x2v, const double *x3v,
-               double a, double fallback_pitch, double *out)
+               double a, double fallback_pitch, const double *torus, double *out)
 {
     orc_snapshot sn = make_snap(nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, 0);
+    sn.torus = torus;
 #pragma omp parallel for schedule(dynamic, 256)
     for (long p = 0; p < nsamples; p++) {
         double prims[8];
@@ -421,10 +448,11 @@ int orc_render(int N, int npx, const double *s0, double div, double tol,
                const double *x1f, const double *x2f, const double *x3f,
                const double *x1v, const double *x2v, const double *x3v,
                double a, double fluid_gamma, double r_high, double Ne_unit, double B_unit, double L_unit,
-               int nfreq, const double *nu_obs, double *image /* (nfreq, npx) */, int32_t *nsteps,
-               int64_t *n_in_domain)
+               int nfreq, const double *nu_obs, const double *torus, double *image /* (nfreq, npx) */,
+               int32_t *nsteps, int64_t *n_in_domain)
 {
     orc_snapshot sn = make_snap(nmb, nk, nj, ni, data, x1f, x2f, x3f, x1v, x2v, x3v, a, fluid_gamma);
+    sn.torus = torus;
     int64_t indom = 0;
 #pragma omp parallel reduction(+ : indom)
     {

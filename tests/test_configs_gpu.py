@@ -1,0 +1,120 @@
+"""BASELINE.json configs at their stated sizes: oracle parity where the oracle finishes in seconds, otherwise
+size-independent properties (determinism, dump <-> final consistency, sub-lattice parity, flux convergence)."""
+import numpy as np
+import pytest
+
+from helpers import M_BH, MASS_SCALE
+
+pytestmark = pytest.mark.gpu
+A = 0.94
+
+
+@pytest.fixture(scope="module")
+def ma(built):
+    import mahakala_b200 as ma
+    return ma
+
+
+def _image_errors(img, ref):
+    scale = np.abs(ref).max()
+    per_px = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * scale)
+    return per_px.max(), abs(img.sum() - ref.sum()) / abs(ref.sum())
+
+
+def test_cfg3_analytic_torus_image(ma):
+    """cfg3: analytic Keplerian thin torus, thermal synchrotron at 230 GHz; 512x512 on the GPU, the C oracle
+    on a 128x128 sub-lattice of the same pixels (every 4th) plus a 64^2 full image."""
+    from mahakala_b200 import images
+    from mahakala_b200.grmhd import AnalyticTorusFluidModel
+    from oracle import c_oracle, mahakala_oracle as onp
+    dm = AnalyticTorusFluidModel(A)
+    om = onp.AnalyticTorusFluidModel(A)
+    units = om.get_units(M_BH, MASS_SCALE)
+    # full small image, fused + unfused, vs the oracle
+    s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 64)
+    ref, _, nin = c_oracle.render(om, s0, units, [230e9])
+    ref = ref[0].reshape(64, 64)
+    img = images.make_image(dm, resolution=64)
+    e_px, e_flux = _image_errors(img, ref)
+    assert ref.max() > 1e-4 and e_px < 1e-6 and e_flux < 1e-8, (e_px, e_flux)
+    img_u = images.make_image_unfused(dm, resolution=32)
+    s032 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 32)
+    ref32, _, _ = c_oracle.render(om, s032, units, [230e9])
+    e_px, e_flux = _image_errors(img_u, ref32[0].reshape(32, 32))
+    assert e_px < 1e-6 and e_flux < 1e-8
+    # sampled scalars of the analytic model vs the NumPy oracle
+    S, dt = c_oracle.geodesic_integrator(10000, s0[::97], 40, 1e-4, A)
+    got = dm.get_fluid_scalars_from_geodesics(S[150:200])
+    want = om.get_fluid_scalars_from_geodesics(S[150:200])
+    for k in ("dens", "u", "kdotu", "b"):
+        assert np.allclose(np.asarray(got[k]), want[k], rtol=1e-11, atol=1e-14 * np.abs(want[k]).max()), k
+    # the stated size: 512x512; parity on the every-4th-pixel sub-lattice, flux convergence vs 256x256
+    big = images.make_image(dm, resolution=512)
+    s0_big = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 512)
+    idx = (np.arange(0, 512, 4)[:, None] * 512 + np.arange(0, 512, 4)[None, :]).reshape(-1)
+    ref_sub, _, _ = c_oracle.render(om, s0_big[idx], units, [230e9])
+    e_px, e_flux = _image_errors(big.reshape(-1)[idx], ref_sub[0])
+    assert e_px < 1e-6 and e_flux < 1e-8, (e_px, e_flux)
+    half = images.make_image(dm, resolution=256)
+    assert abs(big.sum() / 4 - half.sum()) / half.sum() < 2e-2
+    assert (big >= 0).all() and np.isfinite(big).all()
+
+
+def test_cfg2_bundle_1024_properties(ma):
+    """cfg2 at full size (1024x1024 rays, dump mode): properties + parity on the 64x64 sub-lattice."""
+    import torch
+    from mahakala_b200 import geodesics as geo
+    from oracle import c_oracle
+    s0 = ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 1024)
+    store = geo.integrate_paged(10000, s0, 40, 1e-4, A)
+    assert not store.overflowed
+    f, n, rl, total = geo.integrate_final(10000, s0, 40, 1e-4, A, want_total=True)
+    # dump and final modes are the same computation: bit-identical step counts, states and classifier radii
+    assert torch.equal(store.nsteps, n) and torch.equal(store.final, f) and torch.equal(store.r_last, rl)
+    assert int(total) == int(store.total_steps) == int(n.sum())
+    # the frozen row stored in the dump equals the final state; spot-check through the padded view
+    idx = (np.arange(0, 1024, 16)[:, None] * 1024 + np.arange(0, 1024, 16)[None, :]).reshape(-1)
+    S, dt = store.padded(idx)
+    S, dt = np.asarray(S), np.asarray(dt)
+    n_sub = np.asarray(n.cpu())[idx]
+    assert np.array_equal((dt != 0).sum(axis=0), n_sub)
+    assert np.array_equal(S[n_sub, np.arange(idx.size)], np.asarray(f.cpu())[idx])
+    assert (dt <= 0).all()
+    # sub-lattice parity against the oracle (shadow classification bit-exact, escaped final states)
+    s0h = np.asarray(s0)[idx]
+    ref = c_oracle.integrate(10000, s0h, 40, 1e-4, A)
+    cap = np.asarray(rl.cpu())[idx] < 100
+    assert np.array_equal(cap, ref["r_last"] < 100)
+    esc = ~cap
+    err = np.abs(np.asarray(f.cpu())[idx][esc] - ref["final"][esc]) / np.maximum(np.abs(ref["final"][esc]), 1e-300)
+    assert np.median(err) < 1e-12 and err.max() < 5e-8
+    assert np.array_equal(n_sub[esc], ref["nsteps"][esc])
+    # null condition is conserved along escaped rays: g_mn k^m k^n ~ 0 at the final state
+    g = np.asarray(geo.metric(np.asarray(f.cpu())[idx][esc][:, :4], A))
+    k = np.asarray(f.cpu())[idx][esc][:, 4:]
+    norm = np.einsum('ni,nij,nj->n', k, g, k)
+    assert np.abs(norm).max() < 1e-7
+    # determinism across launches although lanes are refilled dynamically
+    f2, n2, rl2 = geo.integrate_final(10000, s0, 40, 1e-4, A)
+    assert torch.equal(f2, f) and torch.equal(n2, n)
+
+
+def test_cfg5_style_multifrequency_multi_inclination(ma):
+    """cfg5 at reduced size: 8 frequencies x 4 inclinations share one geodesic/sample pass per inclination."""
+    from helpers import device_model, oracle_model, snapshot_arrays
+    from mahakala_b200 import images
+    from oracle import c_oracle, mahakala_oracle as onp
+    arr = snapshot_arrays(ncells=32, block=16, extent=16.0, seed=3)
+    om, dm = oracle_model(arr, A), device_model(arr, A)
+    units = om.get_units(M_BH, MASS_SCALE)
+    nus = [43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9]
+    for inc in (17, 30, 60, 80):
+        img = np.asarray(images.render(dm, camera_inclination=inc, resolution=16, observing_frequencies=nus).cpu())
+        s0 = onp.initialize_geodesics_at_camera(A, inc, 1000, -10, 10, 16)
+        ref, _, _ = c_oracle.render(om, s0, units, nus)
+        for f in range(8):
+            e_px, e_flux = _image_errors(img[f], ref[f])
+            assert e_px < 1e-6 and e_flux < 1e-8, (inc, f, e_px, e_flux)
+        # one-frequency launches give the same numbers as the 8-frequency launch
+        single = np.asarray(images.render(dm, camera_inclination=inc, resolution=16, observing_frequencies=[nus[3]]).cpu())
+        assert np.array_equal(single[0], img[3])
