@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(128, 4) integrate_kernel(const Metric g, const
             }
         }
         bool done = frozen;
-        double rl = (it >= 1) ? r_prev : r_cur;     // first zero row = it ; classifier row = it - 1 (wraps)
+        // geodesics.py:373: argmax(dt) is the first zero row (= it) unless some step size was positive (a ray
+        // that jumped inside the horizon steps with dt > 0); the classifier row is argmax - 1, and -1 wraps to
+        // the last row, a copy of the frozen state.
+        double rl = (best_dt > 0.0) ? ((best_idx >= 1) ? r_before_best : r_cur) : ((it >= 1) ? r_prev : r_cur);
         if (!frozen) {
             if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
             r_prev = r_cur; r_cur = r_new;

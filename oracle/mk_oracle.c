@@ -181,8 +181,10 @@ static int integrate_ray(int N, const double s0[8], double div, double tol, doub
         }
         if (dt == 0.0 || dtn == 0.0) {      /* frozen: this row has dt = 0 (geodesics.py:264-267) */
             if (emit) emit(ctx, it, s, 0.0);
-            /* first zero row = it ; classifier row = it - 1 (wraps to the last row, a frozen copy, if it = 0) */
-            *r_last = (it >= 1) ? r_prev : r_cur;
+            /* argmax(dt) = first zero row (= it) unless some dt was positive (ray inside the horizon); classifier
+               row = argmax - 1, where -1 wraps to the last row, a copy of the frozen state (geodesics.py:373-378) */
+            if (best_dt > 0.0) *r_last = (best_idx >= 1) ? r_before_best : r_cur;
+            else *r_last = (it >= 1) ? r_prev : r_cur;
             terminated = 1;
             break;
         }
