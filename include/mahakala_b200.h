@@ -30,6 +30,7 @@ extern "C" {
 /* built-in spacetimes (metric plugins compiled into the library) */
 #define MK_METRIC_KERR_SCHILD 0      /* closed-form Cartesian Kerr-Schild: geodesics.py:88-104 */
 #define MK_METRIC_KERR_SCHILD_DUAL 1 /* same metric through the generic dual-number plugin path */
+#define MK_METRIC_PLUGIN_BASE 16     /* ids >= 16: spacetimes registered at run time (mk_register_metric) */
 
 /* ---- library ------------------------------------------------------------------------------- */
 int mk_abi_version(void);
@@ -39,6 +40,25 @@ int mk_device_info(int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_kh
 /* DFMA microbenchmark: measured FP64 FMA throughput (TFLOP/s, 2 flop per FMA) of the current device.
    Synchronous.  Used as the roofline denominator of the integrator. */
 int mk_measure_fp64_peak(int iters, double* tflops_out, double* ms_out);
+
+/* ---- user-registered spacetimes ------------------------------------------------------------------ */
+/*
+ * The reference lets a user change spacetime by replacing the module-level metric()/imetric()
+ * (geodesics.py:88-104, :304-305, :339-347); jax.jacfwd supplies the derivatives.  Here `source` is CUDA C++
+ * defining `struct UserMetric` (contract in mahakala_b200/csrc/plugin_tu.cuh): the covariant metric on a
+ * generic scalar type, the step-rule radius and the horizon radius.  It is compiled with NVRTC for sm_100a
+ * against the headers in include_dir (the package's csrc directory); derivatives come from forward-mode dual
+ * numbers and the inverse from a 4x4 adjugate.  The returned id (>= MK_METRIC_PLUGIN_BASE) is accepted by
+ * mk_integrate, mk_integrate_paged, mk_rhs, mk_rk4_step, mk_metric and mk_initial_condition_metric; the
+ * `bhspin` argument of those calls becomes UserMetric::params[0], params[1..7] come from
+ * mk_metric_set_params.  Compilation needs no GPU.  log (optional) receives the compiler log.
+ */
+int mk_register_metric(const char* name, const char* source, const char* include_dir, int* metric_id,
+                       char* log, long log_capacity);
+int mk_metric_set_params(int metric_id, const double* params8);
+/* geodesics.py:219-230 initial_condition with the selected spacetime (built-in ids use Kerr-Schild) */
+int mk_initial_condition_metric(int metric_id, double bhspin, const double* s0_x, const double* s0_v, long n,
+                                double* s0, void* stream);
 
 /* ---- camera: geodesics.py:29-55 initialize_geodesics_at_camera ------------------------------- */
 /* 'grid' camera (geodesics.py:158-181 + :219-230): s0 (n*n, 8) = [t,x,y,z,k^t,k^x,k^y,k^z], pixel

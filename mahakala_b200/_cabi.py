@@ -17,6 +17,9 @@ SIGNATURES = {
     "mk_abi_version": "",
     "mk_device_info": "ppppp",
     "mk_measure_fp64_peak": "ipp",
+    "mk_register_metric": "pppppl",
+    "mk_metric_set_params": "ip",
+    "mk_initial_condition_metric": "idpplpp",
     "mk_camera_grid": "ddddddlipp",
     "mk_camera_points": "ddddpplipp",
     "mk_initial_condition": "dpplpp",
@@ -91,6 +94,8 @@ def _ptr(x):
         return ctypes.c_void_p(x.data_ptr())
     if isinstance(x, ctypes.c_void_p):
         return x
+    if isinstance(x, bytes):
+        return ctypes.cast(ctypes.c_char_p(x), ctypes.c_void_p)
     if isinstance(x, (ctypes._SimpleCData, ctypes.Array, ctypes.Structure)):
         return ctypes.cast(ctypes.pointer(x), ctypes.c_void_p)
     if type(x).__name__ == "CArgObject":      # ctypes.byref(...)

@@ -6,6 +6,7 @@
 #include "integrate.cuh"
 #include "ks_metric.cuh"
 #include "metric_plugin.cuh"
+#include "plugin.cuh"
 #include "../../include/mahakala_b200.h"
 
 namespace mk {
@@ -199,6 +200,9 @@ extern "C" int mk_rhs(int metric_id, double bhspin, const double* state, long n,
     } else if (metric_id == MK_METRIC_KERR_SCHILD_DUAL) {
         DualMetric<KerrSchildFn> g; g.fn.a = bhspin; g.rH = 0;
         rhs_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(g, state, n, out);
+    } else if (metric_id >= MK_METRIC_PLUGIN_BASE) {
+        void* extra[] = {&state, &n, &out};
+        return plugin_elementwise(metric_id, bhspin, "mk_plugin_rhs", extra, 3, n, (cudaStream_t)stream);
     } else {
         set_error("unknown metric id %d", metric_id);
         return 2;
@@ -224,6 +228,10 @@ extern "C" int mk_rk4_step(int metric_id, double bhspin, const double* state, co
 {
     if (n <= 0) return 0;
     MK_REQUIRE(state && dt && out, "null pointer");
+    if (metric_id >= MK_METRIC_PLUGIN_BASE) {
+        void* extra[] = {&state, &dt, &n, &out};
+        return plugin_elementwise(metric_id, bhspin, "mk_plugin_rk4", extra, 4, n, (cudaStream_t)stream);
+    }
     unsigned blocks = (unsigned)((n + 127) / 128);
     MK_DISPATCH_METRIC(metric_id, bhspin, (rk4_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(g, state, dt, n, out)));
     MK_CUDA_CHECK(cudaGetLastError());
@@ -234,6 +242,10 @@ extern "C" int mk_metric(int metric_id, double bhspin, const double* x, long n, 
 {
     if (n <= 0) return 0;
     MK_REQUIRE(x != nullptr, "null pointer");
+    if (metric_id >= MK_METRIC_PLUGIN_BASE) {
+        void* extra[] = {&x, &n, &gc, &gi};
+        return plugin_elementwise(metric_id, bhspin, "mk_plugin_metric", extra, 4, n, (cudaStream_t)stream);
+    }
     unsigned blocks = (unsigned)((n + 127) / 128);
     MK_DISPATCH_METRIC(metric_id, bhspin, (metric_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(g, x, n, gc, gi)));
     MK_CUDA_CHECK(cudaGetLastError());

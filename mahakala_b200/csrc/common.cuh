@@ -1,6 +1,7 @@
 // Shared host-side helpers of libmahakala_b200.so (error reporting, launch geometry).
 #pragma once
 #include <cuda_runtime.h>
+#include "fp64_math.cuh"
 #include <cstdint>
 #include <cstdio>
 
@@ -26,7 +27,5 @@ unsigned int* queue_counter(cudaStream_t stream, int slot);   // zeroed device c
             return 2;                                                                              \
         }                                                                                          \
     } while (0)
-
-constexpr unsigned FULL_MASK = 0xffffffffu;
 
 }  // namespace mk

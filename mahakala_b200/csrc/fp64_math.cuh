@@ -6,9 +6,13 @@
 // far inside the 1e-9 trajectory tolerance; inputs on this path are normal, finite and positive
 // (radii, metric denominators), so the IEEE special-case handling of '/' and sqrt() is not needed.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 
 namespace mk {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
 
 __device__ __forceinline__ double rcp_seed(double x)
 {

@@ -1,0 +1,181 @@
+// Device-side body of the persistent integrate kernel (shared by the built-in kernels of integrate.cu and
+// by run-time compiled metric plugins, plugin_tu.cuh).  NVRTC-safe: no host code, no standard headers.
+//
+// Replaces /root/reference/mahakala/geodesics.py:233-281 (geodesic_integrator) and the last-point
+// rule of :370-378.  One ray per lane, state in registers.  The kernel is persistent: each warp pulls
+// rays from a global queue and REFILLS lanes whose ray has frozen (ballot + one atomic per refill), so
+// warps stay full although step counts vary ~5x across the image (photon ring).
+#pragma once
+#include "integrate.cuh"
+
+namespace mk {
+
+struct IntegrateArgs {
+    const double* s0;      // (npx, 8)
+    long npx;
+    int N;                 // iteration cap (rows of the reference's scan)
+    StepRule rule;
+    double* final_state;   // (npx, 8) or null
+    int* nsteps;              // (npx,) or null
+    double* r_last;        // (npx,) or null : radius_cal(S[argmax(dt) - 1]) with the reference's negative wrap
+    double* S;             // dump: (nrows, npx, 8) or null
+    double* dt;            // dump: (nrows, npx)
+    long nrows;
+    unsigned int* queue;   // zero-initialised ray counter
+    unsigned long long* total_steps;  // optional global sum of accepted steps
+    // paged dump (single pass, ragged): page p = [PAGE_ROWS][8] states followed by [PAGE_ROWS] dts
+    double* pages;
+    int* page_next;        // (max_pages,) next page of the same ray or -1
+    int* page_first;       // (npx,) first page of each ray
+    unsigned int* page_counter;
+    unsigned int max_pages;
+    int* overflow;         // set to 1 when the page pool is exhausted
+};
+
+constexpr int PAGE_ROWS = 32;
+constexpr int PAGE_DOUBLES = PAGE_ROWS * 9;
+constexpr unsigned PAGE_SLAB = 64;       // pages a warp takes from the global pool per atomic
+enum { MODE_FINAL = 0, MODE_PADDED = 1, MODE_PAGED = 2 };
+
+template <class Metric, int MODE>
+__device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateArgs& A)
+{
+    constexpr bool DUMP = (MODE == MODE_PADDED);
+    unsigned slab_next = 0, slab_end = 0;      // warp-uniform page slab (MODE_PAGED)
+    int page = -1;
+    const unsigned lane = threadIdx.x & 31u;
+    long ray = -1;
+    bool drained = false;           // queue exhausted (warp-uniform)
+    double s[8];
+    double dt = 0.0, r_cur = 0.0, r_prev = 0.0;
+    typename Metric::Cache cache, cache_new;
+    double best_dt = 0.0, r_before_best = 0.0;
+    int it = 0, best_idx = -1;
+    unsigned long long my_steps = 0;
+
+    for (;;) {
+        // ---- refill idle lanes from the queue ----
+        unsigned idle = __ballot_sync(FULL_MASK, ray < 0);
+        if (idle) {
+            if (!drained) {
+                int cnt = __popc(idle);
+                unsigned base = 0;
+                int leader = __ffs(idle) - 1;
+                if ((int)lane == leader) base = atomicAdd(A.queue, (unsigned)cnt);
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if ((long)base + cnt >= A.npx) drained = true;
+                if (ray < 0) {
+                    long idx = (long)base + __popc(idle & ((1u << lane) - 1u));
+                    if (idx < A.npx) {
+                        ray = idx;
+                        const double4* p = reinterpret_cast<const double4*>(A.s0 + idx * 8);
+                        double4 lo = p[0], hi = p[1];
+                        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+                        s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+                        r_cur = g.radius(s, cache);
+                        dt = A.rule(r_cur);
+                        r_prev = r_cur;
+                        it = 0; best_idx = -1; best_dt = -1.0e300; r_before_best = r_cur;
+                        page = -1;
+                    }
+                }
+            }
+            if (__ballot_sync(FULL_MASK, ray >= 0) == 0) break;
+        }
+        const bool act = ray >= 0;
+
+        // ---- paged dump: lanes starting a new page take one from the warp's slab ----
+        if (MODE == MODE_PAGED) {
+            bool need = act && ((it & (PAGE_ROWS - 1)) == 0);
+            unsigned nm = __ballot_sync(FULL_MASK, need);
+            if (nm) {
+                unsigned cnt = (unsigned)__popc(nm);
+                if (slab_next + cnt > slab_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(A.page_counter, PAGE_SLAB);
+                    slab_next = __shfl_sync(FULL_MASK, base, 0);
+                    slab_end = slab_next + PAGE_SLAB;
+                }
+                if (need) {
+                    unsigned np = slab_next + (unsigned)__popc(nm & ((1u << lane) - 1u));
+                    if (np < A.max_pages) {
+                        if (it == 0) A.page_first[ray] = (int)np;
+                        else if (page >= 0) A.page_next[page] = (int)np;
+                        A.page_next[np] = -1;
+                        page = (int)np;
+                    } else {
+                        *A.overflow = 1;
+                        if (it == 0) A.page_first[ray] = -1;
+                        page = -1;
+                    }
+                }
+                slab_next += cnt;
+            }
+        }
+        if (!act) continue;
+
+        // ---- one iteration of geodesic_step ----
+        double cand[8];
+        double r_new = 0.0, dtn = 0.0;
+        if (dt != 0.0) {
+            rk4_step(g, s, dt, cand, &cache);
+            r_new = g.radius(cand, cache_new);
+            dtn = A.rule(r_new);
+        }
+        bool frozen = (dt == 0.0) || (dtn == 0.0);
+        if (DUMP) {
+            if (it < A.nrows) {
+                double4* p = reinterpret_cast<double4*>(A.S + ((long)it * A.npx + ray) * 8);
+                p[0] = make_double4(s[0], s[1], s[2], s[3]);
+                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+                A.dt[(long)it * A.npx + ray] = frozen ? 0.0 : dt;
+            }
+        }
+        if (MODE == MODE_PAGED) {
+            if (page >= 0) {
+                double* pg = A.pages + (long)page * PAGE_DOUBLES;
+                int rr = it & (PAGE_ROWS - 1);
+                double4* p = reinterpret_cast<double4*>(pg + rr * 8);
+                p[0] = make_double4(s[0], s[1], s[2], s[3]);
+                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+                pg[PAGE_ROWS * 8 + rr] = frozen ? 0.0 : dt;
+            }
+        }
+        bool done = frozen;
+        // geodesics.py:373: argmax(dt) is the first zero row (= it) unless some step size was positive (a ray
+        // that jumped inside the horizon steps with dt > 0); the classifier row is argmax - 1, and -1 wraps to
+        // the last row, a copy of the frozen state.
+        double rl = (best_dt > 0.0) ? ((best_idx >= 1) ? r_before_best : r_cur) : ((it >= 1) ? r_prev : r_cur);
+        if (!frozen) {
+            if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
+            r_prev = r_cur; r_cur = r_new;
+            cache = cache_new;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] = cand[i];
+            dt = dtn;
+            it++;
+            if (it == A.N) {                        // never froze: argmax over the negative dts (:373)
+                done = true;
+                rl = (best_idx >= 1) ? r_before_best : r_prev;
+            }
+        }
+        if (done) {
+            if (A.final_state) {
+                double4* p = reinterpret_cast<double4*>(A.final_state + ray * 8);
+                p[0] = make_double4(s[0], s[1], s[2], s[3]);
+                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+            }
+            if (A.nsteps) A.nsteps[ray] = it;
+            if (A.r_last) A.r_last[ray] = rl;
+            my_steps += (unsigned long long)it;
+            ray = -1;
+        }
+    }
+    if (A.total_steps) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(FULL_MASK, my_steps, o);
+        if (lane == 0 && my_steps) atomicAdd(A.total_steps, my_steps);
+    }
+}
+
+}  // namespace mk

@@ -26,6 +26,37 @@ def set_metric(name):
     return _active_metric
 
 
+def register_metric(name, cuda_source, params=None):
+    """Register a user-defined spacetime at run time and return its metric id.
+
+    ``cuda_source`` is CUDA C++ defining ``struct UserMetric`` (contract: ``csrc/plugin_tu.cuh``): the
+    covariant metric evaluated on a generic scalar type, the step-rule radius and the horizon radius.  NVRTC
+    compiles it for sm_100a together with the integrate kernel; derivatives come from forward-mode dual
+    numbers (the role ``jax.jacfwd`` plays at geodesics.py:305).  ``params`` (up to 7 floats) fill
+    ``UserMetric::params[1..7]``; ``params[0]`` is the ``bhspin`` argument of each call.  Select it with
+    ``set_metric(name)``.  Compilation itself needs no GPU.
+    """
+    import ctypes
+    import os
+    mid = ctypes.c_int(-1)
+    log = ctypes.create_string_buffer(8192)
+    inc = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+    _cabi.call("mk_register_metric", name.encode(), cuda_source.encode(), inc.encode(), ctypes.byref(mid), log, 8192)
+    _METRICS[name] = mid.value
+    if params is not None:
+        set_metric_params(name, params)
+    return mid.value
+
+
+def set_metric_params(name, params):
+    """Set ``UserMetric::params[1..7]`` of a registered spacetime."""
+    import ctypes
+    mid = _METRICS[name] if isinstance(name, str) else int(name)
+    vals = [0.0] + [float(q) for q in params]
+    vals += [0.0] * (8 - len(vals))
+    _cabi.call("mk_metric_set_params", mid, (ctypes.c_double * 8)(*vals[:8]))
+
+
 def _cos_sin_deg(inclination):
     i = inclination * np.pi / 180          # geodesics.py:205
     return float(np.cos(i)), float(np.sin(i))
@@ -96,7 +127,7 @@ def initial_condition(s0_x, s0_v, bhspin):
     sv = as_device(s0_v)
     n = sx.shape[1]
     s0 = empty((n, 8))
-    _cabi.call("mk_initial_condition", float(bhspin), sx, sv, n, s0, stream_ptr())
+    _cabi.call("mk_initial_condition_metric", _active_metric, float(bhspin), sx, sv, n, s0, stream_ptr())
     return DeviceArray.wrap(s0)
 
 

@@ -186,3 +186,99 @@ def test_golden_shadows_through_dropin_api(ma, golden_shadows):
         assert np.allclose(radii, c["radii"], rtol=1e-2), key
     ang, rad = ma.find_shadow_bisection(0.5, 45, 12)
     assert ang.shape == rad.shape == (13,) and rad[0] == rad[-1]
+
+
+KERR_SCHILD_USER = r"""
+// the reference's metric (geodesics.py:95-104) typed by a "user": spin = params[0] (the bhspin argument)
+struct UserMetric {
+    double params[8];
+    template <class T> __device__ void operator()(const T x[4], T g[4][4]) const {
+        const double a = params[0], aa = a * a;
+        T zz = x[3] * x[3];
+        T kk = 0.5 * (x[1] * x[1] + x[2] * x[2] + zz - aa);
+        T rr = mk_sqrt(kk * kk + aa * zz) + kk;
+        T r = mk_sqrt(rr);
+        T f = (2.0 * rr * r) / (rr * rr + aa * zz);
+        T l[4];
+        l[0] = T(1.0);
+        l[1] = (r * x[1] + a * x[2]) / (rr + aa);
+        l[2] = (r * x[2] - a * x[1]) / (rr + aa);
+        l[3] = x[3] / r;
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+                T e = f * (l[i] * l[j]);
+                g[i][j] = (i == j) ? e + (i == 0 ? -1.0 : 1.0) : e;
+            }
+    }
+    __device__ double radius(const double x[4]) const {
+        const double aa = params[0] * params[0];
+        double w = x[1] * x[1] + x[2] * x[2] + x[3] * x[3] - aa;
+        return sqrt((w + sqrt(w * w + 4.0 * aa * x[3] * x[3])) / 2.0);
+    }
+    __device__ double horizon() const { return 1.0 + sqrt(1.0 - params[0] * params[0]); }
+};
+"""
+
+MINKOWSKI_USER = r"""
+struct UserMetric {
+    double params[8];
+    template <class T> __device__ void operator()(const T x[4], T g[4][4]) const {
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) g[i][j] = T((i == j) ? (i == 0 ? -1.0 : 1.0) : 0.0) + 0.0 * x[1];
+    }
+    __device__ double radius(const double x[4]) const { return sqrt(x[1] * x[1] + x[2] * x[2] + x[3] * x[3]); }
+    __device__ double horizon() const { return params[1]; }
+};
+"""
+
+
+def test_user_registered_metrics(ma):
+    """Run-time registered spacetimes: the reference's own metric typed as a user plugin reproduces the oracle
+    (which differentiates the same expression with jets); flat space gives straight lines."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    from mahakala_b200 import geodesics as geo
+    from test_host_cpu import SCHWARZSCHILD_KS
+    geo.register_metric("ks_user", KERR_SCHILD_USER)
+    geo.register_metric("schw_user", SCHWARZSCHILD_KS, params=[1.0])
+    geo.register_metric("flat_user", MINKOWSKI_USER, params=[2.0])
+    try:
+        s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 16)
+        geo.set_metric("ks_user")
+        x, v = onp.get_initial_grid(60, 1000, -10, 10, 16, 'grid')
+        assert np.allclose(np.asarray(geo.initial_condition(x, v, A)), s0, rtol=1e-13)
+        ref = onp.rhs(s0, A)
+        assert (np.abs(np.asarray(geo.rhs(s0, A)) - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-12
+        assert np.allclose(np.asarray(geo.imetric(s0[:, :4], A)), onp.imetric(s0[:, :4], A), rtol=1e-10, atol=1e-12)
+        f, n, rl = geo.integrate_final(2000, s0, 40, 1e-2, A)
+        o = c_oracle.integrate(2000, s0, 40, 1e-2, A)
+        cap = np.asarray(rl.cpu()) < 100
+        assert np.array_equal(cap, o["r_last"] < 100)
+        esc = ~cap
+        assert np.array_equal(np.asarray(n.cpu())[esc], o["nsteps"][esc])
+        err = np.abs(np.asarray(f.cpu())[esc] - o["final"][esc]) / np.abs(o["final"][esc]).max()
+        assert err.max() < 2e-8
+        S, dt = ma.geodesic_integrator(2000, s0[:40], 40, 1e-2, A)       # padded dump through the plugin
+        Sr, dtr = c_oracle.geodesic_integrator(2000, s0[:40], 40, 1e-2, A)
+        assert np.asarray(S).shape == Sr.shape and np.array_equal(np.asarray(dt) == 0, dtr == 0)
+        st = geo.integrate_paged(2000, s0[:40], 40, 1e-2, A)             # paged dump through the plugin
+        Sp, dtp = st.padded()
+        assert np.array_equal(np.asarray(Sp), np.asarray(S))
+        # Schwarzschild plugin (M = 1) == Kerr-Schild with a = 0
+        geo.set_metric("schw_user")
+        s00 = onp.initialize_geodesics_at_camera(0.0, 60, 1000, -10, 10, 12)
+        f1, n1, rl1 = geo.integrate_final(2000, s00, 40, 1e-2, 0.0)
+        geo.set_metric("kerr_schild")
+        f0, n0, rl0 = geo.integrate_final(2000, s00, 40, 1e-2, 0.0)
+        assert np.array_equal(np.asarray(rl1.cpu()) < 100, np.asarray(rl0.cpu()) < 100)
+        e = (np.asarray(rl0.cpu()) >= 100)
+        assert np.allclose(np.asarray(f1.cpu())[e], np.asarray(f0.cpu())[e], rtol=1e-7)
+        # flat space: straight lines x = x0 + k * lambda, k unchanged; cut-off radius params[1] = 2
+        geo.set_metric("flat_user")
+        ff, nf, _ = geo.integrate_final(400, s00, 40, 1e-2, 0.0)
+        ff = np.asarray(ff.cpu())
+        assert np.allclose(ff[:, 4:], s00[:, 4:], rtol=0, atol=1e-15)
+        lam = (ff[:, 1] - s00[:, 1]) / s00[:, 5]
+        assert np.allclose(ff[:, 1:4], s00[:, 1:4] + lam[:, None] * s00[:, 5:8], rtol=1e-12, atol=1e-9)
+        assert np.allclose(ff[:, 0], lam * s00[:, 4], rtol=1e-12, atol=1e-9)
+    finally:
+        geo.set_metric("kerr_schild")

@@ -140,3 +140,36 @@ def test_device_array_numpy_protocol():
     assert np.allclose(t, [[0, 1, 2], [3, 4, 5]])
     assert isinstance(t[0], DeviceArray) and np.asarray(t * t)[1, 2] == 25.0
     assert np.where(np.asarray(t) > 2)[0].tolist() == [1, 1, 1]
+
+
+SCHWARZSCHILD_KS = r"""
+// Schwarzschild in Kerr-Schild coordinates with mass M = params[1]: g = eta + (2M/r) l l, l = (1, x/r, y/r, z/r)
+struct UserMetric {
+    double params[8];
+    template <class T> __device__ void operator()(const T x[4], T g[4][4]) const {
+        const double M = params[1];
+        T r = mk_sqrt(x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+        T f = (2.0 * M) / r;
+        T l[4];
+        l[0] = T(1.0); l[1] = x[1] / r; l[2] = x[2] / r; l[3] = x[3] / r;
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+                T e = f * (l[i] * l[j]);
+                g[i][j] = (i == j) ? e + (i == 0 ? -1.0 : 1.0) : e;
+            }
+    }
+    __device__ double radius(const double x[4]) const { return sqrt(x[1] * x[1] + x[2] * x[2] + x[3] * x[3]); }
+    __device__ double horizon() const { return 2.0 * params[1]; }
+};
+"""
+
+
+def test_user_metric_compiles_without_gpu(built):
+    """NVRTC compiles a user-registered spacetime for sm_100a on a CPU-only host; errors carry the log."""
+    from mahakala_b200 import _cabi, geodesics as geo
+    mid = geo.register_metric("schwarzschild_ks_cpu_test", SCHWARZSCHILD_KS, params=[1.0])
+    assert mid >= 16 and geo._METRICS["schwarzschild_ks_cpu_test"] == mid
+    with pytest.raises(_cabi.MahakalaB200Error, match="compilation of metric"):
+        geo.register_metric("broken", "struct UserMetric { double params[8]; this is not C++ };")
+    with pytest.raises(_cabi.MahakalaB200Error, match="unknown metric id"):
+        _cabi.call("mk_metric_set_params", 999, (__import__("ctypes").c_double * 8)())
