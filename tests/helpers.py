@@ -28,3 +28,70 @@ def device_model(arr, bhspin, **kw):
 def close(a, b, rtol, atol):
     a = np.asarray(a); b = np.asarray(b)
     return np.all(np.abs(a - b) <= atol + rtol * np.abs(b))
+
+
+def two_level_mesh(n=8, seed=0, fluid_gamma=13. / 9):
+    """A two-level AthenaK-style mesh: 2x2x2 root blocks of n^3 cells on [-8, 8]^3, the root block at logical
+    location (1, 1, 1) replaced by its 8 children (level 1).  Fields come from one global fine-resolution
+    array F (level-1 cells) and its 2x2x2 restriction C (level-0 cells), so that the expected ghost cells of
+    every block follow from plain indexing of F and C (brute-force oracle for the AMR ghost fill).
+
+    Returns (arrays dict for from_arrays, expected all_meshblocks).
+    """
+    rng = np.random.default_rng(seed)
+    nf = 4 * n                       # fine cells per side over the whole domain
+    F = np.empty((8, nf, nf, nf))
+    zz, yy, xx = np.meshgrid(*(3 * [(-8 + (np.arange(nf) + 0.5) * 16.0 / nf)]), indexing='ij')
+    from mahakala_b200.synthetic import torus_fields
+    fl = torus_fields(xx, yy, zz, fluid_gamma=fluid_gamma, R0=4.0, R_in=1.0)
+    order = [0, 1, 2, 3, 4, 5, 6, 7]          # dens, velx, vely, velz, eint, b1, b2, b3 (uov then B)
+    for q in range(8):
+        F[q] = fl[order[q]] * (1.0 + 0.05 * rng.standard_normal((nf, nf, nf)))
+    F = F.astype(np.float32).astype(np.float64)
+    C = F.reshape(8, nf // 2, 2, nf // 2, 2, nf // 2, 2).mean(axis=(2, 4, 6))
+    blocks = []                      # (level, li, lj, lk)
+    for lk in range(2):
+        for lj in range(2):
+            for li in range(2):
+                if (li, lj, lk) != (1, 1, 1):
+                    blocks.append((0, li, lj, lk))
+    for lk in range(2, 4):
+        for lj in range(2, 4):
+            for li in range(2, 4):
+                blocks.append((1, li, lj, lk))
+    nmb = len(blocks)
+    uov = np.empty((5, nmb, n, n, n)); B = np.empty((3, nmb, n, n, n))
+    xv = [np.empty((nmb, n)) for _ in range(3)]
+    xf = [np.empty((nmb, n + 1)) for _ in range(3)]
+    expected = np.zeros((nmb, 8, n + 2, n + 2, n + 2))
+
+    def sample_global(level, gk, gj, gi):
+        """value of the mesh at global cell (gk, gj, gi) of `level`, as a block of that level would see it"""
+        size = 2 * n * (2 ** level)
+        if not (0 <= gk < size and 0 <= gj < size and 0 <= gi < size):
+            return None
+        if level == 0:
+            return C[:, gk, gj, gi]          # refined region: average of the 8 children = C by construction
+        refined = gk >= nf // 2 and gj >= nf // 2 and gi >= nf // 2
+        return F[:, gk, gj, gi] if refined else C[:, gk // 2, gj // 2, gi // 2]
+
+    for mb, (lev, li, lj, lk) in enumerate(blocks):
+        dx = 16.0 / (2 * n * 2 ** lev)
+        src = C if lev == 0 else F
+        for ax, l in enumerate((li, lj, lk)):
+            f = -8 + (l * n + np.arange(n + 1)) * dx
+            xf[ax][mb] = f
+            xv[ax][mb] = f[:-1] + dx / 2
+        blk = src[:, lk * n:(lk + 1) * n, lj * n:(lj + 1) * n, li * n:(li + 1) * n]
+        uov[:, mb] = blk[:5]
+        B[:, mb] = blk[5:]
+        for k in range(n + 2):
+            for j in range(n + 2):
+                for i in range(n + 2):
+                    v = sample_global(lev, lk * n + k - 1, lj * n + j - 1, li * n + i - 1)
+                    if v is not None:
+                        expected[mb, :, k, j, i] = v
+    arr = dict(uov=uov, B=B, x1v=xv[0], x2v=xv[1], x3v=xv[2], x1f=xf[0], x2f=xf[1], x3f=xf[2],
+               LogicalLocations=np.array([[b[1], b[2], b[3]] for b in blocks]), Levels=np.array([b[0] for b in blocks]),
+               VariableNames=('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'), fluid_gamma=fluid_gamma)
+    return arr, expected

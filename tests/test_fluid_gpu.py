@@ -191,3 +191,31 @@ def test_distributed_render_two_ranks(built):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mode=queue: identical to single-GPU image: True" in r.stdout
     assert "mode=static: identical to single-GPU image: True" in r.stdout
+
+
+def test_two_level_mesh_sampling(built):
+    """Level-aware O(1) block lookup + sampling on a refined mesh, against the oracle's linear scan."""
+    from helpers import two_level_mesh
+    from oracle import c_oracle, mahakala_oracle as onp
+    arr, expected = two_level_mesh(n=8)
+    dm = device_model(arr, A)
+    om = oracle_model(arr, A)
+    om.all_meshblocks = expected                      # brute-force ghost cells (tests/helpers.py)
+    assert np.abs(dm.all_meshblocks - expected).max() < 1e-15
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-8.5, 8.5, (4000, 3))
+    faces = np.array([-8.0, -4.0, 0.0, 2.0, 4.0, 6.0, 8.0])        # points exactly on coarse and fine faces
+    pts[:600] = rng.choice(faces, (600, 3))
+    pts[600:900, 0] = rng.choice(faces, 300)
+    S = np.concatenate([np.zeros((4000, 1)), pts, np.ones((4000, 1)), rng.normal(0, 0.5, (4000, 3))], 1)[None]
+    ref = c_oracle.sample(om, S, mode="prims")
+    for lookup in ("grid", "scan"):
+        m = device_model(arr, A, lookup=lookup, storage="f64")
+        got = m.get_prims_from_geodesics(S)
+        for k in ref:
+            g = np.asarray(got[k])
+            assert np.array_equal(g == 0, ref[k] == 0), (lookup, k)
+            assert np.allclose(g, ref[k], rtol=1e-13, atol=1e-300), (lookup, k)
+        m.release()
+    mb_ref = om._meshblock_indices(S)[0]
+    assert set(np.unique(mb_ref)) == set(range(-1, 15))            # every block (and "outside") is exercised

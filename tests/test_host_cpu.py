@@ -173,3 +173,19 @@ def test_user_metric_compiles_without_gpu(built):
         geo.register_metric("broken", "struct UserMetric { double params[8]; this is not C++ };")
     with pytest.raises(_cabi.MahakalaB200Error, match="unknown metric id"):
         _cabi.call("mk_metric_set_params", 999, (__import__("ctypes").c_double * 8)())
+
+
+def test_amr_ghost_fill_two_levels_bruteforce(built):
+    """Ghost cells across a refinement boundary (athenak.py:231-514): coarser neighbour -> injection, finer
+    neighbour -> average of the 8 children.  Checked against plain indexing of global fine / coarse arrays."""
+    from helpers import two_level_mesh
+    from mahakala_b200.grmhd.athenak import build_block_grid, fill_ghost_zones
+    arr, expected = two_level_mesh(n=8)
+    amb, index = fill_ghost_zones(arr["uov"], arr["B"], arr["LogicalLocations"], arr["Levels"])
+    assert amb.shape == expected.shape == (15, 8, 10, 10, 10)
+    assert np.abs(amb - expected).max() < 1e-15
+    assert (expected[:, 0] > 0).sum() > 0.7 * expected[:, 0].size     # only domain-boundary ghosts stay zero
+    grid, gn, g0, ginv = build_block_grid(arr["x1f"], arr["x2f"], arr["x3f"])
+    assert grid.shape == (4, 4, 4) and (grid >= 0).all()
+    assert len(set(grid[:2].ravel()) | set(grid[:, :2].ravel()) | set(grid[:, :, :2].ravel())) == 7   # 7 coarse blocks
+    assert len(set(grid[2:, 2:, 2:].ravel())) == 8                                                     # 8 fine blocks
