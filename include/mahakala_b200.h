@@ -124,7 +124,7 @@ typedef struct mk_snapshot mk_snapshot;   /* opaque; owns the repacked, device-r
  * Repack a ghost-padded AthenaK-style snapshot for sampling (replaces the per-call upload of
  * athenak.py:693).  Inputs are DEVICE arrays:
  *   meshblocks (nmb, 8, nk+2, nj+2, ni+2)   the reference's self.all_meshblocks (athenak.py:105-158)
- *   geom (12, nmb)  rows: x1f[0], x2f[0], x3f[0], x1f[-1], x2f[-1], x3f[-1], x1v[0], x2v[0], x3v[0],
+ *   geom (nmb, 12)  per block: x1f[0], x2f[0], x3f[0], x1f[-1], x2f[-1], x3f[-1], x1v[0], x2v[0], x3v[0],
  *                         dx1, dx2, dx3   (dx = x_v[1] - x_v[0], athenak.py:686-691)
  *   grid (gn[2], gn[1], gn[0]) int32 block-lookup table over the bounding box, or NULL for the
  *        reference's linear scan (athenak.py:663-670); cell (c0,c1,c2) covers

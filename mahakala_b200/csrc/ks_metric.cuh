@@ -109,23 +109,23 @@ struct KerrSchild {
         double aaz = aa * Z;
         double g1 = t * X, g2 = t * Y, g3 = fma(t, Z, rid * aaz);
         double Dr = fma(v1, g1, fma(v2, g2, v3 * g3));      // v . grad r
-        // d_i l_j = g_i c_j + (constant part);  c = ((x - 2 r l1)/q, (y - 2 r l2)/q, -z/r^2)
+        // d_i l_j = g_i c_j + k_ij with c = ((x - 2 r l1)/q, (y - 2 r l2)/q, -z/r^2) and the constant parts
+        // k_xx = k_yy = r/q, k_xy = -k_yx = -a/q (i.e. d_x l_2 = -a/q, d_y l_1 = a/q), k_zz = 1/r.
         double r2 = r + r;
         double c1 = fma(-r2, l1, X) * iq;
         double c2 = fma(-r2, l2, Y) * iq;
         double c3 = -(l3 * ri);
         double cv = fma(c1, v1, fma(c2, v2, c3 * v3));
-        double e1 = fma(r, v1, -a * v2) * iq;               // sum_j (const part of d_i l_j) v^j
-        double e2 = fma(a, v1, r * v2) * iq;
-        double e3 = v3 * ri;
-        double h1 = fma(r, v1, a * v2) * iq;                // v^i (const part of d_i l_j)
-        double h2 = fma(r, v2, -a * v1) * iq;
-        // D l_j = v . grad l_j ;  N_i = sum_j d_i l_j v^j ;  the force only needs N_i - D l_i
-        double Dl1 = fma(Dr, c1, h1), Dl2 = fma(Dr, c2, h2), Dl3 = fma(Dr, c3, e3);
-        double n1 = fma(g1, cv, e1) - Dl1;
-        double n2 = fma(g2, cv, e2) - Dl2;
-        double n3 = fma(g3, cv, e3) - Dl3;
-        double M = fma(Dl1, v1, fma(Dl2, v2, Dl3 * v3));    // sum_j D l_j v^j
+        double p1 = v1 * iq, p2 = v2 * iq;
+        // The force needs only  n_i = N_i - D l_i  (N_i = sum_j d_i l_j v^j, D l_i = v . grad l_i) and
+        // M = sum_j D l_j v^j.  The symmetric parts of k cancel in n_i and the antisymmetric part cancels in M:
+        //   n = (g1 cv - Dr c1 - 2a p2,  g2 cv - Dr c2 + 2a p1,  g3 cv - Dr c3)
+        //   M = Dr cv + (r/q)(v1^2 + v2^2) + v3^2 / r
+        double a2 = a + a;
+        double n1 = fma(g1, cv, fma(-Dr, c1, -a2 * p2));
+        double n2 = fma(g2, cv, fma(-Dr, c2, a2 * p1));
+        double n3 = fma(g3, cv, -Dr * c3);
+        double M = fma(Dr, cv, fma(r, fma(p1, v1, p2 * v2), (v3 * v3) * ri));
         // grad f = alpha grad r + beta delta_iz
         double alpha = rr * iden * fma(-4.0 * f, r, 6.0);
         double beta = -2.0 * f * iden * aaz;
@@ -133,10 +133,11 @@ struct KerrSchild {
         double L = fma(l1, v1, fma(l2, v2, fma(l3, v3, v0)));   // l_m v^m
         double K = fma(Df, L, f * M);
         double fL = f * L, hL2 = 0.5 * L * L;
+        double ah = alpha * hL2;
         // lower-index force w_m = -d_k g_ms v^k v^s + 1/2 d_m g_ks v^k v^s ;  w_0 = -K
-        double w1 = fma(-K, l1, fma(fL, n1, hL2 * (alpha * g1)));
-        double w2 = fma(-K, l2, fma(fL, n2, hL2 * (alpha * g2)));
-        double w3 = fma(-K, l3, fma(fL, n3, hL2 * fma(alpha, g3, beta)));
+        double w1 = fma(-K, l1, fma(fL, n1, ah * g1));
+        double w2 = fma(-K, l2, fma(fL, n2, ah * g2));
+        double w3 = fma(-K, l3, fma(fL, n3, fma(ah, g3, hL2 * beta)));
         // raise with g^mn = eta^mn - f l^m l^n
         double P = fma(l1, w1, fma(l2, w2, fma(l3, w3, K)));    // l^n w_n
         double fP = f * P;

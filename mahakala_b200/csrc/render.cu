@@ -50,8 +50,11 @@ struct RenderArgs {
 
 // Resident CTAs per SM, measured on B200 (scripts/variant_probe.py): 3 for one or two frequencies, 4 when
 // the per-frequency synchrotron work dominates (8 frequencies: 75.8 -> 67.0 ms on cfg4).
+#ifndef MK_RENDER_LO
+#define MK_RENDER_LO 3
+#endif
 template <int NF>
-__global__ void __launch_bounds__(128, (NF >= 4) ? 4 : 3) render_kernel(const RenderArgs A)
+__global__ void __launch_bounds__(128, (NF >= 4) ? 4 : MK_RENDER_LO) render_kernel(const RenderArgs A)
 {
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long my_steps = 0, my_samples = 0;

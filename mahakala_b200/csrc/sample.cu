@@ -118,11 +118,8 @@ extern "C" int mk_snapshot_create(long nmb, long nk, long nj, long ni, const dou
     v.source = 0;
     v.cells = s->cells; v.is_f32 = store_f32 ? 1 : 0;
     v.nmb = (int)nmb; v.nk = (int)nk; v.nj = (int)nj; v.ni = (int)ni;
+    v.geom = s->geom;
     for (int d = 0; d < 3; d++) {
-        v.lo[d] = s->geom + (0 + d) * nmb;
-        v.hi[d] = s->geom + (3 + d) * nmb;
-        v.v0[d] = s->geom + (6 + d) * nmb;
-        v.dx[d] = s->geom + (9 + d) * nmb;
         v.bbox_lo[d] = bbox_lo[d]; v.bbox_hi[d] = bbox_hi[d];
         v.gn[d] = grid ? gn[d] : 0;
         v.g0[d] = grid ? g0[d] : 0.0;

@@ -314,7 +314,7 @@ class AthenakFluidModel(DeviceSampledFluidModel):
                          self.x1f[:, -1], self.x2f[:, -1], self.x3f[:, -1],
                          self.x1v[:, 0], self.x2v[:, 0], self.x3v[:, 0],
                          self.x1v[:, 1] - self.x1v[:, 0], self.x2v[:, 1] - self.x2v[:, 0],
-                         self.x3v[:, 1] - self.x3v[:, 0]])
+                         self.x3v[:, 1] - self.x3v[:, 0]]).T.copy()        # (nmb, 12) records
         bbox_lo = (ctypes.c_double * 3)(self.x1f[:, 0].min(), self.x2f[:, 0].min(), self.x3f[:, 0].min())
         bbox_hi = (ctypes.c_double * 3)(self.x1f[:, -1].max(), self.x2f[:, -1].max(), self.x3f[:, -1].max())
         grid = None

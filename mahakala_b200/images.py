@@ -26,6 +26,16 @@ def _params_for(fluid_model, M_bh, mass_scale, r_high):
 
 
 _order_cache = {}
+_staging = {}
+
+
+def _pinned_staging(n):
+    """Reusable pinned host buffer for device -> host image copies (cudaHostAlloc costs milliseconds)."""
+    if n not in _staging:
+        if len(_staging) > 8:
+            _staging.clear()
+        _staging[n] = torch.empty((n,), dtype=torch.float64, pin_memory=True)
+    return _staging[n]
 
 
 def centre_out_patch_order(res, device):
@@ -102,9 +112,9 @@ def make_image(fluid_model, camera_inclination=60, camera_distance=1000,
     if hasattr(fluid_model, "snapshot"):
         img = render(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
                      (observing_frequency,), fov, resolution, max_nsteps)
-        host = torch.empty((resolution * resolution,), dtype=torch.float64, pin_memory=True)
+        host = _pinned_staging(resolution * resolution)
         host.copy_(img[0], non_blocking=False)
-        return host.numpy().reshape((resolution, resolution))
+        return host.numpy().copy().reshape((resolution, resolution))
     return make_image_unfused(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
                               observing_frequency, fov, resolution, max_nsteps, max_chunk_bytes)
 

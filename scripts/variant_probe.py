@@ -24,6 +24,10 @@ if "norender" not in tag:
     m.snapshot()
     torch.save({k: v for k, v in arr.items() if hasattr(v, "shape")}, "/tmp/snap.pt") if False else None
     print(tag, "render 1f ms", timeit(lambda: images.render(m, resolution=1024)))
+    m64 = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                        arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"], storage="f64")
+    print(tag, "render 1f f64-cells ms", timeit(lambda: images.render(m64, resolution=1024)))
+    m64.release()
     print(tag, "render 8f ms", timeit(lambda: images.render(m, resolution=1024, observing_frequencies=[43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9])))
 print(tag, "final ms", timeit(lambda: geo.integrate_final(10000, s0, 40, 1e-4, a)))
 store = geo.TrajectoryStore.allocate(s0.shape[0], 10000, mem_fraction=0.4)
