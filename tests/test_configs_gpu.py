@@ -92,7 +92,7 @@ def test_cfg2_bundle_1024_properties(ma):
     assert np.array_equal(cap, ref["r_last"] < 100)
     esc = ~cap
     err = np.abs(np.asarray(f.cpu())[idx][esc] - ref["final"][esc]) / np.maximum(np.abs(ref["final"][esc]), 1e-300)
-    assert np.median(err) < 1e-12 and err.max() < 5e-8
+    assert np.median(err) < 1e-12 and err.max() < 1e-9          # north-star tolerance
     assert np.array_equal(n_sub[esc], ref["nsteps"][esc])
     # null condition is conserved along escaped rays: g_mn k^m k^n ~ 0 at the final state
     g = np.asarray(geo.metric(np.asarray(f.cpu())[idx][esc][:, :4], A))

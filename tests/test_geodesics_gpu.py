@@ -87,9 +87,10 @@ def test_cfg1_grid_classification_and_states(ma):
     assert np.array_equal(nsteps[esc], ref["nsteps"][esc])
     assert abs(int(nsteps.sum()) - 2079364) <= 64     # captured rays may differ by a step in the chaotic tail
     err = _rel(final[esc], ref["final"][esc])
-    # tolerance: north_star asks 1e-9 relative; the oracle-vs-oracle noise floor is ~3e-9 (tests/test_oracle_pinning.py)
+    # tolerance: the north-star's 1e-9 relative on positions and momenta (measured: median 8e-15, max 2e-11,
+    # profiles/r01_parity_report.txt); captured rays end in a chaotic tail in every implementation
     assert np.median(err) < 1e-12
-    assert err.max() < 2e-8, err.max()
+    assert err.max() < 1e-9, err.max()
 
 
 def test_dump_mode_matches_oracle(ma):
