@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--res", type=int, default=1024, help="rays per side of the bundle (default: cfg2)")
     ap.add_argument("--snapshot-cells", type=int, default=256, help="cells per side of the cfg4 snapshot")
     ap.add_argument("--no-render", action="store_true", help="skip the cfg4 render leg")
+    ap.add_argument("--strong-res", type=int, default=4096,
+                    help="side of the large single image used for the strong-scaling render leg (cfg5-sized frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=341, help="side of the pixel sub-lattice timed on the CPU")
     return ap.parse_args()
@@ -392,29 +394,41 @@ def render_leg(args, rank, world, dev):
         t0 = time.perf_counter()
         host_img = images.make_image(model, camera_inclination=incl, resolution=res)
         e2e_times.append(1e3 * (time.perf_counter() - t0))
-    strong = None
-    if world > 1:
-        shared = multigpu.SharedImage(1, res * res)
+    def strong_leg(sres, reps):
+        """ONE i = 60 deg image of sres^2 pixels shared by all ranks (or the plain render at N = 1)."""
+        shared = multigpu.SharedImage(1, sres * sres) if world > 1 else None
         st = []
-        for it in range(2 + 3):
-            shared.reset()
+        for it in range(1 + reps):
             flush.fill_(it)
-            dist.barrier()
+            if world > 1:
+                shared.reset()
+                dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            images.render(model, camera_inclination=CFG2["inclination"], resolution=res, observing_frequencies=(230e9,),
-                          image_out=shared.image_ptr, queue=shared.queue_ptr)
+            if world > 1:
+                images.render(model, camera_inclination=CFG2["inclination"], resolution=sres,
+                              observing_frequencies=(230e9,), image_out=shared.image_ptr, queue=shared.queue_ptr)
+            else:
+                out = images.render(model, camera_inclination=CFG2["inclination"], resolution=sres,
+                                    observing_frequencies=(230e9,))
             e1.record()
             torch.cuda.synchronize()
-            dist.barrier()
-            if it >= 2:
+            if world > 1:
+                dist.barrier()
+            if it >= 1:
                 st.append(e0.elapsed_time(e1))
-        strong = float(np.mean(st))
-        flux = float(shared.local_view()[1].sum()) if rank == 0 else 0.0
-        dist.barrier()
-        shared.close()
-    t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong or 0.0, bcast_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            fl = float(shared.local_view()[1].sum()) if rank == 0 else 0.0
+            dist.barrier()
+            shared.close()
+        else:
+            fl = float(out.sum())
+        return float(np.mean(st)), fl
+
+    strong, flux = strong_leg(res, 3) if world > 1 else (0.0, 0.0)
+    strong_big, flux_big = strong_leg(args.strong_res, 2) if args.strong_res > 0 else (0.0, 0.0)
+    t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong, bcast_ms, strong_big], dtype=torch.float64, device=dev)
     w = torch.tensor([float(counters[0]), float(counters[1])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -427,10 +441,14 @@ def render_leg(args, rank, world, dev):
            "ray_steps_per_s": steps / (ms * 1e-3),
            "sampling_algorithmic_GBps": samples * (256 if model.storage == "f32" else 512) / (ms * 1e-3) / 1e9,
            "snapshot_bytes": model.snapshot_bytes(), "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
+    if args.strong_res > 0:
+        out["strong_scaling_large_image"] = {"resolution": args.strong_res, "ms": float(t[4]), "image_sum": flux_big,
+                                             "note": "ONE cfg5-sized frame rendered by all ranks together"}
     if world > 1:
         out["strong_scaling_single_image_ms"] = float(t[2])
         out["strong_scaling_note"] = ("one i=60 deg image split over all ranks: shared atomic tile queue + in-kernel "
-                                      "gather into rank 0 over NVLink (CUDA IPC), device-timed, max over ranks")
+                                      "gather into rank 0 over NVLink (CUDA IPC), device-timed, max over ranks; at 1024^2 "
+                                      "the floor is the serial latency of the longest photon-ring ray (~8 ms)")
         out["strong_image_sum"] = flux
         out["snapshot_broadcast_ms"] = float(t[3])
     return out
