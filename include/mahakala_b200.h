@@ -40,6 +40,9 @@ int mk_device_info(int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_kh
 /* DFMA microbenchmark: measured FP64 FMA throughput (TFLOP/s, 2 flop per FMA) of the current device.
    Synchronous.  Used as the roofline denominator of the integrator. */
 int mk_measure_fp64_peak(int iters, double* tflops_out, double* ms_out);
+/* evaluates the kernels' MUFU-seeded reciprocal, square root and reciprocal square root on x (n,) so that
+   their accuracy can be checked against IEEE results (positive normal inputs) */
+int mk_fast_math_probe(const double* x, long n, double* rcp, double* sqrt_out, double* rsqrt_out, void* stream);
 
 /* ---- user-registered spacetimes ------------------------------------------------------------------ */
 /*

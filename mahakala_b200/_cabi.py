@@ -17,6 +17,7 @@ SIGNATURES = {
     "mk_abi_version": "",
     "mk_device_info": "ppppp",
     "mk_measure_fp64_peak": "ipp",
+    "mk_fast_math_probe": "plpppp",
     "mk_register_metric": "pppppl",
     "mk_metric_set_params": "ip",
     "mk_initial_condition_metric": "idpplpp",

@@ -97,6 +97,17 @@ __global__ void rhs_kernel(Metric g, const double* state, long n, double* out)
     for (int m = 0; m < 4; m++) { out[i * 8 + m] = s[4 + m]; out[i * 8 + 4 + m] = acc[m]; }
 }
 
+__global__ void fast_math_probe_kernel(const double* x, long n, double* rcp, double* sq, double* rsq)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, r;
+    fast_sqrt_rsqrt(x[i], s, r);
+    rcp[i] = fast_rcp(x[i]);
+    sq[i] = s;
+    rsq[i] = r;
+}
+
 template <class Metric>
 __global__ void rk4_kernel(Metric g, const double* state, const double* dt, long n, double* out)
 {
@@ -290,5 +301,14 @@ extern "C" int mk_ipc_close(void* ptr)
 extern "C" int mk_ipc_free(void* ptr)
 {
     if (ptr) MK_CUDA_CHECK(cudaFree(ptr));
+    return 0;
+}
+
+extern "C" int mk_fast_math_probe(const double* x, long n, double* rcp, double* sq, double* rsq, void* stream)
+{
+    if (n <= 0) return 0;
+    MK_REQUIRE(x && rcp && sq && rsq, "null pointer");
+    fast_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, rcp, sq, rsq);
+    MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

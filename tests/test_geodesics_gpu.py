@@ -17,6 +17,23 @@ def _rel(a, b):
     return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
 
 
+def test_fast_math_accuracy(ma):
+    """The MUFU-seeded reciprocal / sqrt / rsqrt used inside the kernels stay within 2 ulp of IEEE results."""
+    import torch
+    from mahakala_b200 import _cabi
+    from mahakala_b200._device import as_device, empty, stream_ptr
+    rng = np.random.default_rng(0)
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-12), np.log(1e12), 200000)), rng.uniform(0.5, 2.0, 100000),
+                        [1.0, 2.0, 4.0, 0.25, 3.0, 1e-300, 1e300]])
+    xd = as_device(x)
+    rcp, sq, rsq = empty(x.shape), empty(x.shape), empty(x.shape)
+    _cabi.call("mk_fast_math_probe", xd, x.size, rcp, sq, rsq, stream_ptr())
+    ulp = lambda got, want: np.abs(np.asarray(got.cpu()) - want) / np.spacing(np.abs(want))
+    assert ulp(rcp, 1.0 / x).max() <= 2.0
+    assert ulp(sq, np.sqrt(x)).max() <= 2.0
+    assert ulp(rsq, 1.0 / np.sqrt(x)).max() <= 3.0
+
+
 def test_camera_grid_matches_oracle(ma):
     from oracle import mahakala_oracle as onp
     for (a, inc, res) in [(0.94, 60, 32), (0.0, 90, 8), (0.5, 17, 16)]:
@@ -86,7 +103,8 @@ def test_cfg1_grid_classification_and_states(ma):
     esc = ~cap
     assert np.array_equal(nsteps[esc], ref["nsteps"][esc])
     assert abs(int(nsteps.sum()) - 2079364) <= 64     # captured rays may differ by a step in the chaotic tail
-    err = _rel(final[esc], ref["final"][esc])
+    err = np.concatenate([np.abs(final[esc][:, :4] - ref["final"][esc][:, :4]).max(axis=1) / np.abs(ref["final"][esc][:, :4]).max(axis=1),
+                          np.abs(final[esc][:, 4:] - ref["final"][esc][:, 4:]).max(axis=1) / np.abs(ref["final"][esc][:, 4:]).max(axis=1)])
     # tolerance: the north-star's 1e-9 relative on positions and momenta (measured: median 8e-15, max 2e-11,
     # profiles/r01_parity_report.txt); captured rays end in a chaotic tail in every implementation
     assert np.median(err) < 1e-12
