@@ -10,6 +10,17 @@
 
 namespace mk {
 
+// 256-bit global store (STG.E.256 on sm_100): one instruction per 32 B instead of two 128-bit stores
+__device__ __forceinline__ void store_256(double* p, double a, double b, double c, double d)
+{
+#ifndef __CUDACC_RTC__
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else   // NVRTC 12.9's embedded ptxas rejects 256-bit vector accesses: two 128-bit stores for run-time plugins
+    reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
+    reinterpret_cast<double2*>(p)[1] = make_double2(c, d);
+#endif
+}
+
 struct IntegrateArgs {
     const double* s0;      // (npx, 8)
     long npx;
@@ -125,9 +136,9 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
         bool frozen = (dt == 0.0) || (dtn == 0.0);
         if (DUMP) {
             if (it < A.nrows) {
-                double4* p = reinterpret_cast<double4*>(A.S + ((long)it * A.npx + ray) * 8);
-                p[0] = make_double4(s[0], s[1], s[2], s[3]);
-                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+                double* p = A.S + ((long)it * A.npx + ray) * 8;
+                store_256(p, s[0], s[1], s[2], s[3]);
+                store_256(p + 4, s[4], s[5], s[6], s[7]);
                 A.dt[(long)it * A.npx + ray] = frozen ? 0.0 : dt;
             }
         }
@@ -135,9 +146,8 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
             if (page >= 0) {
                 double* pg = A.pages + (long)page * PAGE_DOUBLES;
                 int rr = it & (PAGE_ROWS - 1);
-                double4* p = reinterpret_cast<double4*>(pg + rr * 8);
-                p[0] = make_double4(s[0], s[1], s[2], s[3]);
-                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+                store_256(pg + rr * 8, s[0], s[1], s[2], s[3]);
+                store_256(pg + rr * 8 + 4, s[4], s[5], s[6], s[7]);
                 pg[PAGE_ROWS * 8 + rr] = frozen ? 0.0 : dt;
             }
         }
