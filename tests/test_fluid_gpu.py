@@ -219,3 +219,28 @@ def test_two_level_mesh_sampling(built):
         m.release()
     mb_ref = om._meshblock_indices(S)[0]
     assert set(np.unique(mb_ref)) == set(range(-1, 15))            # every block (and "outside") is exercised
+
+
+def test_odd_resolution_dead_centre_pixel_and_cap(setup):
+    """Reference quirk: with an odd resolution the centre pixel has a zero direction -> NaN
+    wavevector; such a ray never moves and contributes zero intensity.  Also the iteration cap N."""
+    import mahakala_b200 as ma
+    from mahakala_b200 import images
+    from oracle import c_oracle, mahakala_oracle as onp
+    om, dm = setup["om"], setup["dm"]
+    res = 9
+    s0 = np.asarray(ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, res))
+    ref_s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, res)
+    centre = (res // 2) * res + res // 2
+    assert np.isnan(s0[centre, 5:]).all() and np.isnan(ref_s0[centre, 5:]).all()
+    assert np.array_equal(np.isnan(s0), np.isnan(ref_s0))
+    units = om.get_units(M_BH, MASS_SCALE)
+    ref, nsteps, _ = c_oracle.render(om, ref_s0, units, [230e9])
+    img = images.make_image(dm, resolution=res)
+    assert img.shape == (res, res) and img[res // 2, res // 2] == 0.0 and ref[0][centre] == 0.0
+    assert np.allclose(img.reshape(-1), ref[0], rtol=1e-6, atol=1e-12 * ref[0].max())
+    # iteration cap: max_nsteps smaller than the natural ray length truncates the transfer integral identically
+    ref_cap, _, _ = c_oracle.render(om, ref_s0, units, [230e9], N=260)
+    img_cap = images.make_image(dm, resolution=res, max_nsteps=260)
+    assert np.allclose(img_cap.reshape(-1), ref_cap[0], rtol=1e-6, atol=1e-12 * ref[0].max())
+    assert not np.allclose(img_cap, img)
