@@ -124,12 +124,11 @@ __global__ void __launch_bounds__(128, (NF >= 4) ? 4 : MK_RENDER_LO) render_kern
                             double f, l[4], em[NF], ab[NF];
                             l[0] = 1.0;
                             A.g.fl(s, cache, f, l[1], l[2], l[3]);
-                            if (emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab)) {
+                            emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
 #pragma unroll
-                                for (int fq = 0; fq < NF; fq++) {
-                                    I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
-                                    T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
-                                }
+                            for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
+                                I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
+                                T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
                             }
                         }
                     }

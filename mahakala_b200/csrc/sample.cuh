@@ -372,8 +372,11 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
                                               const double* nu_obs, const double* inv_nu_obs, double em[NF],
                                               double ab[NF])
 {
+    // Straight-line code: every validity test only feeds the final select (invalid lanes may carry NaN/inf
+    // through the arithmetic, which is harmless on the GPU).  Early exits would make the compiler duplicate
+    // the copies of all loop-carried registers on every exit edge (~200 MOVs per sample in SASS).
     const double dens = prims[0], u = prims[1];
-    if (!(dens > 0.0 && u > 0.0)) return false;
+    bool valid = (dens > 0.0) & (u > 0.0);
     const double* U = prims + 2;
     const double* Bp = prims + 5;
     // ---- fluid frame (athenak.py:760-786) ----
@@ -401,56 +404,50 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     double kdotu = fma(s[4], ucov[0], fma(s[5], ucov[1], fma(s[6], ucov[2], s[7] * ucov[3])));
     double kdotb = fma(s[4], bcov[0], fma(s[5], bcov[1], fma(s[6], bcov[2], s[7] * bcov[3])));
     double bsq = fma(bcon[0], bcov[0], fma(bcon[1], bcov[1], fma(bcon[2], bcov[2], bcon[3] * bcov[3])));
-    if (!(bsq > 0.0) || !(kdotu < 0.0)) return false;
+    valid &= (bsq > 0.0) & (kdotu < 0.0);
     double b, ib;
     fast_sqrt_rsqrt(bsq, b, ib);
     double c = kdotb * ib * fast_rcp(-kdotu);                    // cos(pitch), athenak.py:789
     c = fmin(fmax(c, -1.0), 1.0);
     double sin2 = (1.0 - c) * (1.0 + c);
-    if (!(sin2 > 0.0)) return false;
+    valid &= (sin2 > 0.0);
     double sinp = fast_sqrt(sin2);
     // ---- plasma state (images.py:87-102, electrons.py:46-50) ----
     double idens = fast_rcp(dens);
     double sigma = bsq * idens;
-    if (sigma > P.sigma_cut) return false;
+    valid &= !(sigma > P.sigma_cut);
     double beta = C.g1x2 * u * (ib * ib);
     double b2 = beta * beta;
     double T_ratio = fma(P.r_high, b2, P.r_low) * fast_rcp(1.0 + b2);
     double Theta = C.theta_fac * u * idens * fast_rcp(fma(C.egm1, T_ratio, C.igm1));
-    if (!(Theta >= 0.3)) return false;
+    valid &= (Theta >= 0.3);
     // ---- synchrotron (transfer.py:56-81), invariant form ----
     double th2 = Theta * Theta;
     double nus = C.k_nus * b * th2 * sinp;
     double inus = fast_rcp(nus);
     double ith = fast_rcp(Theta);
     double pref = C.k_em * dens * nus * (ith * ith);
-    bool any = false;
 #pragma unroll
     for (int fq = 0; fq < NF; fq++) {
         double nu = -kdotu * nu_obs[fq];
         double X = nu * inus;
-        double e = 0.0, a = 0.0;
-        if (X <= 1.e12) {
-            double x13 = cbrt(X);
-            double x16 = fast_sqrt(x13);
-            double term = fma(x16 * x16, x16, P.two_11_12 * x16);
-            e = pref * (term * term) * exp(-x13);
-            double bx = C.k_bx * nu * ith;
-            double den = (bx < 2.e-3) ? bx * (1. / 24.) * fma(bx, fma(bx, 4. + bx, 12.), 24.) : exp(bx) - 1.0;
-            double inu = fast_rcp(nu);
-            a = e * den * C.k_ab * (inu * inu * inu);
-            double rn = nu * inv_nu_obs[fq];
-            double irn = fast_rcp(rn);
-            e = e * (irn * irn);
-            a = a * rn;
-            if (!(e == e)) e = 0.0;
-            if (!(a == a)) a = 0.0;
-            any = true;
-        }
-        em[fq] = e;
-        ab[fq] = a;
+        double x13 = cbrt(X);
+        double x16 = fast_sqrt(x13);
+        double term = fma(x16 * x16, x16, P.two_11_12 * x16);
+        double e = pref * (term * term) * exp(-x13);
+        double bx = C.k_bx * nu * ith;
+        double den = (bx < 2.e-3) ? bx * (1. / 24.) * fma(bx, fma(bx, 4. + bx, 12.), 24.) : exp(bx) - 1.0;
+        double inu = fast_rcp(nu);
+        double a = e * den * C.k_ab * (inu * inu * inu);
+        double rn = nu * inv_nu_obs[fq];
+        double irn = fast_rcp(rn);
+        e = e * (irn * irn);
+        a = a * rn;
+        bool ok = valid & (X <= 1.e12) & (e == e) & (a == a);
+        em[fq] = ok ? e : 0.0;
+        ab[fq] = ok ? a : 0.0;
     }
-    return any;
+    return valid;
 }
 
 }  // namespace mk
