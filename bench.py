@@ -330,7 +330,7 @@ def run_b200(args):
         }
         if render is not None:
             line["render"] = render
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             v, info = time_cpu_oracle(args.res, args.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": "ray-steps/s", "cores": info["cores"], "kind": "port",
                                     "sample": info["sample"] + "; C/OpenMP restatement of the reference's JAX path"}
