@@ -244,3 +244,30 @@ def test_odd_resolution_dead_centre_pixel_and_cap(setup):
     img_cap = images.make_image(dm, resolution=res, max_nsteps=260)
     assert np.allclose(img_cap.reshape(-1), ref_cap[0], rtol=1e-6, atol=1e-12 * ref[0].max())
     assert not np.allclose(img_cap, img)
+
+
+def test_against_frozen_oracle_fixtures(built):
+    """The CUDA path against committed golden vectors (tests/golden/oracle_fixtures.npz)."""
+    import os
+    import mahakala_b200 as ma
+    from mahakala_b200 import geodesics as geo, images
+    from mahakala_b200.grmhd import AnalyticTorusFluidModel
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_fixtures.npz"))
+    s0 = np.asarray(ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 12))
+    assert np.allclose(s0, g["geo_s0"], rtol=1e-14, atol=0)
+    f, n, rl = geo.integrate_final(2000, s0, 40, 1e-2, A)
+    cap = g["geo_r_last"] < 100
+    assert np.array_equal(np.asarray(rl.cpu()) < 100, cap)
+    assert np.array_equal(np.asarray(n.cpu())[~cap], g["geo_nsteps"][~cap])
+    assert np.allclose(np.asarray(f.cpu())[~cap], g["geo_final"][~cap], rtol=1e-9, atol=1e-9)
+    arr = snapshot_arrays(ncells=32, block=16, extent=16.0)
+    dm = device_model(arr, A)
+    img, cnt = images.render(dm, resolution=12, observing_frequencies=(230e9, 345e9), want_counters=True)
+    ref = g["img_230_345"]
+    assert np.allclose(np.asarray(img.cpu()), ref, rtol=1e-6, atol=1e-12 * ref.max())
+    assert int(cnt[1]) == int(g["img_in_domain_samples"])
+    timg = images.render(AnalyticTorusFluidModel(A), resolution=12)
+    assert np.allclose(np.asarray(timg.cpu()), g["torus_img_230"], rtol=1e-6, atol=1e-12 * g["torus_img_230"].max())
+    em, ab = ma.synchrotron_coefficients(g["syn_Ne"], g["syn_Th"], g["syn_B"], g["syn_pitch"], g["syn_nu"],
+                                         invariant=True, rescale_nu=1 / 230e9)
+    assert np.allclose(np.asarray(em), g["syn_em"], rtol=1e-12) and np.allclose(np.asarray(ab), g["syn_ab"], rtol=1e-12)

@@ -118,3 +118,20 @@ def test_fluid_chain_numpy_vs_c(oracles):
     I = onp.solve_specific_intensity(em, ab, d, 1.0)
     att = onp.solve_attenuated_emissivity(em, ab, d, 1.0)
     assert np.allclose(att.sum(axis=0), I, rtol=1e-3)
+
+
+def test_oracle_reproduces_frozen_fixtures(built):
+    """tests/golden/oracle_fixtures.npz (made by tests/golden/make_oracle_fixtures.py): the oracle has not drifted."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_oracle_fixtures
+    want = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_fixtures.npz"))
+    got = make_oracle_fixtures.compute()
+    assert set(want.files) == set(got)
+    for k in want.files:
+        if np.issubdtype(want[k].dtype, np.integer):
+            assert np.array_equal(want[k], got[k]), k
+        else:
+            # same source, same compiler flags -> normally bit-identical; allow libm differences between hosts
+            assert np.allclose(want[k], got[k], rtol=1e-9, atol=1e-300, equal_nan=True), k
