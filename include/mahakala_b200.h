@@ -94,13 +94,16 @@ int mk_fill_frozen_rows(double* S, double* dt, const double* final_state, const 
                         long nrows, void* stream);
 /*
  * Single-pass trajectory dump into a paged (ragged) store: no row count has to be known in advance and no
- * padding is written.  Page p occupies 288 doubles at pages + 288*p: 32 rows of 8 state doubles followed by
- * the 32 step sizes (mk_page_rows() == 32).  page_first (npx,) holds each ray's first page, page_next
- * (max_pages,) links a ray's pages (-1 terminates).  A ray stores rows 0..n (row n = frozen state, dt = 0;
- * N rows when it never froze).  page_counter (one u32, zeroed by the caller) counts pages handed out (in
- * slabs of 64 per warp); *overflow becomes 1 if more than max_pages were needed (results other than the
- * trajectories stay valid).  mk_paged_gather materialises the reference layout S (nrows, nsel, 8),
- * dt (nrows, nsel) for the rays ray_idx[0..nsel) (NULL = rays 0..nsel-1).
+ * padding is written.  Every warp of the persistent kernel appends to its own log: per loop iteration one
+ * SLOT holding the rows of its 32 lanes (32 x 64 B of state, contiguous, then 32 step sizes), so all dump
+ * stores are fully coalesced.  Page p occupies 4608 doubles at pages + 4608*p: [16 slots][32 lanes][8] states
+ * followed by [16][32] step sizes (mk_page_rows() == 16 slots per page); page_next (max_pages,) chains the
+ * pages of one warp (-1 terminates).  Lanes are refilled when their ray freezes, so a ray is the column
+ * `lane` of consecutive slots starting at page_first[ray] = {page, slot*32 + lane} (page_first is (npx, 2)).
+ * A ray stores rows 0..n (row n = frozen state, dt = 0; N rows when it never froze).  page_counter (one u32,
+ * zeroed by the caller) counts pages handed out; *overflow becomes 1 if more than max_pages were needed
+ * (results other than the trajectories stay valid).  mk_paged_gather materialises the reference layout
+ * S (nrows, nsel, 8), dt (nrows, nsel) for the rays ray_idx[0..nsel) (NULL = rays 0..nsel-1).
  */
 int mk_page_rows(void);
 int mk_integrate_paged(int metric_id, double bhspin, long N, long npx, const double* s0, double div,

@@ -122,7 +122,7 @@ extern "C" int mk_fill_frozen_rows(double* S, double* dt, const double* final_st
 }
 
 // ---- paged (single-pass, ragged) trajectory dump ------------------------------------------------------
-extern "C" int mk_page_rows(void) { return PAGE_ROWS; }
+extern "C" int mk_page_rows(void) { return PAGE_SLOTS; }
 
 extern "C" int mk_integrate_paged(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
                                   double tol, double* final_state, int32_t* nsteps, double* r_last,
@@ -152,7 +152,8 @@ extern "C" int mk_integrate_paged(int metric_id, double bhspin, long N, long npx
 
 namespace mk {
 // paged store -> the reference's padded layout for a selection of rays: S (nrows, nsel, 8), dt (nrows, nsel).
-// One thread per selected ray walks its page chain; rows past the ray's last stored row repeat it with dt = 0.
+// One thread per selected ray walks the column of its warp's log; rows past the ray's last stored row repeat
+// it with dt = 0.
 __global__ void paged_gather_kernel(const double* __restrict__ pages, const int* __restrict__ page_next,
                                     const int* __restrict__ page_first, const int32_t* __restrict__ nsteps,
                                     const long* __restrict__ ray_idx, long nsel, long nrows, long N,
@@ -163,17 +164,20 @@ __global__ void paged_gather_kernel(const double* __restrict__ pages, const int*
     long ray = ray_idx ? ray_idx[j] : j;
     long have = (long)nsteps[ray] + 1;          // rows stored: 0..n (frozen row) or N rows when n == N
     if (have > N) have = N;
-    int page = page_first[ray];
+    int page = page_first[2 * ray];
+    int sl = page_first[2 * ray + 1];
+    int slot = sl >> 5;
+    const int ln = sl & 31;
     double4 lo = make_double4(0, 0, 0, 0), hi = lo;
     for (long row = 0; row < nrows; row++) {
         double d = 0.0;
         if (row < have && page >= 0) {
-            int rr = (int)(row & (PAGE_ROWS - 1));
             const double* pg = pages + (long)page * PAGE_DOUBLES;
+            const int rr = slot * 32 + ln;
             const double4* p = reinterpret_cast<const double4*>(pg + rr * 8);
             lo = p[0]; hi = p[1];
-            d = pg[PAGE_ROWS * 8 + rr];
-            if (rr == PAGE_ROWS - 1) page = page_next[page];
+            d = pg[PAGE_SLOTS * 32 * 8 + rr];
+            if (++slot == PAGE_SLOTS) { slot = 0; page = page_next[page]; }
         }
         double4* o = reinterpret_cast<double4*>(S + (row * nsel + j) * 8);
         o[0] = lo; o[1] = hi;

@@ -34,26 +34,29 @@ struct IntegrateArgs {
     long nrows;
     unsigned int* queue;   // zero-initialised ray counter
     unsigned long long* total_steps;  // optional global sum of accepted steps
-    // paged dump (single pass, ragged): page p = [PAGE_ROWS][8] states followed by [PAGE_ROWS] dts
+    // paged dump (single pass, ragged).  Each WARP appends to its own log: in every loop iteration the active
+    // lanes write their row into the same slot, so one slot is 32 x 64 B = 2 KB of contiguous state (fully
+    // coalesced 256-bit stores) plus 32 contiguous step sizes.  Page p = [PAGE_SLOTS][32][8] states followed
+    // by [PAGE_SLOTS][32] dts; a warp's pages are chained through page_next.  A ray is the column `lane` of
+    // consecutive slots starting at (page, slot) = page_first[ray] (lanes are refilled, so a column holds
+    // several rays one after another).
     double* pages;
-    int* page_next;        // (max_pages,) next page of the same ray or -1
-    int* page_first;       // (npx,) first page of each ray
+    int* page_next;        // (max_pages,) next page of the same warp or -1
+    int* page_first;       // (npx, 2): first page of the ray, slot * 32 + lane of its row 0
     unsigned int* page_counter;
     unsigned int max_pages;
     int* overflow;         // set to 1 when the page pool is exhausted
 };
 
-constexpr int PAGE_ROWS = 32;
-constexpr int PAGE_DOUBLES = PAGE_ROWS * 9;
-constexpr unsigned PAGE_SLAB = 64;       // pages a warp takes from the global pool per atomic
+constexpr int PAGE_SLOTS = 16;
+constexpr int PAGE_DOUBLES = PAGE_SLOTS * 32 * 9;
 enum { MODE_FINAL = 0, MODE_PADDED = 1, MODE_PAGED = 2 };
 
 template <class Metric, int MODE>
 __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateArgs& A)
 {
     constexpr bool DUMP = (MODE == MODE_PADDED);
-    unsigned slab_next = 0, slab_end = 0;      // warp-uniform page slab (MODE_PAGED)
-    int page = -1;
+    int wpage = -1, wslot = 0, my_slot = 0;    // warp-uniform log position (MODE_PAGED)
     const unsigned lane = threadIdx.x & 31u;
     long ray = -1;
     bool drained = false;           // queue exhausted (warp-uniform)
@@ -87,7 +90,6 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                         dt = A.rule(r_cur);
                         r_prev = r_cur;
                         it = 0; best_idx = -1; best_dt = -1.0e300; r_before_best = r_cur;
-                        page = -1;
                     }
                 }
             }
@@ -95,32 +97,28 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
         }
         const bool act = ray >= 0;
 
-        // ---- paged dump: lanes starting a new page take one from the warp's slab ----
+        // ---- paged dump: the warp claims the next slot of its log (a new page every PAGE_SLOTS iterations) ----
         if (MODE == MODE_PAGED) {
-            bool need = act && ((it & (PAGE_ROWS - 1)) == 0);
-            unsigned nm = __ballot_sync(FULL_MASK, need);
-            if (nm) {
-                unsigned cnt = (unsigned)__popc(nm);
-                if (slab_next + cnt > slab_end) {
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(A.page_counter, PAGE_SLAB);
-                    slab_next = __shfl_sync(FULL_MASK, base, 0);
-                    slab_end = slab_next + PAGE_SLAB;
-                }
-                if (need) {
-                    unsigned np = slab_next + (unsigned)__popc(nm & ((1u << lane) - 1u));
-                    if (np < A.max_pages) {
-                        if (it == 0) A.page_first[ray] = (int)np;
-                        else if (page >= 0) A.page_next[page] = (int)np;
+            if (wslot == 0) {
+                unsigned np = 0;
+                if (lane == 0) np = atomicAdd(A.page_counter, 1u);
+                np = __shfl_sync(FULL_MASK, np, 0);
+                if (np < A.max_pages) {
+                    if (lane == 0) {
+                        if (wpage >= 0) A.page_next[wpage] = (int)np;
                         A.page_next[np] = -1;
-                        page = (int)np;
-                    } else {
-                        *A.overflow = 1;
-                        if (it == 0) A.page_first[ray] = -1;
-                        page = -1;
                     }
+                    wpage = (int)np;
+                } else {
+                    if (lane == 0) *A.overflow = 1;
+                    wpage = -1;
                 }
-                slab_next += cnt;
+            }
+            my_slot = wslot;
+            wslot = (wslot + 1) & (PAGE_SLOTS - 1);
+            if (act && it == 0) {
+                A.page_first[2 * ray] = wpage;
+                A.page_first[2 * ray + 1] = my_slot * 32 + (int)lane;
             }
         }
         if (!act) continue;
@@ -143,12 +141,12 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
             }
         }
         if (MODE == MODE_PAGED) {
-            if (page >= 0) {
-                double* pg = A.pages + (long)page * PAGE_DOUBLES;
-                int rr = it & (PAGE_ROWS - 1);
+            if (wpage >= 0) {
+                double* pg = A.pages + (long)wpage * PAGE_DOUBLES;
+                int rr = my_slot * 32 + (int)lane;
                 store_256(pg + rr * 8, s[0], s[1], s[2], s[3]);
                 store_256(pg + rr * 8 + 4, s[4], s[5], s[6], s[7]);
-                pg[PAGE_ROWS * 8 + rr] = frozen ? 0.0 : dt;
+                pg[PAGE_SLOTS * 32 * 8 + rr] = frozen ? 0.0 : dt;
             }
         }
         bool done = frozen;

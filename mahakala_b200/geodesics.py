@@ -265,18 +265,19 @@ class TrajectoryStore:
     """Paged, ragged trajectory dump held in HBM (single integration pass, no padding).
 
     The reference materialises ``S (nrows, npx, 8)`` padded to the longest ray (and its scan to all ``N``
-    iterations); at 1024^2 rays that is hundreds of GB.  Here every ray appends rows to 32-row pages taken
-    from a pool, so memory and write traffic are proportional to the steps actually taken (72 B per
-    ray-step).  ``padded()`` materialises the reference layout for any subset of rays on demand.
+    iterations); at 1024^2 rays that is hundreds of GB.  Here every warp of the persistent kernel appends
+    one 32-lane slot per iteration to its own log of 16-slot pages taken from a pool (fully coalesced
+    stores), so memory and write traffic are proportional to the steps actually taken (72 B per ray-step).
+    ``padded()`` materialises the reference layout for any subset of rays on demand.
     """
-    PAGE_ROWS = 32
-    PAGE_DOUBLES = 32 * 9
+    PAGE_SLOTS = 16
+    PAGE_DOUBLES = 16 * 32 * 9
 
     def __init__(self, npx, N, max_pages, device):
         self.npx, self.N, self.max_pages = int(npx), int(N), int(max_pages)
         self.pages = torch.empty((self.max_pages, self.PAGE_DOUBLES), dtype=torch.float64, device=device)
         self.page_next = torch.empty((self.max_pages,), dtype=torch.int32, device=device)
-        self.page_first = torch.empty((self.npx,), dtype=torch.int32, device=device)
+        self.page_first = torch.empty((self.npx, 2), dtype=torch.int32, device=device)
         self.ctrl = torch.zeros(2, dtype=torch.int32, device=device)       # [page counter, overflow flag]
         self.final = torch.empty((self.npx, 8), dtype=torch.float64, device=device)
         self.nsteps = torch.empty((self.npx,), dtype=torch.int32, device=device)
@@ -286,7 +287,7 @@ class TrajectoryStore:
     @classmethod
     def allocate(cls, npx, N, max_pages=None, mem_fraction=0.6):
         dev = require_gpu()
-        worst = int(npx) * (-(-(int(N) + 1) // cls.PAGE_ROWS)) + 64 * 148 * 64
+        worst = 2 * (-(-int(npx) // 32)) * (-(-(int(N) + 1) // cls.PAGE_SLOTS)) + 148 * 64
         if max_pages is None:
             free, _ = torch.cuda.mem_get_info()
             max_pages = min(worst, int(mem_fraction * free) // (cls.PAGE_DOUBLES * 8))

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built):
     bound = set(_cabi.SIGNATURES) | set(_cabi.OTHER)
     assert bound == set(declared), (bound ^ set(declared))
     assert _cabi.call("mk_abi_version") == 1
-    assert lib.mk_page_rows() == 32
+    assert lib.mk_page_rows() == 16
     # argument-validation paths return an error string without touching the GPU
     with pytest.raises(_cabi.MahakalaB200Error, match="metric"):
         _cabi.call("mk_rhs", 99, 0.5, 1, 1, 1, None)       # unknown metric id is rejected before any launch
