@@ -374,18 +374,17 @@ def render_leg(args, rank, world, dev):
     from mahakala_b200.synthetic import make_synthetic_snapshot
 
     nc = args.snapshot_cells
-    arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
-    if rank != 0:       # replicas keep only the geometry; the cells arrive by broadcast
-        arr["uov"] = np.zeros_like(arr["uov"])
-        arr["B"] = np.zeros_like(arr["B"])
-    model = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
-                                          arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"], CFG2["bhspin"],
-                                          fluid_gamma=arr["fluid_gamma"], storage="f32")
-    del arr
+    model = None
+    if rank == 0:       # the other ranks get a geometry-only replica and the cells by one NCCL broadcast
+        arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
+        model = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
+                                              arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"],
+                                              CFG2["bhspin"], fluid_gamma=arr["fluid_gamma"], storage="f32")
+        del arr
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     b0.record()
-    multigpu.replicate_snapshot(model)
+    model = multigpu.replicate_snapshot(model)
     b1.record()
     torch.cuda.synchronize()
     bcast_ms = b0.elapsed_time(b1)

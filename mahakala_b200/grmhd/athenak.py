@@ -48,6 +48,9 @@ def fill_ghost_zones(uov, B, LogicalLocations, Levels):
     for mb in range(nmb):
         li, lj, lk = (int(q) for q in LogicalLocations[mb])
         index[(int(Levels[mb]), li, lj, lk)] = mb
+    fast = _fill_single_level_box(uov, B, np.asarray(LogicalLocations), np.asarray(Levels), index)
+    if fast is not None:
+        return fast, index
     out = np.zeros((nmb, 8, nk + 2, nj + 2, ni + 2))
     out[:, :nprim, 1:-1, 1:-1, 1:-1] = np.moveaxis(uov, 0, 1)
     out[:, nprim:, 1:-1, 1:-1, 1:-1] = np.moveaxis(B, 0, 1)
@@ -68,6 +71,33 @@ def fill_ghost_zones(uov, B, LogicalLocations, Levels):
                     elif multilevel:
                         _fill_from_other_levels(out, uov, B, index, mb, lev, (li, lj, lk), (di, dj, dk))
     return out, index
+
+
+def _fill_single_level_box(uov, B, loc, levels, index):
+    """Fast path for a single-level mesh whose blocks tile a full box: stitch the blocks into one zero-padded
+    global array per primitive and cut the ghost-padded blocks out of it.  Same result as the neighbour-by-
+    neighbour copy (a ghost cell is the neighbouring block's edge cell, or zero outside the domain)."""
+    if len(set(int(l) for l in levels)) != 1:
+        return None
+    nprim, nmb, nk, nj, ni = uov.shape
+    lo = loc.min(axis=0)
+    ext = loc.max(axis=0) - lo + 1
+    if int(np.prod(ext)) != nmb or len(index) != nmb:
+        return None
+    n1, n2, n3 = (int(q) for q in ext)
+    G = np.zeros((8, n3 * nk + 2, n2 * nj + 2, n1 * ni + 2))
+    data = (uov, B)
+    for mb in range(nmb):
+        li, lj, lk = (int(q) for q in (loc[mb] - lo))
+        sl = (slice(1 + lk * nk, 1 + (lk + 1) * nk), slice(1 + lj * nj, 1 + (lj + 1) * nj),
+              slice(1 + li * ni, 1 + (li + 1) * ni))
+        G[(slice(0, nprim),) + sl] = uov[:, mb]
+        G[(slice(nprim, 8),) + sl] = B[:, mb]
+    out = np.empty((nmb, 8, nk + 2, nj + 2, ni + 2))
+    for mb in range(nmb):
+        li, lj, lk = (int(q) for q in (loc[mb] - lo))
+        out[mb] = G[:, lk * nk:(lk + 1) * nk + 2, lj * nj:(lj + 1) * nj + 2, li * ni:(li + 1) * ni + 2]
+    return out
 
 
 def _fill_from_other_levels(out, uov, B, index, mb, lev, loc, d):
@@ -251,6 +281,29 @@ class AthenakFluidModel(DeviceSampledFluidModel):
                     bhspin=bhspin, fluid_gamma=fluid_gamma, storage=storage, lookup=lookup)
         return self
 
+    @classmethod
+    def replica(cls, x1v, x2v, x3v, x1f, x2f, x3f, bhspin, fluid_gamma, VariableNames, block_shape, storage):
+        """Geometry-only model for a rank that receives the snapshot cells from another rank
+        (``multigpu.replicate_snapshot``): no host copy of the primitives is kept."""
+        self = cls.__new__(cls)
+        self.bhspin, self.fluid_gamma = bhspin, fluid_gamma
+        self.variable_names = np.array(list(VariableNames))
+        self.all_meshblocks = None
+        self._block_shape = tuple(int(q) for q in block_shape)
+        self.x1v, self.x2v, self.x3v = (np.asarray(q, dtype=np.float64) for q in (x1v, x2v, x3v))
+        self.x1f, self.x2f, self.x3f = (np.asarray(q, dtype=np.float64) for q in (x1f, x2f, x3f))
+        self.nprim_all = 8
+        self._storage, self._lookup = storage, 'auto'
+        self._snap, self._snap_device = None, None
+        return self
+
+    def replica_meta(self):
+        """What another rank needs to build a ``replica`` of this model."""
+        return dict(x1v=self.x1v, x2v=self.x2v, x3v=self.x3v, x1f=self.x1f, x2f=self.x2f, x3f=self.x3f,
+                    bhspin=self.bhspin, fluid_gamma=self.fluid_gamma, VariableNames=list(self.variable_names),
+                    block_shape=self.all_meshblocks.shape if self.all_meshblocks is not None else self._block_shape,
+                    storage=self.storage)
+
     @staticmethod
     def _read_athdf(filename):
         try:
@@ -306,7 +359,12 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         if self._snap is not None and self._snap_device == dev:
             return self._snap
         amb = self.all_meshblocks
-        nmb, _, nk2, nj2, ni2 = amb.shape
+        if amb is None:
+            if fill:
+                raise ValueError("a replica model has no host data: fill it with multigpu.replicate_snapshot")
+            nmb, _, nk2, nj2, ni2 = self._block_shape
+        else:
+            nmb, _, nk2, nj2, ni2 = amb.shape
         storage = self._storage
         if storage == 'auto':
             storage = 'f32' if np.array_equal(amb.astype(np.float32).astype(np.float64), amb) else 'f64'
@@ -324,7 +382,7 @@ class AthenakFluidModel(DeviceSampledFluidModel):
                 raise ValueError("mesh is not regular enough for the block-grid lookup; use lookup='scan'")
         pidx = (ctypes.c_int * 8)(*self._prim_index())
         handle = ctypes.c_void_p()
-        d_mb = as_device(amb) if fill else None
+        d_mb = self._upload_meshblocks(amb) if fill else None
         d_geom = as_device(geom)
         if grid is not None:
             g, gn, g0, ginv = grid
@@ -342,6 +400,19 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         self.storage = storage
         self.lookup = 'grid' if grid is not None else 'scan'
         return self._snap
+
+    @staticmethod
+    def _upload_meshblocks(amb, chunk_bytes=1 << 30):
+        """Host -> device copy of the ghost-padded blocks; large snapshots go block-range by block-range so
+        that no multi-GB pinned staging buffer is needed."""
+        if amb.nbytes <= chunk_bytes:
+            return as_device(amb)
+        torch = __import__('torch')
+        d = empty(amb.shape)
+        per = max(1, chunk_bytes // (amb.nbytes // amb.shape[0]))
+        for b0 in range(0, amb.shape[0], per):
+            d[b0:b0 + per].copy_(torch.from_numpy(np.ascontiguousarray(amb[b0:b0 + per])))
+        return d
 
     def snapshot_bytes(self):
         return int(_cabi.load().mk_snapshot_bytes(self.snapshot()))

@@ -120,10 +120,15 @@ class SharedImage:
 # ---------------------------------------------------------------------------------------------------
 # snapshot replication
 # ---------------------------------------------------------------------------------------------------
-def replicate_snapshot(model, src=0):
-    """Give every rank the device snapshot of ``model``: rank ``src`` repacks from its host arrays, the other
-    ranks allocate a same-shaped snapshot (their host arrays only need the right geometry; the cell values
-    are overwritten) and receive the cells with one NCCL broadcast over NVLink."""
+def replicate_snapshot(model=None, src=0):
+    """Give every rank the device snapshot held by rank ``src``.
+
+    Rank ``src`` passes its ``AthenakFluidModel``; the other ranks may pass ``None`` (they receive the mesh
+    geometry with ``broadcast_object_list`` and build a geometry-only replica) or a model of the same shape.
+    Rank ``src`` repacks its host arrays once; the cell array then travels to all other ranks with ONE NCCL
+    broadcast over NVLink.  Returns the (replica) model on every rank.
+    """
+    from .grmhd.athenak import AthenakFluidModel
     rank, nranks = world()
     if nranks == 1:
         model.snapshot()
@@ -131,10 +136,13 @@ def replicate_snapshot(model, src=0):
     meta = [None]
     if rank == src:
         model.snapshot()
-        meta = [model.storage]
+        meta = [model.replica_meta()]
     dist.broadcast_object_list(meta, src=src)
     if rank != src:
-        model._storage = meta[0]
+        if model is None:
+            model = AthenakFluidModel.replica(**meta[0])
+        else:
+            model._storage = meta[0]["storage"]
         model.snapshot(fill=False)
     cells = ctypes.c_void_p()
     nbytes = ctypes.c_long()

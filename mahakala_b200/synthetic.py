@@ -58,7 +58,9 @@ def make_synthetic_snapshot(ncells=64, block=16, extent=32.0, seed=0, fluid_gamm
                             dens_scale=1.0, dtype=np.float64):
     """Single-level cube ``[-extent, extent]^3`` of ``ncells^3`` cells in ``(ncells/block)^3`` meshblocks.
 
-    Returns a dict with the AthenaK arrays plus ``VariableNames`` and ``fluid_gamma``.
+    Returns a dict with the AthenaK arrays plus ``VariableNames`` and ``fluid_gamma``.  Fields are evaluated
+    slab by slab on the global grid (one z-layer of blocks at a time) and cut into blocks, which gives the
+    same numbers as a block-by-block evaluation (every cell is a function of its own coordinates only).
     """
     assert ncells % block == 0
     nb = ncells // block
@@ -69,28 +71,39 @@ def make_synthetic_snapshot(ncells=64, block=16, extent=32.0, seed=0, fluid_gamm
     phase = rng.uniform(0., 2. * np.pi, size=8)
     uov = np.empty((5, nmb, block, block, block), dtype=dtype)
     B = np.empty((3, nmb, block, block, block), dtype=dtype)
+    ar = np.arange(block + 1)
+    faces = [-extent + (l * block + ar) * dx for l in range(nb)]            # per logical index along an axis
+    centres = [f[:-1] + dx / 2 for f in faces]
+    gx = np.concatenate(centres)                                            # global cell centres along one axis
+    loc = np.empty((nmb, 3), dtype=np.int64)
     x1v = np.empty((nmb, block)); x2v = np.empty((nmb, block)); x3v = np.empty((nmb, block))
     x1f = np.empty((nmb, block + 1)); x2f = np.empty((nmb, block + 1)); x3f = np.empty((nmb, block + 1))
-    loc = np.empty((nmb, 3), dtype=np.int64)
-    ar = np.arange(block + 1)
-    mb = 0
+    def slab(lk, lj):
+        zz, yy, xx = np.meshgrid(centres[lk], centres[lj], gx, indexing='ij')      # [k, j, I] pencil of blocks
+        fl = torus_fields(xx, yy, zz, fluid_gamma=fluid_gamma, waves=(kvec, phase), amp=amp, dens_scale=dens_scale)
+        m0 = (lk * nb + lj) * nb
+        for q in range(8):
+            # (k, j, li, i) -> (li, k, j, i)
+            v = fl[q].astype(np.float32).reshape(block, block, nb, block).transpose(2, 0, 1, 3)
+            dst = uov[q] if q < 5 else B[q - 5]
+            dst[m0:m0 + nb] = v
+
+    jobs = [(lk, lj) for lk in range(nb) for lj in range(nb)]
+    if len(jobs) >= 16:                 # NumPy ufuncs release the GIL: evaluate pencils on all host cores
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda a: slab(*a), jobs))
+    else:
+        for a in jobs:
+            slab(*a)
     for lk in range(nb):
         for lj in range(nb):
             for li in range(nb):
-                f1 = -extent + (li * block + ar) * dx
-                f2 = -extent + (lj * block + ar) * dx
-                f3 = -extent + (lk * block + ar) * dx
-                x1f[mb], x2f[mb], x3f[mb] = f1, f2, f3
-                x1v[mb], x2v[mb], x3v[mb] = f1[:-1] + dx / 2, f2[:-1] + dx / 2, f3[:-1] + dx / 2
+                mb = (lk * nb + lj) * nb + li
+                x1f[mb], x2f[mb], x3f[mb] = faces[li], faces[lj], faces[lk]
+                x1v[mb], x2v[mb], x3v[mb] = centres[li], centres[lj], centres[lk]
                 loc[mb] = (li, lj, lk)
-                zz, yy, xx = np.meshgrid(x3v[mb], x2v[mb], x1v[mb], indexing='ij')   # [k, j, i]
-                fl = torus_fields(xx, yy, zz, fluid_gamma=fluid_gamma, waves=(kvec, phase), amp=amp,
-                                  dens_scale=dens_scale)
-                for q in range(5):
-                    uov[q, mb] = fl[q].astype(np.float32)
-                for q in range(3):
-                    B[q, mb] = fl[5 + q].astype(np.float32)
-                mb += 1
     return dict(uov=uov, B=B, x1v=x1v, x2v=x2v, x3v=x3v, x1f=x1f, x2f=x2f, x3f=x3f,
                 LogicalLocations=loc, Levels=np.zeros(nmb, dtype=np.int64),
                 VariableNames=VARIABLE_NAMES, fluid_gamma=fluid_gamma)

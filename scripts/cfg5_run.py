@@ -1,0 +1,76 @@
+"""BASELINE cfg5: 4096x4096 rays x 8 frequencies x 4 inclinations on a synthetic 512^3 snapshot, tiles shared by
+all GPUs of the node through one dynamic queue per frame (torchrun --nproc-per-node N scripts/cfg5_run.py).
+
+    torchrun ... scripts/cfg5_run.py [res=4096] [ncells=512]
+
+Prints one JSON line on rank 0 and writes gpurun_out/cfg5.json.  Development / evidence script, not the bench."""
+import json
+import os
+import sys
+import time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from mahakala_b200 import images, multigpu
+from mahakala_b200.grmhd import AthenakFluidModel
+from mahakala_b200.synthetic import make_synthetic_snapshot
+
+res = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+nc = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+NUS = [43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9]
+INCS = [17.0, 30.0, 60.0, 80.0]
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank = dist.get_rank() if world > 1 else 0
+t0 = time.time()
+m = None
+if rank == 0:
+    arr = make_synthetic_snapshot(ncells=nc, block=32, extent=32.0, seed=0)
+    t_gen = time.time() - t0
+    m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                      arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.94,
+                                      fluid_gamma=arr["fluid_gamma"], storage="f32")
+    del arr
+t1 = time.time()
+m = multigpu.replicate_snapshot(m)          # ranks != 0 get a geometry-only replica + the cells by NCCL broadcast
+torch.cuda.synchronize()
+t_setup = time.time() - t1
+shared = multigpu.SharedImage(len(NUS), res * res) if world > 1 else None
+frames = []
+for inc in INCS:
+    kw = dict(camera_inclination=inc, resolution=res, observing_frequencies=NUS)
+    if world > 1:
+        shared.reset()
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if world > 1:
+        images.render(m, image_out=shared.image_ptr, queue=shared.queue_ptr, **kw)
+    else:
+        img = images.render(m, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            img = shared.local_view()[1]
+    if rank == 0:
+        frames.append({"inclination": inc, "ms": float(ms), "flux_230GHz": float(img[3].sum()), "finite": bool(torch.isfinite(img).all())})
+if rank == 0:
+    out = {"workload": f"cfg5: {res}x{res} rays x {len(NUS)} frequencies x {len(INCS)} inclinations, synthetic {nc}^3 snapshot",
+           "n_gpus": world, "frames": frames, "total_ms": sum(f["ms"] for f in frames),
+           "snapshot_bytes": m.snapshot_bytes(), "host_generate_s": t_gen, "upload_and_broadcast_s": t_setup}
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/cfg5.json", "w"), indent=1)
+    print(json.dumps(out))
+if world > 1:
+    dist.barrier()
+    shared.close()
+    dist.destroy_process_group()

@@ -18,14 +18,14 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
-arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
-if rank != 0:                       # replicas only need the geometry; their cell values come from rank 0
-    arr["uov"] = np.zeros_like(arr["uov"]); arr["B"] = np.zeros_like(arr["B"])
-m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
-                                  arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.94, fluid_gamma=arr["fluid_gamma"],
-                                  storage="f32")
+m = None
+if rank == 0:
+    arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
+    m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                      arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.94,
+                                      fluid_gamma=arr["fluid_gamma"], storage="f32")
 t0 = time.time()
-multigpu.replicate_snapshot(m)
+m = multigpu.replicate_snapshot(m)      # geometry-only replicas on the other ranks + one NCCL broadcast of the cells
 t_bcast = time.time() - t0
 kw = dict(resolution=res, observing_frequencies=(230e9, 345e9))
 ref = images.render(m, **kw) if rank == 0 else None
