@@ -18,6 +18,10 @@ from mahakala_b200.synthetic import make_synthetic_snapshot
 
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 nc = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+# The reference's explicit-Euler transfer (transfer.py:106-109) is only stable while alpha*dt < 2 per step; with
+# the default mass_scale = 1e26 the synthetic torus is far too opaque at 43-86 GHz (|I| ~ 1e300 in the oracle as
+# well).  A lower mass scale keeps all 8 frequencies in the regime where the scheme is meaningful.
+MASS_SCALE = float(sys.argv[3]) if len(sys.argv) > 3 else 2.e24
 NUS = [43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9]
 INCS = [17.0, 30.0, 60.0, 80.0]
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,7 +46,7 @@ t_setup = time.time() - t1
 shared = multigpu.SharedImage(len(NUS), res * res) if world > 1 else None
 frames = []
 for inc in INCS:
-    kw = dict(camera_inclination=inc, resolution=res, observing_frequencies=NUS)
+    kw = dict(camera_inclination=inc, resolution=res, observing_frequencies=NUS, mass_scale=MASS_SCALE)
     if world > 1:
         shared.reset()
         dist.barrier()
@@ -62,10 +66,12 @@ for inc in INCS:
         if rank == 0:
             img = shared.local_view()[1]
     if rank == 0:
-        frames.append({"inclination": inc, "ms": float(ms), "flux_230GHz": float(img[3].sum()), "finite": bool(torch.isfinite(img).all())})
+        frames.append({"inclination": inc, "ms": float(ms), "flux_per_frequency": [float(q) for q in img.sum(dim=1)],
+                       "finite": bool(torch.isfinite(img).all()), "negative_pixels": int((img < 0).sum()),
+                       "max_intensity": float(img.max())})
 if rank == 0:
     out = {"workload": f"cfg5: {res}x{res} rays x {len(NUS)} frequencies x {len(INCS)} inclinations, synthetic {nc}^3 snapshot",
-           "n_gpus": world, "frames": frames, "total_ms": sum(f["ms"] for f in frames),
+           "n_gpus": world, "mass_scale": MASS_SCALE, "frames": frames, "total_ms": sum(f["ms"] for f in frames),
            "snapshot_bytes": m.snapshot_bytes(), "host_generate_s": t_gen, "upload_and_broadcast_s": t_setup}
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/cfg5.json", "w"), indent=1)
