@@ -60,6 +60,25 @@ __device__ __forceinline__ double fast_sqrt(double x)
     return s;
 }
 
+// The same without the final residual correction: sqrt(x) = x * rsqrt(x) to <= ~3 ulp in 6 FP64 ops.  Used
+// inside the geodesic right-hand side, whose inputs already carry the rounding of the previous stage.
+__device__ __forceinline__ void quick_sqrt_rsqrt(double x, double& s, double& rs)
+{
+    double y = rsqrt_seed(x);
+    double e = fma(-(x * y), y, 1.0);
+    double p = fma(0.375, e, 0.5) * e;
+    y = fma(y, p, y);
+    s = x * y;
+    rs = y;
+}
+
+__device__ __forceinline__ double quick_sqrt(double x)
+{
+    double s, rs;
+    quick_sqrt_rsqrt(x, s, rs);
+    return s;
+}
+
 // a / b with b's reciprocal refined and one residual correction (≈ correctly rounded).
 __device__ __forceinline__ double fast_div(double a, double b)
 {

@@ -35,9 +35,9 @@ struct KerrSchild {
     __device__ __forceinline__ double radius(const double x[4], Cache& c) const
     {
         double zz = x[3] * x[3];
-        double kk = 0.5 * (fma(x[1], x[1], fma(x[2], x[2], zz)) - aa);
-        c.rr = fast_sqrt(fma(kk, kk, aa * zz)) + kk;
-        fast_sqrt_rsqrt(c.rr, c.r, c.ri);
+        double kk = fma(0.5, fma(x[1], x[1], fma(x[2], x[2], zz)), -0.5 * aa);
+        c.rr = quick_sqrt(fma(kk, kk, aa * zz)) + kk;
+        quick_sqrt_rsqrt(c.rr, c.r, c.ri);
         return c.r;
     }
 
@@ -91,21 +91,21 @@ struct KerrSchild {
         if (cache) {
             rr = cache->rr; r = cache->r; ri = cache->ri;
         } else {
-            double kk = 0.5 * (fma(X, X, fma(Y, Y, zz)) - aa);
-            rr = fast_sqrt(fma(kk, kk, az2)) + kk;
-            fast_sqrt_rsqrt(rr, r, ri);
+            double kk = fma(0.5, fma(X, X, fma(Y, Y, zz)), -0.5 * aa);
+            rr = quick_sqrt(fma(kk, kk, az2)) + kk;
+            quick_sqrt_rsqrt(rr, r, ri);
         }
         double den = fma(rr, rr, az2);                      // r^4 + a^2 z^2
         double q = rr + aa;
         double inv = fast_rcp(den * q);
         double iden = inv * q, iq = inv * den;              // 1/den, 1/q
         double rid = r * iden;
-        double f = 2.0 * rr * rid;
+        double t = rid * rr;                                // r^3 / den
+        double f = t + t;                                   // 2 r^3 / den
         double l1 = fma(r, X, a * Y) * iq;
         double l2 = fma(r, Y, -a * X) * iq;
         double l3 = Z * ri;
         // grad r = (r/den) (x_i r^2 + a^2 z delta_iz)
-        double t = rid * rr;
         double aaz = aa * Z;
         double g1 = t * X, g2 = t * Y, g3 = fma(t, Z, rid * aaz);
         double Dr = fma(v1, g1, fma(v2, g2, v3 * g3));      // v . grad r
@@ -134,17 +134,19 @@ struct KerrSchild {
         double K = fma(Df, L, f * M);
         double fL = f * L, hL2 = 0.5 * L * L;
         double ah = alpha * hL2;
-        // lower-index force w_m = -d_k g_ms v^k v^s + 1/2 d_m g_ks v^k v^s ;  w_0 = -K
-        double w1 = fma(-K, l1, fma(fL, n1, ah * g1));
-        double w2 = fma(-K, l2, fma(fL, n2, ah * g2));
-        double w3 = fma(-K, l3, fma(fL, n3, fma(ah, g3, hL2 * beta)));
-        // raise with g^mn = eta^mn - f l^m l^n
-        double P = fma(l1, w1, fma(l2, w2, fma(l3, w3, K)));    // l^n w_n
-        double fP = f * P;
-        acc[0] = K + fP;
-        acc[1] = fma(-fP, l1, w1);
-        acc[2] = fma(-fP, l2, w2);
-        acc[3] = fma(-fP, l3, w3);
+        // lower-index force w_m = -d_k g_ms v^k v^s + 1/2 d_m g_ks v^k v^s:  w_0 = -K,  w_i = q_i - K l_i with
+        //   q_i = f L n_i + 1/2 L^2 d_i f
+        double q1 = fma(fL, n1, ah * g1);
+        double q2 = fma(fL, n2, ah * g2);
+        double q3 = fma(fL, n3, fma(ah, g3, hL2 * beta));
+        // raise with g^mn = eta^mn - f l^m l^n.  P = l^n w_n = K + l.w = K - K |l|^2 + l.q = l.q because the
+        // spatial part of the null vector l has unit Euclidean length (l1^2 + l2^2 + l3^2 = 1 analytically).
+        double P = fma(l1, q1, fma(l2, q2, l3 * q3));
+        double a0 = fma(f, P, K);                           // acc^0 = K + f P
+        acc[0] = a0;
+        acc[1] = fma(-a0, l1, q1);                          // acc^i = w_i - f P l_i = q_i - (K + f P) l_i
+        acc[2] = fma(-a0, l2, q2);
+        acc[3] = fma(-a0, l3, q3);
     }
 
     // Covariant and contravariant metric at x (for the fluid-frame algebra, athenak.py:760-762).

@@ -32,6 +32,7 @@ def test_fast_math_accuracy(ma):
     assert ulp(rcp, 1.0 / x).max() <= 2.0
     assert ulp(sq, np.sqrt(x)).max() <= 2.0
     assert ulp(rsq, 1.0 / np.sqrt(x)).max() <= 3.0
+    assert ulp(rsq * xd, np.sqrt(x)).max() <= 4.0          # quick_sqrt = x * rsqrt(x), no residual correction
 
 
 def test_camera_grid_matches_oracle(ma):
