@@ -234,6 +234,11 @@ def run_b200(args):
                 "r_last": torch.empty((npx,), dtype=torch.float64, pin_memory=True)}
 
     def step_e2e():
+        if store is not None and hasattr(geo, "integrate_paged_streamed"):
+            # public host-to-host call: chunked so that H2D, kernel and D2H overlap (all bytes still move)
+            store.reset()
+            geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=4)
+            return int(host_out["nsteps"].sum())
         d = s0_host.to(dev, non_blocking=True)
         if store is not None:
             store.reset()

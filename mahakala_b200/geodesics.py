@@ -340,6 +340,64 @@ def integrate_paged(N, s0, div, tol, bhspin, store=None):
     return store
 
 
+_stream_pool = {}
+
+
+def _side_streams(dev):
+    if dev not in _stream_pool:
+        _stream_pool[dev] = [torch.cuda.Stream(device=dev) for _ in range(4)]      # copy-in, 2 x compute, copy-out
+    return _stream_pool[dev]
+
+
+def integrate_paged_streamed(N, s0_host, div, tol, bhspin, store, host_out, chunks=4):
+    """Host-to-host variant of ``integrate_paged`` that overlaps the PCIe copies with the kernel.
+
+    ``s0_host`` is a pinned CPU tensor (npx, 8); ``host_out`` a dict of pinned CPU tensors ``final`` (npx, 8),
+    ``nsteps`` (npx,) int32 and ``r_last`` (npx,) that receive the per-ray results (the trajectories stay in
+    ``store`` in HBM).  The bundle is cut into ``chunks`` ray ranges: the upload of range i+1, the persistent
+    kernel on range i (two alternating compute streams, so that the tail of one launch overlaps the head of
+    the next) and the download of range i-1 run concurrently.  All ranges share the store's page pool.
+    Returns after the last download has completed.
+    """
+    dev = require_gpu()
+    npx = s0_host.shape[0]
+    if store.npx != npx or store.N != int(N):
+        raise ValueError("TrajectoryStore was allocated for a different bundle")
+    if not hasattr(store, "s0_dev") or store.s0_dev.shape[0] != npx:
+        store.s0_dev = torch.empty((npx, 8), dtype=torch.float64, device=dev)
+    cin, c0, c1, cout = _side_streams(dev)
+    cur = torch.cuda.current_stream()
+    for st in (cin, c0, c1, cout):
+        st.wait_stream(cur)
+    bounds = [npx * k // chunks for k in range(chunks + 1)]
+    for k in range(chunks):
+        lo, hi = bounds[k], bounds[k + 1]
+        if hi <= lo:
+            continue
+        with torch.cuda.stream(cin):
+            store.s0_dev[lo:hi].copy_(s0_host[lo:hi], non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(cin)
+        comp = c0 if k % 2 == 0 else c1
+        with torch.cuda.stream(comp):
+            comp.wait_event(ev_in)
+            _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), hi - lo, store.s0_dev[lo:hi],
+                       float(div), float(tol), store.final[lo:hi], store.nsteps[lo:hi], store.r_last[lo:hi],
+                       store.pages, store.page_next, store.page_first[lo:hi], store.ctrl[0:1], store.max_pages,
+                       store.ctrl[1:2], store.total_steps, comp.cuda_stream)
+            ev_done = torch.cuda.Event()
+            ev_done.record(comp)
+        with torch.cuda.stream(cout):
+            cout.wait_event(ev_done)
+            host_out["final"][lo:hi].copy_(store.final[lo:hi], non_blocking=True)
+            host_out["nsteps"][lo:hi].copy_(store.nsteps[lo:hi], non_blocking=True)
+            host_out["r_last"][lo:hi].copy_(store.r_last[lo:hi], non_blocking=True)
+    cout.synchronize()
+    cur.wait_stream(c0)
+    cur.wait_stream(c1)
+    return store
+
+
 # -------------------------------------------------------------------------------------------------
 # shadow finder
 # -------------------------------------------------------------------------------------------------

@@ -172,6 +172,29 @@ def test_paged_dump_matches_padded_dump(ma):
     assert np.array_equal(np.asarray(small.nsteps.cpu()), np.asarray(n.cpu()))
 
 
+def test_streamed_host_to_host_dump(ma):
+    """Chunked upload / kernel / download pipeline gives the same results as the one-shot call."""
+    import torch
+    from oracle import mahakala_oracle as onp
+    from mahakala_b200 import geodesics as geo
+    s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 40)
+    npx = s0.shape[0]
+    ref = geo.integrate_paged(10000, s0, 40, 1e-4, A)
+    host_s0 = torch.from_numpy(s0).pin_memory()
+    host_out = {"final": torch.empty((npx, 8), dtype=torch.float64).pin_memory(),
+                "nsteps": torch.empty((npx,), dtype=torch.int32).pin_memory(),
+                "r_last": torch.empty((npx,), dtype=torch.float64).pin_memory()}
+    for chunks in (1, 3, 4):
+        store = geo.TrajectoryStore.allocate(npx, 10000, mem_fraction=0.1)
+        geo.integrate_paged_streamed(10000, host_s0, 40, 1e-4, A, store, host_out, chunks=chunks)
+        assert torch.equal(host_out["nsteps"], ref.nsteps.cpu()) and torch.equal(host_out["final"], ref.final.cpu())
+        assert torch.equal(host_out["r_last"], ref.r_last.cpu())
+        assert int(store.total_steps.item()) == int(ref.total_steps.item()) and not store.overflowed
+        S1, d1 = store.padded([0, 17, 399, npx - 1])
+        S0, d0 = ref.padded([0, 17, 399, npx - 1])
+        assert torch.equal(S1, S0) and torch.equal(d1, d0)
+
+
 def test_integrator_edge_cases(ma):
     from oracle import c_oracle, mahakala_oracle as onp
     from mahakala_b200 import geodesics as geo
