@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+E2E_CHUNKS = int(os.environ.get("MK_E2E_CHUNKS", "4"))
 FLOP_PER_RAY_STEP = 859          # 312 add + 523 mul + 12 div + 12 sqrt
 CFG2 = dict(bhspin=0.94, inclination=60.0, distance=1000.0, fov=20.0, div=40.0, tol=1e-4, N=10000)
 WEAK_INCLINATIONS = [60.0, 17.0, 30.0, 80.0, 45.0, 70.0, 25.0, 52.0]    # one frame per rank (cfg5-style)
@@ -237,7 +238,7 @@ def run_b200(args):
         if store is not None and hasattr(geo, "integrate_paged_streamed"):
             # public host-to-host call: chunked so that H2D, kernel and D2H overlap (all bytes still move)
             store.reset()
-            geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=4)
+            geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=E2E_CHUNKS)
             return int(host_out["nsteps"].sum())
         d = s0_host.to(dev, non_blocking=True)
         if store is not None:
