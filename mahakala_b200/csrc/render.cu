@@ -203,7 +203,7 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
     A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol; A.rule.rH = A.g.rH;
     A.sn = snap->view;
     memcpy(&A.P, params, sizeof A.P);
-    A.C = make_emission_consts(A.P);
+    A.C = make_emission_consts(A.P, nu_obs, nfreq);
     for (int f = 0; f < 8; f++) {
         A.nu_obs[f] = nu_obs[f < nfreq ? f : nfreq - 1];
         A.inv_nu_obs[f] = 1.0 / A.nu_obs[f];

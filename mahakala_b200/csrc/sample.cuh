@@ -349,9 +349,17 @@ struct EmissionConsts {      // derived once per launch on the host from Emissio
     double k_em;             // sqrt(2) pi EE^2 / (6 CL) * Ne_unit
     double k_bx;             // HPL / (ME CL^2)
     double k_ab;             // CL^2 / (2 HPL)
+    // frequency ratios relative to nu_obs[0]: X, bx and 1/nu of frequency f follow from those of frequency 0
+    // by one multiplication, so cbrt / sqrt / reciprocal are evaluated once per sample, not once per frequency
+    double nu0;              // nu_obs[0]
+    double ratio[8];         // nu_f / nu_0
+    double iratio[8];        // nu_0 / nu_f
+    double c13[8];           // cbrt(nu_f / nu_0)
+    double c16[8];           // (nu_f / nu_0)^(1/6)
 };
 
-__host__ __device__ inline EmissionConsts make_emission_consts(const EmissionParams& P)
+__host__ __device__ inline EmissionConsts make_emission_consts(const EmissionParams& P, const double* nu_obs = nullptr,
+                                                              int nfreq = 0)
 {
     const double PI = 3.141592653589793;
     EmissionConsts c;
@@ -363,6 +371,14 @@ __host__ __device__ inline EmissionConsts make_emission_consts(const EmissionPar
     c.k_em = 1.4142135623730951 * PI * (P.EE * P.EE) / (6.0 * P.CL) * P.Ne_unit;
     c.k_bx = P.HPL / (P.ME * P.CL * P.CL);
     c.k_ab = (P.CL * P.CL) / (2.0 * P.HPL);
+    c.nu0 = (nu_obs && nfreq > 0) ? nu_obs[0] : 1.0;
+    for (int f = 0; f < 8; f++) {
+        double r = (nu_obs && f < nfreq) ? nu_obs[f] / c.nu0 : 1.0;
+        c.ratio[f] = r;
+        c.iratio[f] = 1.0 / r;
+        c.c13[f] = cbrt(r);
+        c.c16[f] = sqrt(c.c13[f]);
+    }
     return c;
 }
 
@@ -427,21 +443,30 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     double inus = fast_rcp(nus);
     double ith = fast_rcp(Theta);
     double pref = C.k_em * dens * nus * (ith * ith);
+    // quantities of frequency 0; frequency f scales them by powers of nu_f / nu_0
+    double nu0 = -kdotu * C.nu0;
+    double X0 = nu0 * inus;
+    double x13_0 = cbrt(X0);
+    double x16_0 = quick_sqrt(x13_0);
+    double bx0 = C.k_bx * nu0 * ith;
+    double inu0 = fast_rcp(nu0);
+    double kab0 = C.k_ab * (inu0 * inu0 * inu0);
+    // invariant rescaling (transfer.py:77-80): nu * rescale_nu = (-k.u nu_f) / nu_f = -k.u for every frequency
+    double rn = -kdotu;
+    double irn = fast_rcp(rn);
+    double irn2 = irn * irn;
 #pragma unroll
     for (int fq = 0; fq < NF; fq++) {
-        double nu = -kdotu * nu_obs[fq];
-        double X = nu * inus;
-        double x13 = cbrt(X);
-        double x16 = fast_sqrt(x13);
+        double X = X0 * C.ratio[fq];
+        double x13 = x13_0 * C.c13[fq];
+        double x16 = x16_0 * C.c16[fq];
         double term = fma(x16 * x16, x16, P.two_11_12 * x16);
         double e = pref * (term * term) * exp(-x13);
-        double bx = C.k_bx * nu * ith;
+        double bx = bx0 * C.ratio[fq];
         double den = (bx < 2.e-3) ? bx * (1. / 24.) * fma(bx, fma(bx, 4. + bx, 12.), 24.) : exp(bx) - 1.0;
-        double inu = fast_rcp(nu);
-        double a = e * den * C.k_ab * (inu * inu * inu);
-        double rn = nu * inv_nu_obs[fq];
-        double irn = fast_rcp(rn);
-        e = e * (irn * irn);
+        double ir = C.iratio[fq];
+        double a = e * den * kab0 * (ir * ir * ir);
+        e = e * irn2;
         a = a * rn;
         bool ok = valid & (X <= 1.e12) & (e == e) & (a == a);
         em[fq] = ok ? e : 0.0;

@@ -123,6 +123,7 @@ def test_cfg5_style_multifrequency_multi_inclination(ma):
         for f in range(8):
             e_px, e_flux = _image_errors(img[f], ref[f])
             assert e_px < 1e-6 and e_flux < 1e-8, (inc, f, e_px, e_flux)
-        # one-frequency launches give the same numbers as the 8-frequency launch
+        # one-frequency launches give the same numbers as the 8-frequency launch (up to rounding: in a
+        # multi-frequency launch cbrt / sqrt / reciprocals are evaluated for nus[0] and scaled by frequency ratios)
         single = np.asarray(images.render(dm, camera_inclination=inc, resolution=16, observing_frequencies=[nus[3]]).cpu())
-        assert np.array_equal(single[0], img[3])
+        assert np.allclose(single[0], img[3], rtol=1e-11, atol=1e-14 * img[3].max())
