@@ -237,15 +237,31 @@ def dump_rows(N, max_steps):
 def geodesic_integrator(N, s0, div, tol, bhspin):
     """geodesics.py:233-281.  Returns ``(S (nrows, npx, 8), final_dt (nrows, npx))`` in HBM.
 
-    Two passes of the persistent integrate kernel: the first counts steps (so the dump can be allocated
-    exactly as the reference truncates it), the second writes the trajectories.  Use the fused
-    ``images.make_image`` path when the trajectories themselves are not needed.
+    One pass of the persistent integrate kernel dumps the trajectories into a paged store (no row count has
+    to be known in advance), then a gather kernel lays them out as the reference does, truncated at the first
+    all-zero row + 2 (geodesics.py:275-281) with the frozen state repeated below each ray's last row.  If the
+    page pool does not fit next to the padded result the function falls back to two integration passes
+    (count, then write).  Use the fused ``images.make_image`` path when the trajectories themselves are not
+    needed, and ``integrate_paged`` for bundles whose padded rectangle would not fit in HBM.
     """
     s = as_device(s0)
     npx = s.shape[0]
     N = int(N)
     if npx == 0:
         return DeviceArray.wrap(empty((min(N, 2 + N), 0, 8))), DeviceArray.wrap(empty((N, 0)))
+    free, _total = torch.cuda.mem_get_info()
+    # typical rays take a few hundred to a few thousand steps; size the pool for min(N, 4096) rows per ray
+    want_pages = 2 * (-(-npx // 32)) * (-(-(min(N, 4096) + 1) // TrajectoryStore.PAGE_SLOTS)) + 64
+    if want_pages * TrajectoryStore.PAGE_DOUBLES * 8 < 0.35 * free:
+        store = TrajectoryStore(npx, N, want_pages, s.device)
+        integrate_paged(N, s, div, tol, bhspin, store=store)
+        if not store.overflowed:
+            nrows = dump_rows(N, int(store.nsteps.max().item()))
+            if nrows * npx * 72 > torch.cuda.mem_get_info()[0]:
+                raise MemoryError(f"the padded trajectory array ({nrows} rows x {npx} rays) does not fit in HBM: "
+                                  "integrate the bundle in chunks (s0[lo:hi]) or keep it paged (integrate_paged)")
+            return store.padded()
+        del store
     final, nsteps, _ = integrate_final(N, s, div, tol, bhspin)
     nrows = dump_rows(N, int(nsteps.max().item()))
     need = nrows * npx * 72

@@ -137,13 +137,31 @@ def test_dump_mode_matches_oracle(ma):
     assert np.array_equal(np.asarray(dt2) == 0, dtr2 == 0)
 
 
+def _two_pass_padded_dump(N, s0, div, tol, a):
+    """The padded-dump mode of the kernel driven directly (count pass, then write + frozen-row fill)."""
+    from mahakala_b200 import _cabi, geodesics as geo
+    from mahakala_b200._device import as_device, empty, stream_ptr
+    s = as_device(s0)
+    npx = s.shape[0]
+    final, nsteps, _ = geo.integrate_final(N, s, div, tol, a)
+    nrows = geo.dump_rows(N, int(nsteps.max().item()))
+    S, dt = empty((nrows, npx, 8)), empty((nrows, npx))
+    _cabi.call("mk_integrate", geo._active_metric, float(a), N, npx, s, float(div), float(tol), None, None, None,
+               S, dt, nrows, None, stream_ptr())
+    _cabi.call("mk_fill_frozen_rows", S, dt, final, nsteps, npx, nrows, stream_ptr())
+    from mahakala_b200._device import DeviceArray
+    return DeviceArray.wrap(S), DeviceArray.wrap(dt)
+
+
 def test_paged_dump_matches_padded_dump(ma):
     from oracle import c_oracle, mahakala_oracle as onp
     from mahakala_b200 import geodesics as geo
     s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 20)
     store = geo.integrate_paged(10000, s0, 40, 1e-4, A)
     assert not store.overflowed
-    S, dt = ma.geodesic_integrator(10000, s0, 40, 1e-4, A)
+    S, dt = _two_pass_padded_dump(10000, s0, 40, 1e-4, A)
+    Sapi, dtapi = ma.geodesic_integrator(10000, s0, 40, 1e-4, A)          # paged pass + gather
+    assert np.array_equal(np.asarray(Sapi), np.asarray(S)) and np.array_equal(np.asarray(dtapi), np.asarray(dt))
     Sp, dtp = store.padded()
     assert np.array_equal(np.asarray(Sp), np.asarray(S)) and np.array_equal(np.asarray(dtp), np.asarray(dt))
     f, n, rl = geo.integrate_final(10000, s0, 40, 1e-4, A)
@@ -160,7 +178,7 @@ def test_paged_dump_matches_padded_dump(ma):
     assert np.array_equal(np.asarray(dts) == 0, dtr == 0)
     # iteration cap: rays that never freeze store exactly N rows
     st2 = geo.integrate_paged(70, s0, 40, 1e-4, A)
-    S2, dt2 = ma.geodesic_integrator(70, s0, 40, 1e-4, A)
+    S2, dt2 = _two_pass_padded_dump(70, s0, 40, 1e-4, A)
     Sp2, dtp2 = st2.padded()
     assert np.array_equal(np.asarray(Sp2), np.asarray(S2)) and np.array_equal(np.asarray(dtp2), np.asarray(dt2))
     # a pool that is too small is reported, not silently truncated
