@@ -127,3 +127,36 @@ def test_cfg5_style_multifrequency_multi_inclination(ma):
         # multi-frequency launch cbrt / sqrt / reciprocals are evaluated for nus[0] and scaled by frequency ratios)
         single = np.asarray(images.render(dm, camera_inclination=inc, resolution=16, observing_frequencies=[nus[3]]).cpu())
         assert np.allclose(single[0], img[3], rtol=1e-11, atol=1e-14 * img[3].max())
+
+
+def test_cfg4_full_size_image(ma):
+    """cfg4 at its stated size: synthetic AthenaK-shaped 256^3 snapshot (512 meshblocks of 32^3), 1024x1024
+    image at 230 GHz.  Oracle parity on the every-16th-pixel sub-lattice, plus size-independent properties."""
+    from helpers import device_model, oracle_model, snapshot_arrays
+    from mahakala_b200 import images
+    from oracle import c_oracle, mahakala_oracle as onp
+    arr = snapshot_arrays(ncells=256, block=32, extent=32.0)
+    dm = device_model(arr, A)
+    assert dm.all_meshblocks.shape == (512, 8, 34, 34, 34)
+    img = images.make_image(dm, resolution=1024)
+    assert img.shape == (1024, 1024) and np.isfinite(img).all() and (img >= 0).all() and img.max() > 1e-4
+    assert dm.storage == "f32" and dm.lookup == "grid"
+    # determinism of the dynamically scheduled fused kernel
+    assert np.array_equal(img, images.make_image(dm, resolution=1024))
+    # f64 cell storage and the linear-scan lookup give the same image (explicit rays instead of the in-kernel
+    # camera: initial states agree to rounding, so compare at 1e-10)
+    alt = device_model(arr, A, storage="f64", lookup="scan")
+    sub_rays = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 1024)
+    idx = (np.arange(0, 1024, 16)[:, None] * 1024 + np.arange(0, 1024, 16)[None, :]).reshape(-1)
+    got_alt = np.asarray(images.render(alt, s0=sub_rays[idx]).cpu())[0]
+    assert np.allclose(got_alt, img.reshape(-1)[idx], rtol=1e-10, atol=1e-14 * img.max())
+    alt.release()
+    # oracle parity on the sub-lattice (4096 rays through the literal O(nmb) block scan)
+    om = oracle_model(arr, A)
+    units = om.get_units(M_BH, MASS_SCALE)
+    ref, nsteps, nin = c_oracle.render(om, sub_rays[idx], units, [230e9])
+    e_px, e_flux = _image_errors(img.reshape(-1)[idx], ref[0])
+    assert e_px < 1e-6 and e_flux < 1e-8, (e_px, e_flux)
+    # flux converges with resolution (pixel area x sum)
+    half = images.make_image(dm, resolution=512)
+    assert abs(img.sum() / 4 - half.sum()) / half.sum() < 2e-2
