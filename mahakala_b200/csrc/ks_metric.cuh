@@ -18,6 +18,7 @@
 namespace mk {
 
 struct KerrSchild {
+    static constexpr bool kHeavy = false;   // fits 4 CTAs of 128 threads per SM (126 registers)
     double a;    // spin
     double aa;   // a^2
     double rH;   // 1 + sqrt(1 - a^2), computed on the host exactly as geodesics.py:351

@@ -143,9 +143,21 @@ __device__ __forceinline__ void inverse4(const double m[4][4], double inv[4][4])
     inv[3][3] = ( m[2][0] * s3 - m[2][1] * s1 + m[2][2] * s0) * id;
 }
 
+// A functor may declare `static constexpr bool stationary = true;` (no dependence on x[0]): the t tangent is
+// then identically zero and only the 3 spatial tangents are propagated.
+template <class T, class = void>
+struct tangent_count {
+    static constexpr int value = 4;
+};
+template <class T>
+struct tangent_count<T, decltype((void)T::stationary)> {
+    static constexpr int value = T::stationary ? 3 : 4;
+};
+
 // Generic plugin: derivatives by forward-mode duals through the user's metric functor.
 template <class Fn>
 struct DualMetric {
+    static constexpr bool kHeavy = true;    // 16 metric jets live at once: give each thread the full register file
     Fn fn;
     double rH;
 
@@ -164,12 +176,14 @@ struct DualMetric {
     __device__ __forceinline__ void accel(const double x[4], const double v[4], double acc[4],
                                           const Cache* = nullptr) const
     {
-        typedef Dual<4> D;
+        constexpr int NT = tangent_count<Fn>::value;     // tangent k differentiates along x^(k + OFF)
+        constexpr int OFF = 4 - NT;
+        typedef Dual<NT> D;
         D xd[4];
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             xd[m] = D(x[m]);
-            xd[m].d[m] = 1.0;
+            if (m >= OFF) xd[m].d[m - OFF] = 1.0;
         }
         D gd[4][4];
         fn(xd, gd);
@@ -177,25 +191,35 @@ struct DualMetric {
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) g[i][j] = gd[i][j].v;
+            for (int j = 0; j < 4; j++) g[i][j] = gd[i < j ? i : j][i < j ? j : i].v;      // symmetric: upper triangle
         inverse4(g, gi);
+        // directional derivative along v of the (symmetric) metric, upper triangle only
+        double Dg[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = i; j < 4; j++) {
+                double dir = 0.0;
+#pragma unroll
+                for (int k = 0; k < NT; k++) dir = fma(gd[i][j].d[k], v[k + OFF], dir);
+                Dg[i][j] = dir;
+                Dg[j][i] = dir;
+            }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             double t1 = 0.0;        // sum_jk d_k g_ij v^k v^j
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                double dir = 0.0;
+            for (int j = 0; j < 4; j++) t1 = fma(Dg[i][j], v[j], t1);
+            double t2 = 0.0;        // sum_jk v^j v^k d_i g_jk  (zero for the t component of a stationary metric)
+            if (i >= OFF) {
 #pragma unroll
-                for (int k = 0; k < 4; k++) dir = fma(gd[i][j].d[k], v[k], dir);
-                t1 = fma(dir, v[j], t1);
-            }
-            double t2 = 0.0;        // sum_jk v^j v^k d_i g_jk
+                for (int j = 0; j < 4; j++) {
+                    double in = 0.5 * gd[j][j].d[i - OFF] * v[j];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                double in = 0.0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) in = fma(gd[j][k].d[i], v[k], in);
-                t2 = fma(in, v[j], t2);
+                    for (int k = j + 1; k < 4; k++) in = fma(gd[j][k].d[i - OFF], v[k], in);
+                    t2 = fma(in, v[j], t2);
+                }
+                t2 *= 2.0;
             }
             w[i] = fma(0.5, t2, -t1);
         }
@@ -208,6 +232,7 @@ struct DualMetric {
 // The Kerr-Schild metric typed generically (geodesics.py:95-104): exercises the dual-number path and
 // serves as the template for user-registered spacetimes.
 struct KerrSchildFn {
+    static constexpr bool stationary = true;
     double a;
 
     template <class T>

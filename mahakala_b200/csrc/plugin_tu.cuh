@@ -2,6 +2,7 @@
 // the user's source, which must define
 //
 //     struct UserMetric {
+//         static constexpr bool stationary = true;    // OPTIONAL: metric independent of x[0] -> 3 tangents
 //         double params[8];          // params[0] = the bhspin argument of the call; [1..7] = mk_metric_set_params
 //         template <class T> __device__ void operator()(const T x[4], T g[4][4]) const;   // covariant metric
 //         __device__ double radius(const double x[4]) const;     // radius used by the step rule

@@ -145,6 +145,7 @@ def test_device_array_numpy_protocol():
 SCHWARZSCHILD_KS = r"""
 // Schwarzschild in Kerr-Schild coordinates with mass M = params[1]: g = eta + (2M/r) l l, l = (1, x/r, y/r, z/r)
 struct UserMetric {
+    static constexpr bool stationary = true;      // optional: lets the plugin skip the t tangent
     double params[8];
     template <class T> __device__ void operator()(const T x[4], T g[4][4]) const {
         const double M = params[1];
