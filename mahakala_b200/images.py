@@ -16,7 +16,7 @@ from . import geodesics as geo
 from .constants import Msun
 from .electrons import rlow_rhigh_model
 from .transfer import emission_params, solve_specific_intensity, synchrotron_coefficients
-from ._device import DeviceArray, as_device, empty, require_gpu, stream_ptr
+from ._device import as_device, empty, require_gpu, stream_ptr
 
 
 def _params_for(fluid_model, M_bh, mass_scale, r_high):

@@ -5,7 +5,7 @@ import os
 import sys
 import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
+
 import torch
 import torch.distributed as dist
 from mahakala_b200 import images, multigpu

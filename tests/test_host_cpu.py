@@ -65,7 +65,7 @@ def test_product_package_never_imports_the_oracle():
 def test_api_surface_matches_reference_exports():
     import inspect
     import mahakala_b200 as ma
-    from mahakala_b200 import geodesics, images, electrons, transfer
+    from mahakala_b200 import geodesics, images, electrons
     assert ma.__all__ == ["find_shadow_bisection", "find_shadow_bisection_angles", "geodesic_integrator",
                           "initialize_geodesics_at_camera", "synchrotron_coefficients", "solve_specific_intensity",
                           "solve_attenuated_emissivity"]
