@@ -397,9 +397,9 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     const double* Bp = prims + 5;
     // ---- fluid frame (athenak.py:760-786) ----
     double sq1f, alpha;                                          // sqrt(1+f), 1/sqrt(1+f) = lapse
-    fast_sqrt_rsqrt(1.0 + f, sq1f, alpha);
+    quick_sqrt_rsqrt(1.0 + f, sq1f, alpha);
     double lU = fma(l[1], U[0], fma(l[2], U[1], l[3] * U[2]));
-    double gamma = fast_sqrt(fma(f * lU, lU, 1.0 + fma(U[0], U[0], fma(U[1], U[1], U[2] * U[2]))));
+    double gamma = quick_sqrt(fma(f * lU, lU, 1.0 + fma(U[0], U[0], fma(U[1], U[1], U[2] * U[2]))));
     double ucon[4], ucov[4], bcon[4], bcov[4];
     ucon[0] = gamma * sq1f;
     double gaf = gamma * alpha * f;
@@ -422,12 +422,12 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     double bsq = fma(bcon[0], bcov[0], fma(bcon[1], bcov[1], fma(bcon[2], bcov[2], bcon[3] * bcov[3])));
     valid &= (bsq > 0.0) & (kdotu < 0.0);
     double b, ib;
-    fast_sqrt_rsqrt(bsq, b, ib);
+    quick_sqrt_rsqrt(bsq, b, ib);
     double c = kdotb * ib * fast_rcp(-kdotu);                    // cos(pitch), athenak.py:789
     c = fmin(fmax(c, -1.0), 1.0);
     double sin2 = (1.0 - c) * (1.0 + c);
     valid &= (sin2 > 0.0);
-    double sinp = fast_sqrt(sin2);
+    double sinp = quick_sqrt(sin2);
     // ---- plasma state (images.py:87-102, electrons.py:46-50) ----
     double idens = fast_rcp(dens);
     double sigma = bsq * idens;
