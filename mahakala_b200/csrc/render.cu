@@ -50,11 +50,14 @@ struct RenderArgs {
 
 // Resident CTAs per SM, measured on B200 (scripts/variant_probe.py): 3 for one or two frequencies, 4 when
 // the per-frequency synchrotron work dominates (8 frequencies: 75.8 -> 67.0 ms on cfg4).
+#ifndef MK_RENDER_SPLIT
+#define MK_RENDER_SPLIT 4
+#endif
 #ifndef MK_RENDER_LO
 #define MK_RENDER_LO 3
 #endif
 template <int NF>
-__global__ void __launch_bounds__(128, (NF >= 4) ? 4 : MK_RENDER_LO) render_kernel(const RenderArgs A)
+__global__ void __launch_bounds__(128, (NF >= MK_RENDER_SPLIT) ? 4 : MK_RENDER_LO) render_kernel(const RenderArgs A)
 {
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long my_steps = 0, my_samples = 0;
@@ -101,34 +104,79 @@ __global__ void __launch_bounds__(128, (NF >= 4) ? 4 : MK_RENDER_LO) render_kern
         if (active) dt = A.rule(A.g.radius(s, cache));
         if (dt == 0.0) active = false;          // never moves: n = 0, no row pair contributes
 
-        while (__any_sync(FULL_MASK, active)) {
-            if (active) {
-                double cand[8];
-                rk4_step(A.g, s, dt, cand, &cache);
-                double dtn = A.rule(A.g.radius(cand, cache_new));
-                if (dtn == 0.0) {
-                    active = false;             // step rejected; ray frozen at s (geodesics.py:264-267)
-                } else {
-                    const double wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0)
-#pragma unroll
-                    for (int i = 0; i < 8; i++) s[i] = cand[i];
-                    cache = cache_new;
-                    dt = dtn;
-                    it++;
-                    if (it == A.N) {
-                        active = false;         // row N is not part of the reference's scan output
+        // Two loop shapes, chosen by measurement (scripts/variant_probe.py): with one or two frequencies the
+        // software-pipelined form is ~2 % faster; with many frequencies its extra live registers spill.
+        if constexpr (NF <= 2) {
+            // Software-pipelined loop: the sample of state s (accepted in the previous iteration, weight wdt) and
+            // the RK4 step that leaves s are independent, so they sit in ONE straight-line block and the scheduler
+            // can fill the latency of the gathers and of the emission chain with RK4 arithmetic.
+            double wdt = 0.0;
+            bool pending = false;
+            while (__any_sync(FULL_MASK, active)) {
+                if (active) {
+                    double cand[8], prims[8];
+                    double dtn;
+                    if (pending && interp_prims(A.sn, s, prims)) {
+                        my_samples++;
+                        double f, l[4], em[NF], ab[NF];
+                        l[0] = 1.0;
+                        A.g.fl(s, cache, f, l[1], l[2], l[3]);
+                        emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
+                        rk4_step(A.g, s, dt, cand, &cache);
+                        dtn = A.rule(A.g.radius(cand, cache_new));
+    #pragma unroll
+                        for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
+                            I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
+                            T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
+                        }
                     } else {
-                        double prims[8];
-                        if (interp_prims(A.sn, s, prims)) {
-                            my_samples++;
-                            double f, l[4], em[NF], ab[NF];
-                            l[0] = 1.0;
-                            A.g.fl(s, cache, f, l[1], l[2], l[3]);
-                            emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
-#pragma unroll
-                            for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
-                                I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
-                                T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
+                        rk4_step(A.g, s, dt, cand, &cache);
+                        dtn = A.rule(A.g.radius(cand, cache_new));
+                    }
+                    if (dtn == 0.0) {
+                        active = false;             // step rejected; ray frozen at s (already sampled above)
+                    } else {
+                        wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
+    #pragma unroll
+                        for (int i = 0; i < 8; i++) s[i] = cand[i];
+                        cache = cache_new;
+                        dt = dtn;
+                        it++;
+                        pending = true;
+                        if (it == A.N) active = false;      // row N is not part of the reference's scan output
+                    }
+                }
+            }
+        } else {
+            while (__any_sync(FULL_MASK, active)) {
+                if (active) {
+                    double cand[8];
+                    rk4_step(A.g, s, dt, cand, &cache);
+                    double dtn = A.rule(A.g.radius(cand, cache_new));
+                    if (dtn == 0.0) {
+                        active = false;             // step rejected; ray frozen at s (geodesics.py:264-267)
+                    } else {
+                        const double wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0)
+    #pragma unroll
+                        for (int i = 0; i < 8; i++) s[i] = cand[i];
+                        cache = cache_new;
+                        dt = dtn;
+                        it++;
+                        if (it == A.N) {
+                            active = false;         // row N is not part of the reference's scan output
+                        } else {
+                            double prims[8];
+                            if (interp_prims(A.sn, s, prims)) {
+                                my_samples++;
+                                double f, l[4], em[NF], ab[NF];
+                                l[0] = 1.0;
+                                A.g.fl(s, cache, f, l[1], l[2], l[3]);
+                                emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
+    #pragma unroll
+                                for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
+                                    I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
+                                    T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
+                                }
                             }
                         }
                     }
