@@ -469,7 +469,7 @@ def render_leg(args, rank, world, dev):
                                       "gather into rank 0 over NVLink (CUDA IPC), device-timed, max over ranks; at 1024^2 "
                                       "the floor is the serial latency of the longest photon-ring ray (~8 ms)")
         out["strong_image_sum"] = flux
-        out["snapshot_broadcast_ms"] = float(t[3])
+        out["snapshot_upload_repack_broadcast_ms"] = float(t[3])      # incl. rank 0 upload + repack and NCCL start-up
     return out
 
 
