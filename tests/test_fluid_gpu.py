@@ -296,3 +296,19 @@ def test_optically_thick_regime_matches_where_finite(built):
     # rounding level, the worst pixels at ~1e-5 (the result itself is numerical garbage in both implementations)
     assert np.percentile(rel[big], 99) < 1e-8 and rel[big].max() < 1e-3
     assert (fin_r != fin_g).sum() <= 0.01 * res * res
+
+
+def test_variable_order_follows_names(setup):
+    """The primitive order of the file (VariableNames, athenak.py:697-710) may differ from the usual one."""
+    from mahakala_b200.grmhd import AthenakFluidModel
+    arr, S = setup["arr"], setup["S"][::9]
+    base = {k: np.asarray(v) for k, v in setup["dm"].get_fluid_scalars_from_geodesics(S).items()}
+    perm = [4, 0, 1, 2, 3]                                   # eint, dens, velx, vely, velz
+    names = ('eint', 'dens', 'velx', 'vely', 'velz', 'bcc1', 'bcc2', 'bcc3')
+    m = AthenakFluidModel.from_arrays(arr["uov"][perm], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
+                                      arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"], A,
+                                      fluid_gamma=arr["fluid_gamma"], VariableNames=names)
+    got = m.get_fluid_scalars_from_geodesics(S)
+    for k in base:
+        assert np.array_equal(np.asarray(got[k]), base[k]), k
+    m.release()

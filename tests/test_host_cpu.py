@@ -190,3 +190,29 @@ def test_amr_ghost_fill_two_levels_bruteforce(built):
     assert grid.shape == (4, 4, 4) and (grid >= 0).all()
     assert len(set(grid[:2].ravel()) | set(grid[:, :2].ravel()) | set(grid[:, :, :2].ravel())) == 7   # 7 coarse blocks
     assert len(set(grid[2:, 2:, 2:].ravel())) == 8                                                     # 8 fine blocks
+
+
+def test_primitive_name_mapping_and_errors():
+    """athenak.py:55-65 / :697-710: primitives are found by name; non-contiguous velocity or field components
+    raise ValueError (checked on the host before anything is uploaded)."""
+    from helpers import snapshot_arrays
+    from mahakala_b200.grmhd import AthenakFluidModel
+    arr = snapshot_arrays(ncells=16, block=8, extent=8.0)
+
+    def model(names):
+        return AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
+                                             arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.5,
+                                             fluid_gamma=4. / 3, VariableNames=names)
+
+    m = model(('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'))
+    assert m.get_index_for_primitive_by_name(' EINT ') == 4 and m.get_index_for_primitive_by_name('nope') == -1
+    assert m._prim_index() == [0, 4, 1, 2, 3, 5, 6, 7]
+    # a different but valid file order is honoured
+    m2 = model(('eint', 'dens', 'bcc1', 'bcc2', 'bcc3', 'velx', 'vely', 'velz'))
+    assert m2._prim_index() == [1, 0, 5, 6, 7, 2, 3, 4]
+    with pytest.raises(ValueError, match="Velocity"):
+        model(('dens', 'velx', 'eint', 'vely', 'velz', 'bcc1', 'bcc2', 'bcc3'))._prim_index()
+    with pytest.raises(ValueError, match="Magnetic"):
+        model(('dens', 'velx', 'vely', 'velz', 'bcc1', 'eint', 'bcc2', 'bcc3'))._prim_index()
+    assert m.all_meshblocks.shape == (8, 8, 10, 10, 10) and m.nprim_all == 8
+    assert set(m.mb_index_map) == {(0, i, j, k) for i in range(2) for j in range(2) for k in range(2)}
