@@ -2,6 +2,7 @@
 // the DFMA peak microbenchmark and small utility kernels (radius_cal, rhs on a bundle).
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include "common.cuh"
 #include "integrate.cuh"
 #include "ks_metric.cuh"
@@ -40,7 +41,9 @@ unsigned int* queue_counter(cudaStream_t stream, int slot)
 {
     static unsigned int* pool[64] = {nullptr};
     static unsigned next[64] = {0};
+    static std::mutex mtx;
     constexpr int SLOTS = 64;
+    std::lock_guard<std::mutex> lock(mtx);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_error("cudaGetDevice failed"); return nullptr; }
     if (!pool[dev]) {

@@ -302,6 +302,9 @@ class TrajectoryStore:
 
     @classmethod
     def allocate(cls, npx, N, max_pages=None, mem_fraction=0.6):
+        """Reserve the page pool.  Without ``max_pages`` the pool is sized for the worst case but capped at
+        ``mem_fraction`` of the currently free HBM (a cfg2-sized dump needs ~42 GB); an undersized pool is
+        reported through ``overflowed``, never silently truncated."""
         dev = require_gpu()
         worst = 2 * (-(-int(npx) // 32)) * (-(-(int(N) + 1) // cls.PAGE_SLOTS)) + 148 * 64
         if max_pages is None:
