@@ -343,3 +343,27 @@ def test_user_registered_metrics(ma):
         assert np.allclose(ff[:, 0], lam * s00[:, 4], rtol=1e-12, atol=1e-9)
     finally:
         geo.set_metric("kerr_schild")
+
+
+def test_classification_sweep_spins_and_inclinations(ma):
+    """Shadow classification (captured vs escaped) is bit-exact against the oracle across spins, inclinations,
+    fields of view and both tolerance settings used by the reference (1e-2 shadow finder, 1e-4 imaging)."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    from mahakala_b200 import geodesics as geo
+    rng = np.random.default_rng(42)
+    cases = [(0.0, 90.0), (0.998, 90.0), (0.998, 1.0), (0.5, 45.0)]
+    cases += [(float(rng.uniform(0, 0.99)), float(rng.uniform(1, 90))) for _ in range(8)]
+    total = mism = 0
+    for k, (a, inc) in enumerate(cases):
+        tol, N = ((1e-2, 2000), (1e-4, 10000))[k % 2]
+        fov = (7.0, 10.0, 14.0)[k % 3]
+        s0 = onp.initialize_geodesics_at_camera(a, inc, 1000, -fov, fov, 24)
+        f, n, rl = geo.integrate_final(N, s0, 40, tol, a)
+        ref = c_oracle.integrate(N, s0, 40, tol, a)
+        cap, cap_ref = np.asarray(rl.cpu()) < 100, ref["r_last"] < 100
+        total += cap.size
+        mism += int((cap != cap_ref).sum())
+        esc = ~cap_ref
+        assert np.array_equal(np.asarray(n.cpu())[esc], ref["nsteps"][esc]), (a, inc)
+        assert 0 < cap_ref.sum() < cap.size, (a, inc)
+    assert mism == 0, f"{mism} of {total} rays classified differently"
