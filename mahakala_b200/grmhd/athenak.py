@@ -261,8 +261,12 @@ class AnalyticTorusFluidModel(DeviceSampledFluidModel):
 class AthenakFluidModel(DeviceSampledFluidModel):
 
     def __init__(self, grmhd_filename, bhspin, fluid_gamma=None):
-        """athenak.py:50-53.  Reads an AthenaK ``.athdf`` dump (h5py required, imported lazily)."""
-        arrays = self._read_athdf(grmhd_filename)
+        """athenak.py:50-53.  Reads an AthenaK ``.athdf`` dump (h5py required, imported lazily) or an ``.npz``
+        file holding the same datasets (``scripts/athdf_to_npz.py`` converts on a machine that has h5py)."""
+        if str(grmhd_filename).endswith(".npz"):
+            arrays = self._read_npz(grmhd_filename)
+        else:
+            arrays = self._read_athdf(grmhd_filename)
         self._setup(bhspin=bhspin, fluid_gamma=fluid_gamma, **arrays)
 
     @classmethod
@@ -303,6 +307,15 @@ class AthenakFluidModel(DeviceSampledFluidModel):
                     bhspin=self.bhspin, fluid_gamma=self.fluid_gamma, VariableNames=list(self.variable_names),
                     block_shape=self.all_meshblocks.shape if self.all_meshblocks is not None else self._block_shape,
                     storage=self.storage)
+
+    DATASETS = ('x1v', 'x2v', 'x3v', 'x1f', 'x2f', 'x3f', 'uov', 'B', 'LogicalLocations', 'Levels')
+
+    @classmethod
+    def _read_npz(cls, filename):
+        with np.load(filename, allow_pickle=False) as z:
+            out = {k: np.array(z[k]) for k in cls.DATASETS}
+            out['VariableNames'] = [str(n) for n in z['VariableNames']]
+        return out
 
     @staticmethod
     def _read_athdf(filename):

@@ -216,3 +216,23 @@ def test_primitive_name_mapping_and_errors():
         model(('dens', 'velx', 'vely', 'velz', 'bcc1', 'eint', 'bcc2', 'bcc3'))._prim_index()
     assert m.all_meshblocks.shape == (8, 8, 10, 10, 10) and m.nprim_all == 8
     assert set(m.mb_index_map) == {(0, i, j, k) for i in range(2) for j in range(2) for k in range(2)}
+
+
+def test_file_constructor_npz_roundtrip(tmp_path):
+    """AthenakFluidModel(filename, bhspin, fluid_gamma) keeps the reference signature (athenak.py:50); .npz files
+    with the .athdf datasets are read without h5py, .athdf needs h5py (absent here -> ImportError, not a crash)."""
+    from helpers import snapshot_arrays
+    from mahakala_b200.grmhd import AthenakFluidModel
+    arr = snapshot_arrays(ncells=16, block=8, extent=8.0)
+    fn = tmp_path / "snap.npz"
+    np.savez(fn, **{k: arr[k] for k in AthenakFluidModel.DATASETS}, VariableNames=np.array(arr["VariableNames"]))
+    m = AthenakFluidModel(str(fn), 0.7, fluid_gamma=13. / 9)
+    ref = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                        arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.7, fluid_gamma=13. / 9)
+    assert np.array_equal(m.all_meshblocks, ref.all_meshblocks) and m.bhspin == 0.7 and m.fluid_gamma == 13. / 9
+    assert list(m.variable_names) == list(ref.variable_names)
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            AthenakFluidModel("missing.athdf", 0.7)
