@@ -67,8 +67,16 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
     P, units = _params_for(fluid_model, M_bh, mass_scale, r_high)
     nus = np.atleast_1d(np.asarray(observing_frequencies, dtype=np.float64))
     nfreq = nus.size
-    if not 1 <= nfreq <= 8:
-        raise ValueError("1..8 observing frequencies per launch")
+    if nfreq < 1:
+        raise ValueError("at least one observing frequency")
+    if nfreq > 8:
+        # one launch carries up to 8 frequencies (they share the geodesic and the samples); more are batched
+        if image_out is not None or queue is not None or want_counters:
+            raise ValueError("at most 8 observing frequencies per launch with image_out / queue / want_counters")
+        parts = [render(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high, nus[k:k + 8], fov,
+                        resolution, max_nsteps, s0, div, tol, None, None, patch_range, False, patch_order)
+                 for k in range(0, nfreq, 8)]
+        return torch.cat(parts, dim=0)
     c_nu = (ctypes.c_double * 8)(*(list(nus) + [nus[-1]] * (8 - nfreq)))
     if s0 is not None:
         s0d = as_device(s0)

@@ -312,3 +312,14 @@ def test_variable_order_follows_names(setup):
     for k in base:
         assert np.array_equal(np.asarray(got[k]), base[k]), k
     m.release()
+
+
+def test_more_than_eight_frequencies_are_batched(setup):
+    from mahakala_b200 import images
+    dm = setup["dm"]
+    nus = [30e9 * (1.35 ** k) for k in range(11)]
+    img = np.asarray(images.render(dm, resolution=12, observing_frequencies=nus).cpu())
+    assert img.shape == (11, 144)
+    for k in (0, 7, 8, 10):
+        one = np.asarray(images.render(dm, resolution=12, observing_frequencies=[nus[k]]).cpu())[0]
+        assert np.allclose(img[k], one, rtol=1e-10, atol=1e-14 * max(one.max(), 1e-300))
