@@ -122,10 +122,6 @@ struct KerrSchild {
         // M = sum_j D l_j v^j.  The symmetric parts of k cancel in n_i and the antisymmetric part cancels in M:
         //   n = (g1 cv - Dr c1 - 2a p2,  g2 cv - Dr c2 + 2a p1,  g3 cv - Dr c3)
         //   M = Dr cv + (r/q)(v1^2 + v2^2) + v3^2 / r
-        double a2 = a + a;
-        double n1 = fma(g1, cv, fma(-Dr, c1, -a2 * p2));
-        double n2 = fma(g2, cv, fma(-Dr, c2, a2 * p1));
-        double n3 = fma(g3, cv, -Dr * c3);
         double M = fma(Dr, cv, fma(r, fma(p1, v1, p2 * v2), (v3 * v3) * ri));
         // grad f = alpha grad r + beta delta_iz
         double alpha = rr * iden * fma(-4.0 * f, r, 6.0);
@@ -136,10 +132,11 @@ struct KerrSchild {
         double fL = f * L, hL2 = 0.5 * L * L;
         double ah = alpha * hL2;
         // lower-index force w_m = -d_k g_ms v^k v^s + 1/2 d_m g_ks v^k v^s:  w_0 = -K,  w_i = q_i - K l_i with
-        //   q_i = f L n_i + 1/2 L^2 d_i f
-        double q1 = fma(fL, n1, ah * g1);
-        double q2 = fma(fL, n2, ah * g2);
-        double q3 = fma(fL, n3, fma(ah, g3, hL2 * beta));
+        //   q_i = f L n_i + 1/2 L^2 d_i f = g_i (f L cv + alpha L^2/2) - (f L Dr) c_i + f L (antisymmetric part)
+        double A1 = fma(fL, cv, ah), B1 = fL * Dr, C1 = fL * (a + a);
+        double q1 = fma(g1, A1, fma(-B1, c1, -C1 * p2));
+        double q2 = fma(g2, A1, fma(-B1, c2, C1 * p1));
+        double q3 = fma(g3, A1, fma(-B1, c3, hL2 * beta));
         // raise with g^mn = eta^mn - f l^m l^n.  P = l^n w_n = K + l.w = K - K |l|^2 + l.q = l.q because the
         // spatial part of the null vector l has unit Euclidean length (l1^2 + l2^2 + l3^2 = 1 analytically).
         double P = fma(l1, q1, fma(l2, q2, l3 * q3));
