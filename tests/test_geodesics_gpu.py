@@ -367,3 +367,13 @@ def test_classification_sweep_spins_and_inclinations(ma):
         assert np.array_equal(np.asarray(n.cpu())[esc], ref["nsteps"][esc]), (a, inc)
         assert 0 < cap_ref.sum() < cap.size, (a, inc)
     assert mism == 0, f"{mism} of {total} rays classified differently"
+
+
+def test_notebook_trajectory_shape_through_dropin(ma):
+    """demos/shadows.ipynb cells 4-5 verbatim through the drop-in API: S.shape == (819, 60, 8)."""
+    bhspin, lim, spacing = 0.0, 15, 60
+    s0 = ma.initialize_geodesics_at_camera(bhspin, 60, 1000, -lim, lim, spacing, camera_type='Equator')
+    S, final_dt = ma.geodesic_integrator(10000, s0, 40, 1e-4, bhspin)
+    assert tuple(S.shape) == (819, 60, 8) and tuple(final_dt.shape) == (819, 60)
+    x, y = np.asarray(S[:, :, 1]), np.asarray(S[:, :, 2])
+    assert int((np.sqrt(x * x + y * y).min(axis=0) < 2.01).sum()) == 20      # the rays the notebook draws in red

@@ -135,3 +135,15 @@ def test_oracle_reproduces_frozen_fixtures(built):
         else:
             # same source, same compiler flags -> normally bit-identical; allow libm differences between hosts
             assert np.allclose(want[k], got[k], rtol=1e-9, atol=1e-300, equal_nan=True), k
+
+
+def test_notebook_trajectory_shape_pin(oracles):
+    """A second reference-produced number: demos/shadows.ipynb (cells 4-5) integrates an equatorial camera with
+    bhspin = 0, lim = 15, 60 rays, N = 10000, div = 40, tol = 1e-4 and prints S.shape == (819, 60, 8).  That pins
+    the 'Equator' camera, nullify, the integrator's termination rule and the +2 truncation."""
+    onp, oc = oracles
+    s0 = onp.initialize_geodesics_at_camera(0.0, 60, 1000, -15, 15, 60, camera_type='Equator')
+    S, dt = oc.geodesic_integrator(10000, s0, 40, 1e-4, 0.0)
+    assert S.shape == (819, 60, 8) and dt.shape == (819, 60)
+    S2, dt2 = onp.geodesic_integrator(10000, s0[::12], 40, 1e-4, 0.0)
+    assert S2.shape[0] <= 819 and np.array_equal(dt2 == 0, dt[:S2.shape[0], ::12] == 0)
