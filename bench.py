@@ -445,6 +445,27 @@ def render_leg(args, rank, world, dev):
             fl = float(out.sum())
         return float(np.mean(st)), fl
 
+    # The only timing the reference publishes for this path (demos/grmhd_detailed.ipynb cells 10-11, hardware not
+    # stated): get_fluid_scalars_from_geodesics on the trajectories of a 160x160 image, 456 meshblocks: 31.8 s for
+    # the meshblock-index loop + 0.96 s for the sampling scan.  Same call here (512 meshblocks of 32^3).
+    stage = None
+    if rank == 0:
+        from mahakala_b200 import geodesics as geo
+        s160 = geo.initialize_geodesics_at_camera(CFG2["bhspin"], 60, 1000, -10, 10, 160)
+        S160, dt160 = geo.geodesic_integrator(CFG2["N"], s160, 40, 1e-4, CFG2["bhspin"])
+        model.get_fluid_scalars_from_geodesics(S160)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.get_fluid_scalars_from_geodesics(S160)
+        e1.record()
+        torch.cuda.synchronize()
+        stage = {"call": "AthenakFluidModel.get_fluid_scalars_from_geodesics(S), 160x160 rays", "rows": int(S160.shape[0]),
+                 "samples": int(S160.shape[0] * S160.shape[1]), "ms": e0.elapsed_time(e1),
+                 "reference_notebook_s": {"meshblock_index_loop": 31.81, "sampling_scan": 0.957,
+                                          "source": "demos/grmhd_detailed.ipynb cell 10 (456 meshblocks, hardware not stated)"}}
+        del S160, dt160
+        torch.cuda.empty_cache()
     strong, flux = strong_leg(res, 3) if world > 1 else (0.0, 0.0)
     strong_big, flux_big = strong_leg(args.strong_res, 2) if args.strong_res > 0 else (0.0, 0.0)
     t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong, bcast_ms, strong_big], dtype=torch.float64, device=dev)
@@ -460,6 +481,8 @@ def render_leg(args, rank, world, dev):
            "ray_steps_per_s": steps / (ms * 1e-3),
            "sampling_algorithmic_GBps": samples * (256 if model.storage == "f32" else 512) / (ms * 1e-3) / 1e9,
            "snapshot_bytes": model.snapshot_bytes(), "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
+    if stage is not None:
+        out["sampling_stage_160px"] = stage
     if args.strong_res > 0:
         out["strong_scaling_large_image"] = {"resolution": args.strong_res, "ms": float(t[4]), "image_sum": flux_big,
                                              "note": "ONE cfg5-sized frame rendered by all ranks together"}
