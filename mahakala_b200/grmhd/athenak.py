@@ -22,6 +22,18 @@ from .. import _cabi
 from .._device import DeviceArray, as_device, empty, require_gpu, stream_ptr
 from .grmhd import GRMHDFluidModel
 
+def vec_metric(X, bhspin):
+    """athenak.py:38-40: covariant metric at a batch of points (the device kernel is batched already)."""
+    from ..geodesics import metric
+    return metric(X, bhspin)
+
+
+def vec_imetric(X, bhspin):
+    """athenak.py:43-45: contravariant metric at a batch of points."""
+    from ..geodesics import imetric
+    return imetric(X, bhspin)
+
+
 CANONICAL_PRIMS = ('dens', 'eint', 'velx', 'vely', 'velz', 'bcc1', 'bcc2', 'bcc3')
 
 
