@@ -15,6 +15,7 @@
 // the lanes of a warp traverse the same snapshot cells at the same time) from a global atomic queue.  The
 // queue counter and the image may live in a peer GPU's memory: several GPUs then share ONE dynamic tile
 // queue over NVLink and write finished pixels straight into the gathering rank's image.
+#include <cstdlib>
 #include "common.cuh"
 #include "camera.cuh"
 #include "integrate.cuh"
@@ -201,9 +202,107 @@ __global__ void __launch_bounds__(128, (NF >= MK_RENDER_SPLIT) ? 4 : MK_RENDER_L
     }
 }
 
+#ifdef MK_EXPERIMENTS
+// EXPERIMENT (compiled only with -DMK_EXPERIMENTS, e.g. scripts/build_variant.sh "-DMK_EXPERIMENTS"; not part
+// of the product library): lane-level refill for the fused kernel.  Idle lanes take single pixels from a
+// pixel-granular queue (same centre-out patch order) as soon as at least `thr` lanes of the warp are idle.
+// Measured on B200 (cfg4, scripts/dev/refill_probe.py): thr = 1 / 8 / 16 / 24 / 32 -> 54.1 / 48.6 / 40.5 / 34.8 /
+// 28.2 ms against 27.7 ms for whole patches, i.e. incoherent warps cost far more than idle tail lanes.
+__global__ void __launch_bounds__(128, 3) render_refill_kernel(const RenderArgs A, int thr)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    long ray = -1;
+    bool drained = false;
+    double s[8], I = 0.0, T = 1.0, dt = 0.0, wdt = 0.0;
+    int it = 0;
+    bool pending = false;
+    KerrSchild::Cache cache, cache_new;
+    const long total = (A.patch_end - A.patch_begin) * 32;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL_MASK, ray < 0);
+        if (idle) {
+            if (!drained && (__popc(idle) >= thr || idle == FULL_MASK)) {
+                int cnt = __popc(idle);
+                unsigned base = 0;
+                int leader = __ffs(idle) - 1;
+                if ((int)lane == leader) base = atomicAdd(A.queue, (unsigned)cnt);
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if ((long)base + cnt >= total) drained = true;
+                if (ray < 0) {
+                    long q = (long)base + __popc(idle & ((1u << lane) - 1u));
+                    if (q < total) {
+                        long patch = A.patch_begin + (q >> 5);
+                        if (A.patch_order) patch = A.patch_order[patch];
+                        unsigned k = (unsigned)(q & 31);
+                        long px = patch / A.patches_y, py = patch - px * A.patches_y;
+                        long ix = px * PATCH_X + (k >> 3), iy = py * PATCH_Y + (k & 7u);
+                        if (ix < A.res && iy < A.res) {
+                            ray = ix * A.res + iy;
+                            double x[4], v[4];
+                            camera_point(A.cam, pixel_centre(A.fov_lo, A.step, ix), pixel_centre(A.fov_lo, A.step, iy), x, v);
+                            nullify_state(A.g, x, v, s);
+                            dt = A.rule(A.g.radius(s, cache));
+                            I = 0.0; T = 1.0; it = 0; pending = false;
+                            if (dt == 0.0) { A.image[ray] = 0.0; ray = -1; }
+                        }
+                    }
+                }
+            }
+            if (__ballot_sync(FULL_MASK, ray >= 0) == 0) {
+                if (drained) break;
+                continue;
+            }
+        }
+        if (ray < 0) continue;
+        double cand[8], prims[8], dtn;
+        if (pending && interp_prims(A.sn, s, prims)) {
+            double f, l[4], em[1], ab[1];
+            l[0] = 1.0;
+            A.g.fl(s, cache, f, l[1], l[2], l[3]);
+            emission_fast<1>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
+            rk4_step(A.g, s, dt, cand, &cache);
+            dtn = A.rule(A.g.radius(cand, cache_new));
+            I = fma(T, wdt * em[0], I);
+            T = T * fma(-wdt, ab[0], 1.0);
+        } else {
+            rk4_step(A.g, s, dt, cand, &cache);
+            dtn = A.rule(A.g.radius(cand, cache_new));
+        }
+        bool done = (dtn == 0.0);
+        if (!done) {
+            wdt = -dt * A.P.L_unit;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s[i] = cand[i];
+            cache = cache_new;
+            dt = dtn;
+            it++;
+            pending = true;
+            if (it == A.N) done = true;
+        }
+        if (done) {
+            A.image[ray] = I;
+            ray = -1;
+        }
+    }
+}
+
+#endif  // MK_EXPERIMENTS
+
 template <int NF>
 static int launch_render(const RenderArgs& A, long npatches, cudaStream_t stream)
 {
+#ifdef MK_EXPERIMENTS
+    if (NF == 1 && !A.s0) {
+        static int thr = -2;
+        if (thr == -2) { const char* e = getenv("MK_RENDER_REFILL_THR"); thr = e ? atoi(e) : -1; }
+        if (thr >= 1) {
+            long blocks = (long)sm_count() * 3;
+            render_refill_kernel<<<(unsigned)blocks, 128, 0, stream>>>(A, thr);
+            MK_CUDA_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
+#endif
     int per_sm = 0;
     MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF>, 128, 0));
     if (per_sm < 1) per_sm = 1;
