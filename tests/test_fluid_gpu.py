@@ -323,3 +323,15 @@ def test_more_than_eight_frequencies_are_batched(setup):
     for k in (0, 7, 8, 10):
         one = np.asarray(images.render(dm, resolution=12, observing_frequencies=[nus[k]]).cpu())[0]
         assert np.allclose(img[k], one, rtol=1e-10, atol=1e-14 * max(one.max(), 1e-300))
+
+
+def test_unfused_chunking_is_transparent(setup):
+    """images.py:62-78: max_chunk_bytes only changes how many pixels go through the pipeline at once."""
+    from mahakala_b200 import images
+    dm = setup["dm"]
+    whole = images.make_image_unfused(dm, resolution=12)
+    # int(max_chunk_bytes // 4 // 20 // max_nsteps) pixels per chunk (images.py:69): 50 px -> 3 chunks of 144 px
+    chunked = images.make_image_unfused(dm, resolution=12, max_chunk_bytes=50 * 4 * 20 * 10000)
+    assert np.array_equal(whole, chunked)
+    fused = images.make_image(dm, resolution=12, max_chunk_bytes=1e9)        # accepted, irrelevant for the fused path
+    assert np.allclose(fused, whole, rtol=1e-9, atol=1e-14 * whole.max())
