@@ -30,6 +30,8 @@ extern "C" {
 /* built-in spacetimes (metric plugins compiled into the library) */
 #define MK_METRIC_KERR_SCHILD 0      /* closed-form Cartesian Kerr-Schild: geodesics.py:88-104 */
 #define MK_METRIC_KERR_SCHILD_DUAL 1 /* same metric through the generic dual-number plugin path */
+#define MK_METRIC_KERR_SCHILD_STRICT 2 /* literal jets + 4x4 inverse in non-contracted IEEE arithmetic: bit-identical to
+                                        the CPU restatement of geodesics.py:233-351; mk_integrate final-state mode only */
 #define MK_METRIC_PLUGIN_BASE 16     /* ids >= 16: spacetimes registered at run time (mk_register_metric) */
 
 /* ---- library ------------------------------------------------------------------------------- */

@@ -39,6 +39,9 @@ __global__ void fill_frozen_rows_kernel(double* S, double* dt, const double* fin
     }
 }
 
+int strict_integrate(double bhspin, long N, long npx, const double* s0, double div, double tol, double* final_state,
+                     int* nsteps, double* r_last, unsigned long long* total_steps, cudaStream_t stream);
+
 template <class Metric>
 static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_t stream)
 {
@@ -98,6 +101,13 @@ static int dispatch_integrate(int metric_id, double bhspin, IntegrateArgs& A, cu
         DualMetric<KerrSchildFn> g; g.fn.a = bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
         A.rule.rH = g.rH;
         rc = launch_integrate(g, A, stream);
+    } else if (metric_id == MK_METRIC_KERR_SCHILD_STRICT) {
+        if (A.S || A.pages) {
+            set_error("the strict (literal IEEE) integrator provides final states only; use a dump mode of the default metric");
+            return 2;
+        }
+        rc = strict_integrate(bhspin, A.N, A.npx, A.s0, A.rule.div, A.rule.tol, A.final_state, A.nsteps, A.r_last,
+                              A.total_steps, stream);
     } else if (metric_id >= MK_METRIC_PLUGIN_BASE) {
         rc = plugin_integrate(metric_id, bhspin, A, stream);
     } else {

@@ -13,8 +13,9 @@ from ._device import DeviceArray, as_device, empty, require_gpu, stream_ptr
 
 KERR_SCHILD = 0
 KERR_SCHILD_DUAL = 1
+KERR_SCHILD_STRICT = 2       # literal IEEE evaluation (integrate_final only), bit-identical to the CPU restatement
 
-_METRICS = {"kerr_schild": KERR_SCHILD, "kerr_schild_dual": KERR_SCHILD_DUAL}
+_METRICS = {"kerr_schild": KERR_SCHILD, "kerr_schild_dual": KERR_SCHILD_DUAL, "kerr_schild_strict": KERR_SCHILD_STRICT}
 _active_metric = KERR_SCHILD
 
 

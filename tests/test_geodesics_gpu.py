@@ -377,3 +377,38 @@ def test_notebook_trajectory_shape_through_dropin(ma):
     assert tuple(S.shape) == (819, 60, 8) and tuple(final_dt.shape) == (819, 60)
     x, y = np.asarray(S[:, :, 1]), np.asarray(S[:, :, 2])
     assert int((np.sqrt(x * x + y * y).min(axis=0) < 2.01).sum()) == 20      # the rays the notebook draws in red
+
+
+def test_strict_mode_is_bit_identical_to_the_oracle(ma):
+    """The literal IEEE evaluation on the GPU (metric 'kerr_schild_strict', no FMA contraction) reproduces the C
+    restatement BIT FOR BIT on every ray, captured ones included: same algorithm, same arithmetic.  The fast
+    closed-form kernel is then compared against it at the tolerance level."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    from mahakala_b200 import geodesics as geo
+    s0 = onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 64)
+    ref = c_oracle.integrate(2000, s0, 40, 1e-2, A)
+    geo.set_metric("kerr_schild_strict")
+    try:
+        f, n, rl, tot = geo.integrate_final(2000, s0, 40, 1e-2, A, want_total=True)
+        with pytest.raises(Exception, match="final states only"):
+            geo.integrate_paged(50, s0[:4], 40, 1e-2, A)
+    finally:
+        geo.set_metric("kerr_schild")
+    f, n, rl = (np.asarray(q.cpu()) for q in (f, n, rl))
+    assert np.array_equal(n, ref["nsteps"]) and int(tot) == int(ref["nsteps"].sum()) == 2079364
+    assert np.array_equal(f, ref["final"])                 # all 4096 rays, all 8 components, every bit
+    assert np.array_equal(rl, ref["r_last"])
+    # second configuration: imaging tolerance, other spin / inclination
+    s1 = onp.initialize_geodesics_at_camera(0.5, 30, 1000, -8, 8, 24)
+    ref1 = c_oracle.integrate(10000, s1, 40, 1e-4, 0.5)
+    geo.set_metric("kerr_schild_strict")
+    try:
+        f1, n1, rl1 = geo.integrate_final(10000, s1, 40, 1e-4, 0.5)
+    finally:
+        geo.set_metric("kerr_schild")
+    assert np.array_equal(np.asarray(f1.cpu()), ref1["final"]) and np.array_equal(np.asarray(n1.cpu()), ref1["nsteps"])
+    # fast kernel vs strict kernel on the GPU: the 1e-9 bar on escaped rays
+    ff, nf, rlf = geo.integrate_final(2000, s0, 40, 1e-2, A)
+    esc = rl >= 100
+    d = np.abs(np.asarray(ff.cpu())[esc] - f[esc]).max(axis=1) / np.abs(f[esc]).max(axis=1)
+    assert d.max() < 1e-9 and np.array_equal(np.asarray(nf.cpu())[esc], n[esc])
