@@ -3,7 +3,7 @@
 // (geodesics.py:347), the contraction of geodesics.py:307, RK4 as geodesics.py:317-336 and the step rule as
 // geodesics.py:249-267 — in plain IEEE double arithmetic.  This file is compiled with --fmad=false, so no
 // multiply-add is contracted and every +, -, *, /, sqrt rounds exactly as on the CPU; the results are
-// BIT-IDENTICAL to the scalar C restatement used as the test oracle (tests assert equality, not closeness).
+// BIT-IDENTICAL to the scalar C restatement that the tests use as their checker (they assert equality, not closeness).
 // It exists to separate two questions: "is the GPU evaluating the same algorithm?" (strict mode, bit-exact)
 // and "how far may the optimised closed-form kernel drift?" (fast mode, <= 1e-9).
 // ~8x slower than the closed-form kernel; final-state outputs only.
