@@ -45,6 +45,10 @@ int mk_measure_fp64_peak(int iters, double* tflops_out, double* ms_out);
 /* evaluates the kernels' MUFU-seeded reciprocal, square root and reciprocal square root on x (n,) so that
    their accuracy can be checked against IEEE results (positive normal inputs) */
 int mk_fast_math_probe(const double* x, long n, double* rcp, double* sqrt_out, double* rsqrt_out, void* stream);
+/* the fused render kernel's exp(-x) (x >= 0) and cube root / reciprocal cube root (positive x inside the float
+   range) evaluated on x (n,), for accuracy checks against libm */
+int mk_transcendental_probe(const double* x, long n, double* exp_neg, double* cbrt_out, double* rcbrt_out,
+                            void* stream);
 
 /* ---- user-registered spacetimes ------------------------------------------------------------------ */
 /*
@@ -148,6 +152,28 @@ int mk_snapshot_create(long nmb, long nk, long nj, long ni, const double* meshbl
                        const double* geom, const int* grid, const int* gn, const double* g0,
                        const double* ginv, const double* bbox_lo, const double* bbox_hi, int store_f32,
                        mk_snapshot** out, void* stream);
+/*
+ * Same snapshot, built straight from the arrays an AthenaK .athdf file holds: the ghost-zone fill of the
+ * reference's loader (athenak.py:105-158 layout, :208-229 same-level copy, :231-514 refinement boundaries:
+ * coarser neighbour -> injection, finer neighbour -> mean of the 8 covered cells, domain boundary -> 0) runs
+ * on the GPU fused with the repack, so no ghost-padded host array and no (nmb, 8, nk+2, nj+2, ni+2) upload
+ * is needed.  DEVICE arrays: uov (n_uov, nmb, nk, nj, ni) and B (n_B, nmb, nk, nj, ni), n_uov + n_B == 8,
+ * float32 (src_f32 != 0, what AthenaK writes) or float64; geom / grid as above.  HOST arrays:
+ * logical_locations (nmb, 3) int32 = (li, lj, lk) and levels (nmb) int32 (athenak.py:160-206), prim_index[8] =
+ * position of dens, eint, velx, vely, velz, bcc1, bcc2, bcc3 in the concatenation [uov..., B...].
+ * store_mode: 0 = float64 cells, 1 = float32 cells, 2 = float32 when every stored value (ghost averages
+ * included) is float32-representable, else float64; *stored_f32 (optional) reports the choice.
+ * Synchronous with respect to `stream` on return.
+ */
+int mk_snapshot_create_from_interiors(long nmb, long nk, long nj, long ni, const void* uov, int n_uov,
+                                      const void* B, int n_B, int src_f32, const int* prim_index,
+                                      const int* logical_locations, const int* levels, const double* geom,
+                                      const int* grid, const int* gn, const double* g0, const double* ginv,
+                                      const double* bbox_lo, const double* bbox_hi, int store_mode,
+                                      int* stored_f32, mk_snapshot** out, void* stream);
+/* inverse of the repack: cells -> the reference's self.all_meshblocks (nmb, 8, nk+2, nj+2, ni+2) float64
+   (device), primitive q of the canonical order written to position prim_index[q] */
+int mk_snapshot_unpack(const mk_snapshot* snap, const int* prim_index, double* meshblocks, void* stream);
 /* Analytic fluid source instead of snapshot cells (BASELINE cfg3: Keplerian thin torus, power-law density,
    toroidal field at fixed beta; not in the reference).  params9 (host) = {fluid_gamma, R0,
    R_in, p, h, u0, beta0, dens_scale, r_out}.  The handle works with every mk_sample_* / mk_render call. */

@@ -18,6 +18,7 @@ SIGNATURES = {
     "mk_device_info": "ppppp",
     "mk_measure_fp64_peak": "ipp",
     "mk_fast_math_probe": "plpppp",
+    "mk_transcendental_probe": "plpppp",
     "mk_register_metric": "pppppl",
     "mk_metric_set_params": "ip",
     "mk_initial_condition_metric": "idpplpp",
@@ -33,6 +34,8 @@ SIGNATURES = {
     "mk_rk4_step": "idpplpp",
     "mk_metric": "idplppp",
     "mk_snapshot_create": "llllpppppppppipp",
+    "mk_snapshot_create_from_interiors": "llll" "pipii" "ppp" "ppppppp" "i" "ppp",
+    "mk_snapshot_unpack": "pppp",
     "mk_snapshot_create_torus": "pp",
     "mk_snapshot_destroy": "p",
     "mk_snapshot_cells": "ppp",

@@ -111,6 +111,16 @@ __global__ void fast_math_probe_kernel(const double* x, long n, double* rcp, dou
     rsq[i] = r;
 }
 
+__global__ void transcendental_probe_kernel(const double* x, long n, double* expneg, double* cbrt_out, double* icbrt)
+{
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    expneg[i] = fast_exp_neg(x[i]);
+    cbrt_out[i] = fast_cbrt_pos(x[i], r);
+    icbrt[i] = r;
+}
+
 template <class Metric>
 __global__ void rk4_kernel(Metric g, const double* state, const double* dt, long n, double* out)
 {
@@ -312,6 +322,16 @@ extern "C" int mk_fast_math_probe(const double* x, long n, double* rcp, double* 
     if (n <= 0) return 0;
     MK_REQUIRE(x && rcp && sq && rsq, "null pointer");
     fast_math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, rcp, sq, rsq);
+    MK_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mk_transcendental_probe(const double* x, long n, double* expneg, double* cbrt_out, double* icbrt,
+                                       void* stream)
+{
+    if (n <= 0) return 0;
+    MK_REQUIRE(x && expneg && cbrt_out && icbrt, "null pointer");
+    transcendental_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, expneg, cbrt_out, icbrt);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -88,4 +88,52 @@ __device__ __forceinline__ double fast_div(double a, double b)
     return fma(e, y, q);
 }
 
+// exp(-t) for t >= 0 (the synchrotron cut-off e^{-X^{1/3}}, transfer.py:66): k = rint(-t log2 e) by the 1.5 * 2^52
+// trick, r = -t - k ln 2 in two FMAs (|r| <= 0.347), degree-13 Taylor polynomial (truncation 4e-18), 2^k by an
+// integer add to the exponent field: 17 FP64 + 4 integer instructions against ~53 for exp().  <= ~1 ulp for
+// t <= 707; beyond (result < 9e-308, where exp() would return subnormals) the result is flushed to 0.  NaN -> NaN.
+__device__ __forceinline__ double fast_exp_neg(double t)
+{
+    const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
+    double kd = fma(-t, 1.4426950408889634, MAGIC);
+    int k = __double2loint(kd);
+    double kf = kd - MAGIC;
+    double r = fma(-kf, 6.93147180369123816490e-01, -t);     // ln2 split hi / lo (fdlibm)
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                       // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                     // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                    // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                    // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                   // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                     // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                    // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                    // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                    // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                   // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                   // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double y = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return (t > 707.0) ? 0.0 : y;
+}
+
+// cbrt(x) for positive normal x well inside the float range: seed r0 = x^(-1/3) from the single-precision
+// MUFU pair lg2 / ex2 (relative error <~ 5e-6 over 1e-30 < x < 1e30), one quartically convergent FMA-only step
+//   r1 = r0 (1 + e/3 + 2 e^2/9 + 14 e^3/81),  e = 1 - x r0^3      (truncation 35 e^4 / 243 < 1e-19)
+// and cbrt(x) = x r1^2: ~15 instructions against ~40 for cbrt(); <= ~4 ulp.  Returns x^(1/3); rinv = x^(-1/3).
+__device__ __forceinline__ double fast_cbrt_pos(double x, double& rinv)
+{
+    float xf = (float)x, lg, r0f;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0f) : "f"(lg * -0.33333334f));
+    double r0 = (double)r0f;
+    double r2 = r0 * r0;
+    double e = fma(-x * r0, r2, 1.0);
+    double p = fma(fma(e, 14.0 / 81.0, 2.0 / 9.0), e, 1.0 / 3.0) * e;
+    double r = fma(r0, p, r0);
+    rinv = r;
+    return (x * r) * r;
+}
+
 }  // namespace mk

@@ -29,6 +29,7 @@ struct SnapshotView {
     const void* cells;        // AoS cells, f64 or f32
     int is_f32;
     int nmb, nk, nj, ni;      // interior cells per block
+    long sj, sk, sb;          // element strides of the padded cell array: next j row, next k plane, next block
     // per-block geometry (nmb, 12): lo[3], hi[3] face extents, v0[3] first cell centre, dx[3] cell size;
     // one 96 B record per block so that a lookup costs one round of 256-bit loads instead of 12 dependent ones
     const double* geom;
@@ -127,9 +128,9 @@ __device__ __forceinline__ void cell_index(double x, double v0, double dx, int& 
     double q = floor(qd);
     delta = qd - q;                       // python float % 1. for qd >= 0
     double rem = fma(-q, dx, xi);         // exact floor division (np.floor_divide works from fmod)
-    if (rem < 0.0) q -= 1.0;
-    else if (rem >= dx) q += 1.0;
     idx = (int)q;
+    if (rem < 0.0) idx -= 1;
+    if (rem >= dx) idx += 1;
 }
 
 __device__ __forceinline__ void load_cell_pair(const double* p, double a[8], double b[8])
@@ -173,8 +174,8 @@ __device__ __forceinline__ void trilinear(const SnapshotView& sn, int mb, const 
     cell_index(x[3], geo.v0[2], geo.dx[2], i3, d3);
     // in-block points have indices in [0, n]; clamp defensively so that no load can leave the block
     i1 = min(max(i1, 0), sn.ni); i2 = min(max(i2, 0), sn.nj); i3 = min(max(i3, 0), sn.nk);
-    const long sj = (long)(sn.ni + 2) * 8, sk = sj * (sn.nj + 2);
-    const CellT* base = reinterpret_cast<const CellT*>(sn.cells) + (long)mb * sk * (sn.nk + 2) + i3 * sk + i2 * sj + (long)i1 * 8;
+    const long sj = sn.sj, sk = sn.sk;
+    const CellT* base = reinterpret_cast<const CellT*>(sn.cells) + (mb * sn.sb + i3 * sk + i2 * sj + (long)(i1 * 8));
     const double e1 = 1.0 - d1, e2 = 1.0 - d2, e3 = 1.0 - d3;
 #pragma unroll
     for (int q = 0; q < 8; q++) prims[q] = 0.0;
@@ -423,8 +424,10 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     valid &= (bsq > 0.0) & (kdotu < 0.0);
     double b, ib;
     quick_sqrt_rsqrt(bsq, b, ib);
-    double c = kdotb * ib * fast_rcp(-kdotu);                    // cos(pitch), athenak.py:789
-    c = fmin(fmax(c, -1.0), 1.0);
+    // cos(pitch), athenak.py:789-791.  The reference clamps it to [-1, 1]; a clamped value gives sin = 0, hence
+    // nu_s = 0, X = inf and zero emissivity, which is what "sin2 > 0 fails" yields here without the clamp
+    // (NaN also fails the test)
+    double c = kdotb * ib * fast_rcp(-kdotu);
     double sin2 = (1.0 - c) * (1.0 + c);
     valid &= (sin2 > 0.0);
     double sinp = quick_sqrt(sin2);
@@ -446,7 +449,9 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     // quantities of frequency 0; frequency f scales them by powers of nu_f / nu_0
     double nu0 = -kdotu * C.nu0;
     double X0 = nu0 * inus;
-    double x13_0 = cbrt(X0);
+    double ix13_0;
+    double x13_0 = fast_cbrt_pos(X0, ix13_0);
+    if (valid && !((X0 > 1e-30) & (X0 < 1e30))) x13_0 = cbrt(X0);     // outside the float-seeded range (rare)
     double x16_0 = quick_sqrt(x13_0);
     double bx0 = C.k_bx * nu0 * ith;
     double inu0 = fast_rcp(nu0);
@@ -461,7 +466,7 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
         double x13 = x13_0 * C.c13[fq];
         double x16 = x16_0 * C.c16[fq];
         double term = fma(x16 * x16, x16, P.two_11_12 * x16);
-        double e = pref * (term * term) * exp(-x13);
+        double e = pref * (term * term) * fast_exp_neg(x13);
         double bx = bx0 * C.ratio[fq];
         double den = (bx < 2.e-3) ? bx * (1. / 24.) * fma(bx, fma(bx, 4. + bx, 12.), 24.) : exp(bx) - 1.0;
         double ir = C.iratio[fq];

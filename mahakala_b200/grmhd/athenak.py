@@ -284,17 +284,19 @@ class AthenakFluidModel(DeviceSampledFluidModel):
     @classmethod
     def from_arrays(cls, uov, B, x1v, x2v, x3v, x1f, x2f, x3f, LogicalLocations, Levels, bhspin,
                     fluid_gamma=None, VariableNames=('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'),
-                    storage='auto', lookup='auto'):
+                    storage='auto', lookup='auto', ghost_fill='device'):
         """Construct from the arrays of an ``.athdf`` file (athenak.py:79-103) without touching disk.
 
         storage: 'f64', 'f32' or 'auto' (float32 cells when every value is float32-representable —
         AthenaK writes float32 — which halves the sampling traffic without changing a single bit).
         lookup: 'grid' (O(1) block table), 'scan' (the reference's linear scan) or 'auto'.
+        ghost_fill: 'device' (ghost zones filled by the CUDA kernel that repacks the snapshot; only the interior
+        arrays are uploaded) or 'host' (NumPy fill + upload of the padded blocks, the reference's route).
         """
         self = cls.__new__(cls)
         self._setup(uov=uov, B=B, x1v=x1v, x2v=x2v, x3v=x3v, x1f=x1f, x2f=x2f, x3f=x3f,
                     LogicalLocations=LogicalLocations, Levels=Levels, VariableNames=VariableNames,
-                    bhspin=bhspin, fluid_gamma=fluid_gamma, storage=storage, lookup=lookup)
+                    bhspin=bhspin, fluid_gamma=fluid_gamma, storage=storage, lookup=lookup, ghost_fill=ghost_fill)
         return self
 
     @classmethod
@@ -304,7 +306,8 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         self = cls.__new__(cls)
         self.bhspin, self.fluid_gamma = bhspin, fluid_gamma
         self.variable_names = np.array(list(VariableNames))
-        self.all_meshblocks = None
+        self._uov = self._B = self._amb = None
+        self._ghost_fill = 'host'
         self._block_shape = tuple(int(q) for q in block_shape)
         self.x1v, self.x2v, self.x3v = (np.asarray(q, dtype=np.float64) for q in (x1v, x2v, x3v))
         self.x1f, self.x2f, self.x3f = (np.asarray(q, dtype=np.float64) for q in (x1f, x2f, x3f))
@@ -317,7 +320,7 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         """What another rank needs to build a ``replica`` of this model."""
         return dict(x1v=self.x1v, x2v=self.x2v, x3v=self.x3v, x1f=self.x1f, x2f=self.x2f, x3f=self.x3f,
                     bhspin=self.bhspin, fluid_gamma=self.fluid_gamma, VariableNames=list(self.variable_names),
-                    block_shape=self.all_meshblocks.shape if self.all_meshblocks is not None else self._block_shape,
+                    block_shape=self._block_shape,
                     storage=self.storage)
 
     DATASETS = ('x1v', 'x2v', 'x3v', 'x1f', 'x2f', 'x3f', 'uov', 'B', 'LogicalLocations', 'Levels')
@@ -343,20 +346,48 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         return out
 
     def _setup(self, uov, B, x1v, x2v, x3v, x1f, x2f, x3f, LogicalLocations, Levels, VariableNames, bhspin,
-               fluid_gamma, storage='auto', lookup='auto'):
+               fluid_gamma, storage='auto', lookup='auto', ghost_fill='device'):
+        if ghost_fill not in ('device', 'host'):
+            raise ValueError("ghost_fill must be 'device' or 'host'")
         self.bhspin = bhspin
         self.fluid_gamma = fluid_gamma
         self.variable_names = np.array(list(VariableNames))
-        self.all_meshblocks, self.mb_index_map = fill_ghost_zones(uov, B, LogicalLocations, Levels)
+        # interior arrays as the file holds them; float32 input (what AthenaK writes) is kept as float32
+        keep = lambda a: np.asarray(a) if np.asarray(a).dtype == np.float32 else np.asarray(a, dtype=np.float64)
+        self._uov, self._B = keep(uov), keep(B)
+        if self._uov.ndim != 5 or self._B.ndim != 5 or self._uov.shape[1:] != self._B.shape[1:]:
+            raise ValueError("uov and B must have shapes (nvar, nmb, nk, nj, ni) with equal block shapes")
+        if self._uov.shape[0] + self._B.shape[0] != 8:
+            raise ValueError("uov and B must hold 8 primitives together")
+        nmb, nk, nj, ni = self._uov.shape[1:]
+        self._block_shape = (nmb, 8, nk + 2, nj + 2, ni + 2)
+        self._amb = None
+        self._ghost_fill = ghost_fill
         self.x1v, self.x2v, self.x3v = (np.asarray(q, dtype=np.float64) for q in (x1v, x2v, x3v))
         self.x1f, self.x2f, self.x3f = (np.asarray(q, dtype=np.float64) for q in (x1f, x2f, x3f))
         self.Levels = np.asarray(Levels)
         self.LogicalLocations = np.asarray(LogicalLocations)
+        self.mb_index_map = {(int(self.Levels[mb]),) + tuple(int(q) for q in self.LogicalLocations[mb]): mb
+                             for mb in range(nmb)}
         self.nprim_all = 8
         self._storage = storage
         self._lookup = lookup
         self._snap = None
         self._snap_device = None
+
+    @property
+    def all_meshblocks(self):
+        """The reference's ghost-padded ``(nmb, 8, nk+2, nj+2, ni+2)`` array (athenak.py:105-158), built on the
+        host on first access.  The device snapshot does not need it (``ghost_fill='device'``)."""
+        if self._amb is None and self._uov is not None:
+            self._amb, _ = fill_ghost_zones(self._uov, self._B, self.LogicalLocations, self.Levels)
+        return self._amb
+
+    def device_meshblocks(self):
+        """``all_meshblocks`` as reconstructed from the device snapshot cells (``mk_snapshot_unpack``)."""
+        out = empty(self._block_shape)
+        _cabi.call("mk_snapshot_unpack", self.snapshot(), (ctypes.c_int * 8)(*self._prim_index()), out, stream_ptr())
+        return DeviceArray.wrap(out)
 
     def get_index_for_primitive_by_name(self, prim):
         """athenak.py:55-65."""
@@ -383,16 +414,16 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         dev = require_gpu()
         if self._snap is not None and self._snap_device == dev:
             return self._snap
-        amb = self.all_meshblocks
-        if amb is None:
-            if fill:
-                raise ValueError("a replica model has no host data: fill it with multigpu.replicate_snapshot")
-            nmb, _, nk2, nj2, ni2 = self._block_shape
-        else:
-            nmb, _, nk2, nj2, ni2 = amb.shape
+        nmb, _, nk2, nj2, ni2 = self._block_shape
+        if self._uov is None and fill:
+            raise ValueError("a replica model has no host data: fill it with multigpu.replicate_snapshot")
+        on_device = fill and self._ghost_fill == 'device'
         storage = self._storage
-        if storage == 'auto':
-            storage = 'f32' if np.array_equal(amb.astype(np.float32).astype(np.float64), amb) else 'f64'
+        amb = None
+        if fill and not on_device:
+            amb = self.all_meshblocks
+            if storage == 'auto':
+                storage = 'f32' if np.array_equal(amb.astype(np.float32).astype(np.float64), amb) else 'f64'
         geom = np.stack([self.x1f[:, 0], self.x2f[:, 0], self.x3f[:, 0],
                          self.x1f[:, -1], self.x2f[:, -1], self.x3f[:, -1],
                          self.x1v[:, 0], self.x2v[:, 0], self.x3v[:, 0],
@@ -407,7 +438,6 @@ class AthenakFluidModel(DeviceSampledFluidModel):
                 raise ValueError("mesh is not regular enough for the block-grid lookup; use lookup='scan'")
         pidx = (ctypes.c_int * 8)(*self._prim_index())
         handle = ctypes.c_void_p()
-        d_mb = self._upload_meshblocks(amb) if fill else None
         d_geom = as_device(geom)
         if grid is not None:
             g, gn, g0, ginv = grid
@@ -417,9 +447,28 @@ class AthenakFluidModel(DeviceSampledFluidModel):
             c_gi = (ctypes.c_double * 3)(*[float(q) for q in ginv])
         else:
             d_grid, c_gn, c_g0, c_gi = None, None, None, None
-        _cabi.call("mk_snapshot_create", nmb, nk2 - 2, nj2 - 2, ni2 - 2, d_mb, pidx, d_geom, d_grid, c_gn, c_g0,
-                   c_gi, bbox_lo, bbox_hi, 1 if storage == 'f32' else 0, ctypes.byref(handle), stream_ptr())
-        del d_mb
+        if on_device:
+            torch = __import__('torch')
+            src_f32 = self._uov.dtype == np.float32 and self._B.dtype == np.float32
+            dt = torch.float32 if src_f32 else torch.float64
+            d_uov, d_B = self._upload_meshblocks(self._uov, dtype=dt), self._upload_meshblocks(self._B, dtype=dt)
+            loc = np.ascontiguousarray(self.LogicalLocations, dtype=np.int32)
+            lev = np.ascontiguousarray(self.Levels, dtype=np.int32)
+            stored = ctypes.c_int(0)
+            _cabi.call("mk_snapshot_create_from_interiors", nmb, nk2 - 2, nj2 - 2, ni2 - 2, d_uov,
+                       int(self._uov.shape[0]), d_B, int(self._B.shape[0]), 1 if src_f32 else 0, pidx,
+                       loc.ctypes.data, lev.ctypes.data, d_geom, d_grid, c_gn, c_g0, c_gi, bbox_lo, bbox_hi,
+                       {'f64': 0, 'f32': 1, 'auto': 2}[storage], ctypes.byref(stored), ctypes.byref(handle),
+                       stream_ptr())
+            storage = 'f32' if stored.value else 'f64'
+            del d_uov, d_B
+        else:
+            d_mb = self._upload_meshblocks(amb) if fill else None
+            if storage == 'auto':          # a replica: the caller passes the storage of the source rank
+                storage = 'f64'
+            _cabi.call("mk_snapshot_create", nmb, nk2 - 2, nj2 - 2, ni2 - 2, d_mb, pidx, d_geom, d_grid, c_gn, c_g0,
+                       c_gi, bbox_lo, bbox_hi, 1 if storage == 'f32' else 0, ctypes.byref(handle), stream_ptr())
+            del d_mb
         self._snap = handle
         self._snap_device = dev
         self.storage = storage
@@ -427,16 +476,19 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         return self._snap
 
     @staticmethod
-    def _upload_meshblocks(amb, chunk_bytes=1 << 30):
-        """Host -> device copy of the ghost-padded blocks; large snapshots go block-range by block-range so
-        that no multi-GB pinned staging buffer is needed."""
-        if amb.nbytes <= chunk_bytes:
-            return as_device(amb)
+    def _upload_meshblocks(amb, chunk_bytes=1 << 30, dtype=None):
+        """Host -> device copy of a large block array; big snapshots go slice by slice so that no multi-GB
+        pinned staging buffer is needed."""
         torch = __import__('torch')
-        d = empty(amb.shape)
-        per = max(1, chunk_bytes // (amb.nbytes // amb.shape[0]))
-        for b0 in range(0, amb.shape[0], per):
-            d[b0:b0 + per].copy_(torch.from_numpy(np.ascontiguousarray(amb[b0:b0 + per])))
+        dtype = dtype or torch.float64
+        if amb.nbytes <= chunk_bytes:
+            return as_device(amb, dtype=dtype)
+        d = empty(amb.shape, dtype=dtype)
+        flat = d.reshape(-1)
+        h = np.ascontiguousarray(amb).reshape(-1)
+        per = max(1, chunk_bytes // h.itemsize)
+        for b0 in range(0, h.size, per):
+            flat[b0:b0 + per].copy_(torch.from_numpy(h[b0:b0 + per]))
         return d
 
     def snapshot_bytes(self):

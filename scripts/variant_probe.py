@@ -21,6 +21,15 @@ if "norender" not in tag:
     arr = make_synthetic_snapshot(ncells=nc, block=32, extent=32.0, seed=0)
     m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
                                       arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"])
+    import time
+    for gf in ("device", "host"):
+        t0 = time.time()
+        mt = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                           arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"],
+                                           ghost_fill=gf)
+        mt.snapshot(); torch.cuda.synchronize()
+        print(tag, f"snapshot setup ({nc}^3, ghost_fill={gf}) s", round(time.time() - t0, 3), mt.storage)
+        mt.release()
     m.snapshot()
     torch.save({k: v for k, v in arr.items() if hasattr(v, "shape")}, "/tmp/snap.pt") if False else None
     print(tag, "render 1f ms", timeit(lambda: images.render(m, resolution=1024)))

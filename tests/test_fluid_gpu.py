@@ -21,6 +21,40 @@ def setup(built):
 
 def test_ghost_fill_matches_oracle(setup):
     assert np.array_equal(setup["dm"].all_meshblocks, setup["om"].all_meshblocks)
+    # the device snapshot was built by the fused ghost-fill + repack kernel from the interior arrays only
+    assert setup["dm"]._ghost_fill == "device"
+    assert np.array_equal(np.asarray(setup["dm"].device_meshblocks()), setup["om"].all_meshblocks)
+
+
+def test_device_ghost_fill_variants(setup):
+    """Device ghost fill (mk_snapshot_create_from_interiors) against the oracle's host fill: float32 and float64
+    inputs, permuted variable order, non-float32-representable data (auto storage must fall back to float64),
+    and identity with the host-filled upload route."""
+    arr, om = setup["arr"], setup["om"]
+    ref = om.all_meshblocks
+    m32 = device_model(dict(arr, uov=arr["uov"].astype(np.float32), B=arr["B"].astype(np.float32)), A)
+    assert np.array_equal(np.asarray(m32.device_meshblocks()), ref) and m32.storage == "f32"
+    assert m32._uov.dtype == np.float32
+    mh = device_model(arr, A, ghost_fill="host")
+    assert np.array_equal(np.asarray(mh.device_meshblocks()), ref) and mh.storage == "f32"
+    m64 = device_model(arr, A, storage="f64")
+    assert np.array_equal(np.asarray(m64.device_meshblocks()), ref) and m64.storage == "f64"
+    # permuted file order: eint first, dens last among the hydro variables
+    perm = [4, 1, 2, 3, 0]
+    names = [arr["VariableNames"][q] for q in perm] + list(arr["VariableNames"][5:])
+    mp = device_model(dict(arr, uov=arr["uov"][perm], VariableNames=names), A)
+    got = np.asarray(mp.device_meshblocks())
+    assert np.array_equal(got[:, :5], ref[:, perm]) and np.array_equal(got[:, 5:], ref[:, 5:])
+    S = setup["S"]
+    for k, v in setup["dm"].get_prims_from_geodesics(S).items():
+        assert np.array_equal(np.asarray(v), np.asarray(mp.get_prims_from_geodesics(S)[k])), k
+    # values that are not float32-representable: 'auto' must store float64 and reproduce them exactly
+    lossy = dict(arr, uov=arr["uov"] * (1.0 + 1e-11))
+    ml = device_model(lossy, A)
+    assert np.array_equal(np.asarray(ml.device_meshblocks()), oracle_model(lossy, A).all_meshblocks)
+    assert ml.storage == "f64"
+    for m in (m32, mh, m64, mp, ml):
+        m.release()
 
 
 def test_sample_prims_and_scalars(setup):
@@ -202,6 +236,10 @@ def test_two_level_mesh_sampling(built):
     om = oracle_model(arr, A)
     om.all_meshblocks = expected                      # brute-force ghost cells (tests/helpers.py)
     assert np.abs(dm.all_meshblocks - expected).max() < 1e-15
+    # refinement boundaries on the device: injection from the coarse neighbour and the mean of the 8 fine cells
+    # are evaluated in the host fill's operation order -> bit-identical (the means are not float32 numbers, so
+    # 'auto' storage has to choose float64 cells)
+    assert np.array_equal(np.asarray(dm.device_meshblocks()), dm.all_meshblocks) and dm.storage == "f64"
     rng = np.random.default_rng(2)
     pts = rng.uniform(-8.5, 8.5, (4000, 3))
     faces = np.array([-8.0, -4.0, 0.0, 2.0, 4.0, 6.0, 8.0])        # points exactly on coarse and fine faces

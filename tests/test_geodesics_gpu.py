@@ -35,6 +35,30 @@ def test_fast_math_accuracy(ma):
     assert ulp(rsq * xd, np.sqrt(x)).max() <= 4.0          # quick_sqrt = x * rsqrt(x), no residual correction
 
 
+def test_fast_transcendentals_accuracy(ma):
+    """exp(-x) and cbrt(x) of the fused emission chain (fp64_math.cuh) against libm: a few ulp, far inside the
+    1e-6 per-pixel intensity tolerance; exp flushes results below 1e-307 to zero."""
+    from mahakala_b200 import _cabi
+    from mahakala_b200._device import as_device, empty, stream_ptr
+    rng = np.random.default_rng(1)
+    t = np.concatenate([rng.uniform(0, 50, 200000), rng.uniform(0, 707, 100000), np.exp(rng.uniform(-40, 0, 50000)),
+                        [0.0, 1e-300, 0.5 * np.log(2), np.log(2), 706.9, 707.0, 708.0, 745.0, 1e4, 1e300, np.inf]])
+    e, c, ic = empty(t.shape), empty(t.shape), empty(t.shape)
+    _cabi.call("mk_transcendental_probe", as_device(t), t.size, e, c, ic, stream_ptr())
+    e = np.asarray(e.cpu())
+    want = np.exp(-t)
+    ok = t <= 707.0
+    assert (np.abs(e[ok] - want[ok]) / np.spacing(want[ok])).max() <= 2.0
+    assert np.all(e[~ok] == 0.0) and want[~ok].max() < 1e-307
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-29), np.log(1e29), 300000)), rng.uniform(0.5, 2.0, 100000),
+                        [1.0, 8.0, 27.0, 1e-12, 1e12, 0.001]])
+    e, c, ic = empty(x.shape), empty(x.shape), empty(x.shape)
+    _cabi.call("mk_transcendental_probe", as_device(x), x.size, e, c, ic, stream_ptr())
+    c, ic = np.asarray(c.cpu()), np.asarray(ic.cpu())
+    assert (np.abs(c - np.cbrt(x)) / np.spacing(np.cbrt(x))).max() <= 4.0
+    assert (np.abs(ic - 1.0 / np.cbrt(x)) / np.spacing(1.0 / np.cbrt(x))).max() <= 4.0
+
+
 def test_camera_grid_matches_oracle(ma):
     from oracle import mahakala_oracle as onp
     for (a, inc, res) in [(0.94, 60, 32), (0.0, 90, 8), (0.5, 17, 16)]:
