@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmahakala_b200.so")
+# MAHAKALA_B200_LIB selects another build of the same library (kernel-variant experiments, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("MAHAKALA_B200_LIB") or os.path.join(_HERE, "libmahakala_b200.so")
 
 _c = {"d": ctypes.c_double, "l": ctypes.c_long, "i": ctypes.c_int, "p": ctypes.c_void_p}
 

@@ -49,16 +49,32 @@ struct RenderArgs {
     const int* patch_order;    // optional permutation of the patch indices (scheduling order)
 };
 
-// Resident CTAs per SM, measured on B200 (scripts/variant_probe.py): 3 for one or two frequencies, 4 when
-// the per-frequency synchrotron work dominates (8 frequencies: 75.8 -> 67.0 ms on cfg4).
+// Resident CTAs per SM.  Measured on B200 (scripts/dev/render_variants.py, cfg4, 1 / 2 / 8 frequencies): 4 CTAs of
+// 128 threads at 128 registers 26.8 / 28.8 / 39.5 ms; 3 CTAs at 168 registers 27.2 / 29.8 / 39.5 ms; 13-15 warps per
+// SM with 136-152 registers (one- or two-warp CTAs) 27.7-28.1 / 30.2-30.5 / 39.7-41.6 ms.  The plateau is flat
+// (+-2 %): the kernel is bound by dependent FP64 latency plus FP64 issue, and occupancy trades against spills.
 #ifndef MK_RENDER_SPLIT
 #define MK_RENDER_SPLIT 4
 #endif
 #ifndef MK_RENDER_LO
-#define MK_RENDER_LO 3
+#define MK_RENDER_LO 4
+#endif
+#ifndef MK_RENDER_THREADS
+#define MK_RENDER_THREADS 128
+#endif
+#ifndef MK_RENDER_HI
+#define MK_RENDER_HI 4
+#endif
+#ifndef MK_RENDER_PIPE_MAX
+#define MK_RENDER_PIPE_MAX 2
+#endif
+#ifdef MK_RENDER_MAXREG        // experiment: cap registers directly (any warp count per SM with small CTAs)
+#define MK_RENDER_BOUNDS __maxnreg__(MK_RENDER_MAXREG)
+#else
+#define MK_RENDER_BOUNDS __launch_bounds__(MK_RENDER_THREADS, (NF >= MK_RENDER_SPLIT) ? MK_RENDER_HI : MK_RENDER_LO)
 #endif
 template <int NF>
-__global__ void __launch_bounds__(128, (NF >= MK_RENDER_SPLIT) ? 4 : MK_RENDER_LO) render_kernel(const RenderArgs A)
+__global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
 {
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long my_steps = 0, my_samples = 0;
@@ -107,7 +123,7 @@ __global__ void __launch_bounds__(128, (NF >= MK_RENDER_SPLIT) ? 4 : MK_RENDER_L
 
         // Two loop shapes, chosen by measurement (scripts/variant_probe.py): with one or two frequencies the
         // software-pipelined form is ~2 % faster; with many frequencies its extra live registers spill.
-        if constexpr (NF <= 2) {
+        if constexpr (NF <= MK_RENDER_PIPE_MAX) {
             // Software-pipelined loop: the sample of state s (accepted in the previous iteration, weight wdt) and
             // the RK4 step that leaves s are independent, so they sit in ONE straight-line block and the scheduler
             // can fill the latency of the gathers and of the emission chain with RK4 arithmetic.
@@ -304,13 +320,14 @@ static int launch_render(const RenderArgs& A, long npatches, cudaStream_t stream
     }
 #endif
     int per_sm = 0;
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF>, 128, 0));
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF>, MK_RENDER_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     long blocks = (long)sm_count() * per_sm;
-    long need = (npatches + 3) / 4;
+    const long warps = MK_RENDER_THREADS / 32;
+    long need = (npatches + warps - 1) / warps;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    render_kernel<NF><<<(unsigned)blocks, 128, 0, stream>>>(A);
+    render_kernel<NF><<<(unsigned)blocks, MK_RENDER_THREADS, 0, stream>>>(A);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

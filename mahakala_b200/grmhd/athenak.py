@@ -476,19 +476,21 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         return self._snap
 
     @staticmethod
-    def _upload_meshblocks(amb, chunk_bytes=1 << 30, dtype=None):
-        """Host -> device copy of a large block array; big snapshots go slice by slice so that no multi-GB
-        pinned staging buffer is needed."""
+    def _upload_meshblocks(amb, chunk_bytes=256 << 20, dtype=None):
+        """Host -> device copy of a large block array.  Large arrays are copied slice by slice from pageable
+        memory (the driver pipelines them through its own staging buffers): pinning a multi-GB NumPy array first
+        costs more than the copy itself."""
         torch = __import__('torch')
         dtype = dtype or torch.float64
-        if amb.nbytes <= chunk_bytes:
+        if amb.nbytes <= (16 << 20):
             return as_device(amb, dtype=dtype)
+        np_dtype = {torch.float64: np.float64, torch.float32: np.float32}[dtype]
+        h = np.ascontiguousarray(amb, dtype=np_dtype).reshape(-1)
         d = empty(amb.shape, dtype=dtype)
         flat = d.reshape(-1)
-        h = np.ascontiguousarray(amb).reshape(-1)
         per = max(1, chunk_bytes // h.itemsize)
         for b0 in range(0, h.size, per):
-            flat[b0:b0 + per].copy_(torch.from_numpy(h[b0:b0 + per]))
+            flat[b0:b0 + per].copy_(torch.from_numpy(h[b0:b0 + per]), non_blocking=True)
         return d
 
     def snapshot_bytes(self):

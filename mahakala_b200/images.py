@@ -118,10 +118,12 @@ def make_image(fluid_model, camera_inclination=60, camera_distance=1000,
     so there is nothing to chunk (the unfused fallback for foreign fluid models does honour it).
     """
     if hasattr(fluid_model, "snapshot"):
-        img = render(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
-                     (observing_frequency,), fov, resolution, max_nsteps)
+        # the kernel stores the pixels straight into pinned host memory (mapped under unified addressing):
+        # no device image, no separate device -> host copy
         host = _pinned_staging(resolution * resolution)
-        host.copy_(img[0], non_blocking=False)
+        render(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
+               (observing_frequency,), fov, resolution, max_nsteps, image_out=host)
+        torch.cuda.current_stream().synchronize()
         return host.numpy().copy().reshape((resolution, resolution))
     return make_image_unfused(fluid_model, camera_inclination, camera_distance, mass_scale, M_bh, r_high,
                               observing_frequency, fov, resolution, max_nsteps, max_chunk_bytes)

@@ -33,6 +33,10 @@ if "norender" not in tag:
     m.snapshot()
     torch.save({k: v for k, v in arr.items() if hasattr(v, "shape")}, "/tmp/snap.pt") if False else None
     print(tag, "render 1f ms", timeit(lambda: images.render(m, resolution=1024)))
+    import time as _t
+    for it in range(5):
+        t0 = _t.perf_counter(); h = images.make_image(m, resolution=1024); t1 = _t.perf_counter()
+        print(tag, "make_image host-to-host ms", round(1e3 * (t1 - t0), 2))
     m64 = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
                                         arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"], storage="f64")
     print(tag, "render 1f f64-cells ms", timeit(lambda: images.render(m64, resolution=1024)))

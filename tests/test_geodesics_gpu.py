@@ -436,3 +436,32 @@ def test_strict_mode_is_bit_identical_to_the_oracle(ma):
     esc = rl >= 100
     d = np.abs(np.asarray(ff.cpu())[esc] - f[esc]).max(axis=1) / np.abs(f[esc]).max(axis=1)
     assert d.max() < 1e-9 and np.array_equal(np.asarray(nf.cpu())[esc], n[esc])
+
+
+def test_zero_copy_host_to_host_matches_device_path(ma):
+    """integrate_paged_host: the kernel reads s0 from pinned host memory and writes the per-ray results into pinned
+    host memory; results and trajectories are identical to the device-resident launch and to the chunked pipeline."""
+    import torch
+    from mahakala_b200 import geodesics as geo
+    a, N = 0.94, 10000
+    s0 = ma.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 48)
+    npx = s0.shape[0]
+    dev = geo.integrate_paged(N, s0, 40, 1e-4, a)
+    S_ref, dt_ref = dev.padded(rays=np.arange(0, npx, 7))
+    s0_host = torch.empty((npx, 8), dtype=torch.float64, pin_memory=True)
+    s0_host.copy_(s0)
+    def outs():
+        return {"final": torch.zeros((npx, 8), dtype=torch.float64, pin_memory=True),
+                "nsteps": torch.zeros((npx,), dtype=torch.int32, pin_memory=True),
+                "r_last": torch.zeros((npx,), dtype=torch.float64, pin_memory=True)}
+    for fn in (geo.integrate_paged_host, lambda *args: geo.integrate_paged_streamed(*args, chunks=3)):
+        store = geo.TrajectoryStore.allocate(npx, N)
+        out = outs()
+        fn(N, s0_host, 40, 1e-4, a, store, out)
+        assert torch.equal(out["final"], dev.final.cpu()) and torch.equal(out["nsteps"], dev.nsteps.cpu())
+        assert torch.equal(out["r_last"], dev.r_last.cpu())
+        assert int(store.total_steps.item()) == int(dev.total_steps.item()) == int(out["nsteps"].sum())
+        S, dt = store.padded(rays=np.arange(0, npx, 7))
+        assert torch.equal(S, S_ref) and torch.equal(dt, dt_ref)
+    with pytest.raises(ValueError):
+        geo.integrate_paged_host(N, s0_host.clone(), 40, 1e-4, a, geo.TrajectoryStore.allocate(npx, N), outs())   # not pinned
