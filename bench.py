@@ -513,9 +513,21 @@ def render_leg(args, rank, world, dev):
     return out
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout when NCCL_DEBUG is set)
+    and child processes write to stderr instead.  Returns a file object bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
     args = parse()
+    _real_stdout = _claim_stdout()
+    sys.stdout = _real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    _real_stdout.flush()
