@@ -197,6 +197,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from mahakala_b200._device import bind_host_to_gpu_numa_node
+    numa_node = bind_host_to_gpu_numa_node(local)       # pinned buffers next to the GPU (zero-copy e2e path)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -331,6 +333,7 @@ def run_b200(args):
             "ray_steps_per_pass_rank0": steps_per_pass,
             "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": int(npx * 64),
                     "d2h_bytes_per_step": int(npx * (64 + 4 + 8)), "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                    "host_numa_node": numa_node,
                     "transfer": ("zero-copy: the kernel reads s0 from / writes results to pinned host memory over PCIe"
                                  if E2E_CHUNKS <= 0 else f"{E2E_CHUNKS}-chunk H2D / kernel / D2H pipeline")},
             "gpu_launches": n_launch,

@@ -61,3 +61,31 @@ def empty(shape, dtype=torch.float64):
 
 def zeros(shape, dtype=torch.float64):
     return torch.zeros(shape, dtype=dtype, device=require_gpu())
+
+
+def bind_host_to_gpu_numa_node(device_index=None):
+    """Pin this process (and therefore its first-touch page placement, pinned staging buffers included) to the
+    CPUs of the NUMA node the GPU hangs off.  Matters for the zero-copy host-to-host path at one process per GPU:
+    the kernel's PCIe reads of pinned host memory should not cross the inter-socket link.  Returns the node or
+    None when the topology is not exposed (virtualised hosts report -1)."""
+    import os
+    try:
+        idx = torch.cuda.current_device() if device_index is None else int(device_index)
+        bus = torch.cuda.get_device_properties(idx).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(idx), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(idx), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
