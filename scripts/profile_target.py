@@ -28,7 +28,8 @@ if what in ("all", "render"):
     nc = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     arr = make_synthetic_snapshot(ncells=nc, block=32, extent=32.0, seed=0)
     m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
-                                      arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"])
+                                      arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"],
+                                      storage=os.environ.get("MK_RENDER_STORAGE", "f64"))     # as bench.py's render leg
     for _ in range(2):
         images.render(m, resolution=1024, observing_frequencies=(230e9,))
     torch.cuda.synchronize()
