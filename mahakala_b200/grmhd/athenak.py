@@ -10,8 +10,9 @@ Reference: /root/reference/mahakala/grmhd/athenak.py (AthenakFluidModel, :48-812
   so that the left-open/right-closed membership rule is reproduced bit for bit;
 * sampling, the fluid-frame algebra and (in ``images.make_image``) the transfer solve run in CUDA kernels.
 
-``AthenakFluidModel(filename, bhspin, fluid_gamma)`` keeps the reference signature (needs h5py, imported
-lazily); ``AthenakFluidModel.from_arrays(...)`` takes the arrays an ``.athdf`` file holds.
+``AthenakFluidModel(filename, bhspin, fluid_gamma)`` keeps the reference signature (h5py if present, else the
+built-in minimal HDF5 reader ``_hdf5_min``); ``AthenakFluidModel.from_arrays(...)`` takes the arrays an ``.athdf``
+file holds.
 """
 import ctypes
 import time
@@ -273,8 +274,8 @@ class AnalyticTorusFluidModel(DeviceSampledFluidModel):
 class AthenakFluidModel(DeviceSampledFluidModel):
 
     def __init__(self, grmhd_filename, bhspin, fluid_gamma=None):
-        """athenak.py:50-53.  Reads an AthenaK ``.athdf`` dump (h5py required, imported lazily) or an ``.npz``
-        file holding the same datasets (``scripts/athdf_to_npz.py`` converts on a machine that has h5py)."""
+        """athenak.py:50-53.  Reads an AthenaK ``.athdf`` dump (with h5py if installed, else with the built-in
+        minimal HDF5 reader) or an ``.npz`` file holding the same datasets (``scripts/athdf_to_npz.py``)."""
         if str(grmhd_filename).endswith(".npz"):
             arrays = self._read_npz(grmhd_filename)
         else:
@@ -334,15 +335,18 @@ class AthenakFluidModel(DeviceSampledFluidModel):
 
     @staticmethod
     def _read_athdf(filename):
+        """athenak.py:79-103.  Uses h5py when it is installed, else the built-in minimal HDF5 reader
+        (``_hdf5_min``: the subset of the format h5py writes for AthenaK dumps)."""
         try:
             import h5py
-        except ImportError as e:      # pragma: no cover - h5py is not installed in the build image
-            raise ImportError("reading .athdf files needs h5py; use AthenakFluidModel.from_arrays(...) "
-                              "when the arrays are already in memory") from e
-        with h5py.File(filename, 'r') as hfp:
+        except ImportError:
+            from ._hdf5_min import read_athdf
+            return read_athdf(filename)
+        with h5py.File(filename, 'r') as hfp:      # pragma: no cover - h5py is not installed in the build image
             out = {k: np.array(hfp[k]) for k in ('x1v', 'x2v', 'x3v', 'x1f', 'x2f', 'x3f', 'uov', 'B',
                                                  'LogicalLocations', 'Levels')}
-            out['VariableNames'] = [n.decode('utf-8') for n in hfp.attrs['VariableNames']]
+            out['VariableNames'] = [n.decode('utf-8') if isinstance(n, bytes) else str(n)
+                                    for n in hfp.attrs['VariableNames']]
         return out
 
     def _setup(self, uov, B, x1v, x2v, x3v, x1f, x2f, x3f, LogicalLocations, Levels, VariableNames, bhspin,

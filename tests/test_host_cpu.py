@@ -220,7 +220,7 @@ def test_primitive_name_mapping_and_errors():
 
 def test_file_constructor_npz_roundtrip(tmp_path):
     """AthenakFluidModel(filename, bhspin, fluid_gamma) keeps the reference signature (athenak.py:50); .npz files
-    with the .athdf datasets are read without h5py, .athdf needs h5py (absent here -> ImportError, not a crash)."""
+    with the .athdf datasets are read as well; a missing file is an OSError."""
     from helpers import snapshot_arrays
     from mahakala_b200.grmhd import AthenakFluidModel
     arr = snapshot_arrays(ncells=16, block=8, extent=8.0)
@@ -231,8 +231,64 @@ def test_file_constructor_npz_roundtrip(tmp_path):
                                         arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.7, fluid_gamma=13. / 9)
     assert np.array_equal(m.all_meshblocks, ref.all_meshblocks) and m.bhspin == 0.7 and m.fluid_gamma == 13. / 9
     assert list(m.variable_names) == list(ref.variable_names)
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError, match="h5py"):
-            AthenakFluidModel("missing.athdf", 0.7)
+    with pytest.raises(OSError):
+        AthenakFluidModel("missing.athdf", 0.7)
+
+
+MATLAB_HDF5 = os.path.join(os.path.dirname(__import__("scipy").__file__), "io", "matlab", "tests", "data",
+                           "testhdf5_7.4_GLNX86.mat")
+
+
+@pytest.mark.skipif(not os.path.exists(MATLAB_HDF5), reason="scipy's MATLAB v7.3 test file is not installed")
+def test_minimal_hdf5_reader_on_a_third_party_file():
+    """The built-in HDF5 reader (used for .athdf dumps when h5py is missing) parses a file written by someone
+    else's HDF5 library: MATLAB 7.4's v7.3 MAT-file from SciPy's test data (512 B user block, superblock 0,
+    symbol-table group, version-1 object headers, version-2 layout message).  Its one variable is the same
+    0 : pi/4 : 2 pi ramp that SciPy reads from the v5 twin of the file."""
+    import scipy.io
+    from mahakala_b200.grmhd._hdf5_min import Hdf5File
+    f = Hdf5File(MATLAB_HDF5)
+    assert f.base == 512 and f.keys() == ["testdouble"]
+    got = f["testdouble"]
+    twin = scipy.io.loadmat(MATLAB_HDF5.replace("testhdf5", "testdouble"))["testdouble"]
+    assert got.dtype == np.float64 and np.array_equal(got.ravel(), twin.ravel())
+    assert np.array_equal(got.ravel(), np.arange(9) * np.pi / 4)
+    with pytest.raises(KeyError):
+        f["nope"]
+
+
+@pytest.mark.parametrize("variant", ["contiguous_f32", "chunked_userblock_f64"])
+def test_file_constructor_reads_athdf_without_h5py(tmp_path, variant):
+    """AthenakFluidModel("x.athdf", bhspin, fluid_gamma) (athenak.py:50, :79-103) through the built-in reader: an
+    .athdf-shaped HDF5 file (float32 data as AthenaK writes it, int LogicalLocations / Levels, VariableNames as a
+    fixed-length byte-string attribute) gives the same model as from_arrays."""
+    from hdf5_writer import write_hdf5
+    from helpers import snapshot_arrays
+    from mahakala_b200.grmhd import AthenakFluidModel
+    from mahakala_b200.grmhd._hdf5_min import Hdf5File, Hdf5FormatError
+    arr = snapshot_arrays(ncells=16, block=8, extent=8.0)
+    f32 = variant.endswith("f32")
+    fdt = np.float32 if f32 else np.float64
+    data = {k: np.asarray(arr[k], dtype=fdt) for k in ('x1v', 'x2v', 'x3v', 'x1f', 'x2f', 'x3f', 'uov', 'B')}
+    data["LogicalLocations"] = np.asarray(arr["LogicalLocations"], dtype=np.int64)
+    data["Levels"] = np.asarray(arr["Levels"], dtype=np.int32)
+    fn = str(tmp_path / "snap.athdf")
+    write_hdf5(fn, data, attrs={"VariableNames": np.array(arr["VariableNames"], dtype="S"), "Time": np.float64(12.5),
+                                "NumCycles": np.int32(7)},
+               chunked=("uov", "B", "x1v") if variant.startswith("chunked") else (),
+               userblock=512 if "userblock" in variant else 0)
+    f = Hdf5File(fn)
+    assert sorted(f.keys()) == sorted(data) and f.attrs["Time"] == 12.5 and f.attrs["NumCycles"] == 7
+    for k, v in data.items():
+        got = f[k]
+        assert got.dtype == v.dtype and np.array_equal(got, v), k
+    m = AthenakFluidModel(fn, 0.7, fluid_gamma=13. / 9)
+    ref = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                        arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.7, fluid_gamma=13. / 9)
+    assert list(m.variable_names) == list(ref.variable_names) and m._uov.dtype == fdt
+    assert np.array_equal(m.all_meshblocks, ref.all_meshblocks)         # the synthetic values are float32-exact
+    assert np.array_equal(m.x1f, ref.x1f) and np.array_equal(m.Levels, ref.Levels)
+    bad = tmp_path / "bad.athdf"
+    bad.write_bytes(b"not an hdf5 file" * 100)
+    with pytest.raises(Hdf5FormatError):
+        AthenakFluidModel(str(bad), 0.7)
