@@ -14,8 +14,11 @@ namespace mk {
 // Resident CTAs per SM, measured on B200 (scripts/variant_probe.py): the final/padded modes are fastest at
 // 4 CTAs (124 registers), the paged dump at 3 (its page bookkeeping fits in registers and the scattered
 // stores contend less): 25.9 -> 23.4 ms on cfg2.
+#ifndef MK_PAGED_CTAS
+#define MK_PAGED_CTAS 3
+#endif
 template <class Metric, int MODE>
-__global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? 3 : 4)) integrate_kernel(const Metric g, const IntegrateArgs A)
+__global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : 4)) integrate_kernel(const Metric g, const IntegrateArgs A)
 {
     integrate_body<Metric, MODE>(g, A);
 }

@@ -117,7 +117,11 @@ def make_image(fluid_model, camera_inclination=60, camera_distance=1000,
     ``max_chunk_bytes`` is accepted for signature compatibility; the fused kernel stores no trajectories,
     so there is nothing to chunk (the unfused fallback for foreign fluid models does honour it).
     """
-    if hasattr(fluid_model, "snapshot"):
+    # The fused kernel integrates in the built-in Kerr-Schild spacetime.  With a user-registered spacetime selected
+    # (geodesics.set_metric) the image goes through the stage-by-stage chain, whose geodesic_integrator follows the
+    # active metric while the fluid frame stays Kerr-Schild -- what the reference does when its module-level
+    # metric is replaced (athenak.py:34 binds the Kerr-Schild metric at import).
+    if hasattr(fluid_model, "snapshot") and geo._active_metric in (geo.KERR_SCHILD, geo.KERR_SCHILD_DUAL):
         # the kernel stores the pixels straight into pinned host memory (mapped under unified addressing):
         # no device image, no separate device -> host copy
         host = _pinned_staging(resolution * resolution)

@@ -10,7 +10,7 @@ make -j8 NVCCFLAGS="$FLAGS $1" 2>&1 | grep -E "error" || true
 if [ -n "$2" ]; then
   mkdir -p ../variants
   cp ../libmahakala_b200.so ../variants/lib$2.so
-  grep -A2 "render_kernelILi[18]E" render.o.ptxas.log | grep -i "registers\|spill" | tr '\n' ' '; echo
+  grep -A2 "render_kernelILi[18]E\|integrate_kernelINS_10KerrSchildELi2" render.o.ptxas.log integrate.o.ptxas.log | grep -i "registers\|spill" | tr "\n" " "; echo
   make clean >/dev/null
   make -j8 2>&1 | grep -E "error" || true
 fi

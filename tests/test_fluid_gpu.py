@@ -373,3 +373,22 @@ def test_unfused_chunking_is_transparent(setup):
     assert np.array_equal(whole, chunked)
     fused = images.make_image(dm, resolution=12, max_chunk_bytes=1e9)        # accepted, irrelevant for the fused path
     assert np.allclose(fused, whole, rtol=1e-9, atol=1e-14 * whole.max())
+
+
+def test_make_image_follows_a_user_registered_spacetime(setup):
+    """With a run-time registered spacetime selected, make_image runs the stage-by-stage chain whose geodesics
+    follow that metric (the fused kernel is Kerr-Schild only).  Registering the reference's own metric as the user
+    plugin must therefore reproduce the fused Kerr-Schild image."""
+    from mahakala_b200 import geodesics as geo, images
+    from test_geodesics_gpu import KERR_SCHILD_USER
+    dm = setup["dm"]
+    fused = images.make_image(dm, resolution=12)
+    geo.register_metric("ks_user_img", KERR_SCHILD_USER)
+    geo.set_metric("ks_user_img")
+    try:
+        user = images.make_image(dm, resolution=12)
+    finally:
+        geo.set_metric("kerr_schild")
+    assert user.shape == fused.shape and fused.max() > 0
+    assert np.allclose(user, fused, rtol=1e-6, atol=1e-12 * fused.max())
+    assert not np.array_equal(user, fused)          # different code path (dual-number geodesics, literal transfer order)
