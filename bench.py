@@ -483,6 +483,41 @@ def render_leg(args, rank, world, dev):
                                           "source": "demos/grmhd_detailed.ipynb cell 10 (456 meshblocks, hardware not stated)"}}
         del S160, dt160
         torch.cuda.empty_cache()
+    # the other single-GPU BASELINE configs, timed once each for the record (rank 0): cfg1 = the reference's own test
+    # (4 golden shadow curves through find_shadow_bisection_angles, tests/test_shadows.py), cfg3 = analytic torus 512^2
+    other = None
+    if rank == 0:
+        import mahakala_b200 as ma
+        from mahakala_b200.grmhd.athenak import AnalyticTorusFluidModel
+        other = {}
+        gold = os.path.join(ROOT, "tests", "golden", "shadow_golden.npz")
+        if os.path.exists(gold):
+            z = np.load(gold)
+            cases = sorted({k.split("__")[0] for k in z.files})
+            def shadows():
+                worst = 0.0
+                for c in cases:
+                    r = np.asarray(ma.find_shadow_bisection_angles(float(z[c + "__bhspin"]), float(z[c + "__inclination"]),
+                                                                   z[c + "__angles"]))
+                    worst = max(worst, float(np.max(np.abs(r - z[c + "__radii"]) / z[c + "__radii"])))
+                return worst
+            shadows()
+            t0 = time.perf_counter()
+            worst = shadows()
+            other["cfg1_shadow_golden"] = {"call": "find_shadow_bisection_angles on the reference's 4 golden cases "
+                                                   "(305 angles, 14 bisection iterations each, N=2000, tol=1e-2)",
+                                           "ms": 1e3 * (time.perf_counter() - t0), "max_rel_err_vs_golden": worst,
+                                           "reference_rtol": 1e-2}
+        torus = AnalyticTorusFluidModel(CFG2["bhspin"])
+        images.render(torus, resolution=512)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        timg = images.render(torus, resolution=512)
+        e1.record()
+        torch.cuda.synchronize()
+        other["cfg3_torus_512"] = {"call": "fused render of the analytic thin torus, 512x512 at 230 GHz", "ms": e0.elapsed_time(e1),
+                                   "image_sum": float(timg.sum())}
     strong, flux = strong_leg(res, 3) if world > 1 else (0.0, 0.0)
     strong_big, flux_big = strong_leg(args.strong_res, 2) if args.strong_res > 0 else (0.0, 0.0)
     t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong, bcast_ms, strong_big], dtype=torch.float64, device=dev)
@@ -503,6 +538,8 @@ def render_leg(args, rank, world, dev):
            "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
     if stage is not None:
         out["sampling_stage_160px"] = stage
+    if other:
+        out["other_configs"] = other
     if args.strong_res > 0:
         out["strong_scaling_large_image"] = {"resolution": args.strong_res, "ms": float(t[4]), "image_sum": flux_big,
                                              "note": "ONE cfg5-sized frame rendered by all ranks together"}
