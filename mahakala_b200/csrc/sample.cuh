@@ -21,6 +21,9 @@ namespace mk {
 // cfg3 analytic thin torus: primitives are closed-form functions of position.
 struct TorusParams {
     double fluid_gamma, R0, R_in, p, h, u0, beta0, dens_scale, r_out;
+    // derived on the host (mk_snapshot_create_torus)
+    double inv_R0, inv_2h2, cB, u0R0;     // 1/R0, 1/(2 h^2), 2 (gamma - 1)/beta0, u0 R0
+    int p_is_three_halves;                // the default power law: x^-1.5 = rsqrt(x)^3 instead of pow()
 };
 
 struct SnapshotView {
@@ -190,27 +193,42 @@ __device__ __forceinline__ void trilinear(const SnapshotView& sn, int mb, const 
     }
 }
 
-// Analytic torus primitives in canonical order; zero outside r <= r_out (the model's "domain").
+// Analytic torus primitives in canonical order; zero outside r <= r_out (the model's "domain").  Same formulas as
+// mahakala_b200/synthetic.py::torus_fields (no waves); divisions, square roots and the two Gaussians use the
+// MUFU-seeded FP64 helpers (<= few ulp; the exponentials flush results below 1e-307 to zero).
 __device__ __forceinline__ bool torus_prims(const TorusParams& t, const double x[4], double prims[8])
 {
-    double R2 = x[1] * x[1] + x[2] * x[2];
-    double R = sqrt(R2) + 1e-12, r = sqrt(R2 + x[3] * x[3]) + 1e-12;
+    double R2 = fma(x[1], x[1], x[2] * x[2]);
+    double R = fast_sqrt(R2) + 1e-12, r = fast_sqrt(fma(x[3], x[3], R2)) + 1e-12;
     if (!(r <= t.r_out)) {
 #pragma unroll
         for (int q = 0; q < 8; q++) prims[q] = 0.0;
         return false;
     }
-    double H = t.h * R;
-    double q4 = t.R_in / R;
-    q4 = q4 * q4;
-    double taper = exp(-(q4 * q4));
-    double dens = t.dens_scale * pow(R / t.R0, -t.p) * exp(-x[3] * x[3] / (2. * H * H)) * taper;
-    double eint = t.u0 * dens * (t.R0 / r);
-    double vphi = 0.5 / sqrt(1. + R);
-    double bmag = sqrt(2. * eint * (t.fluid_gamma - 1.) / t.beta0);
+    double iR = fast_rcp(R);
+    double q2 = t.R_in * iR;
+    q2 = q2 * q2;
+    double taper = fast_exp_neg((q2 * q2));                               // exp(-(R_in/R)^4)
+    double zr = x[3] * iR;
+    double gauss = fast_exp_neg(zr * zr * t.inv_2h2);                     // exp(-z^2 / (2 (h R)^2))
+    double xr = R * t.inv_R0, plaw;
+    if (t.p_is_three_halves) {
+        double sx, isx;
+        fast_sqrt_rsqrt(xr, sx, isx);
+        plaw = isx * isx * isx;
+    } else {
+        plaw = pow(xr, -t.p);
+    }
+    double dens = t.dens_scale * plaw * gauss * taper;
+    double eint = t.u0R0 * dens * fast_rcp(r);
+    double s1R, vphi2;
+    fast_sqrt_rsqrt(1. + R, s1R, vphi2);
+    double vphi = 0.5 * vphi2;
+    double bmag = fast_sqrt(eint * t.cB);
+    double cx = x[1] * iR, cy = x[2] * iR;
     prims[0] = dens; prims[1] = eint;
-    prims[2] = -vphi * x[2] / R; prims[3] = vphi * x[1] / R; prims[4] = 0.02 * x[3] / (1. + r);
-    prims[5] = -bmag * x[2] / R; prims[6] = bmag * x[1] / R; prims[7] = 0.1 * bmag;
+    prims[2] = -vphi * cy; prims[3] = vphi * cx; prims[4] = 0.02 * x[3] * fast_rcp(1. + r);
+    prims[5] = -bmag * cy; prims[6] = bmag * cx; prims[7] = 0.1 * bmag;
     return true;
 }
 
