@@ -132,6 +132,7 @@ def cpu_sample_rays(res, side, inclination=CFG2["inclination"]):
 
 def time_cpu_oracle(res, side):
     from oracle import c_oracle
+    c_oracle.use_all_cores()
     s0, stride = cpu_sample_rays(res, side)
     c_oracle.integrate(200, s0[:64], CFG2["div"], CFG2["tol"], CFG2["bhspin"])       # load + thread warm-up
     t0 = time.perf_counter()
@@ -148,6 +149,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import c_oracle
+    c_oracle.use_all_cores()
     side = 64
     s0, stride = cpu_sample_rays(args.res, side)
     times, steps = [], 0

@@ -37,6 +37,14 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def use_all_cores():
+    """Run the OpenMP loops on every core this process may use (torchrun sets OMP_NUM_THREADS=1 for its workers)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def integrate(N, s0, div, tol, bhspin, dump=False):
     """-> dict(final (npx,8), nsteps (npx,), r_last (npx,)[, S (nrows,npx,8), dt (nrows,npx)]).
 

@@ -489,6 +489,16 @@ int orc_render(int N, int npx, const double *s0, double div, double tol,
     return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the timed CPU legs ask for all host cores explicitly */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP
