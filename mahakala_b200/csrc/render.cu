@@ -68,6 +68,13 @@ struct RenderArgs {
 #ifndef MK_RENDER_PIPE_MAX
 #define MK_RENDER_PIPE_MAX 2
 #endif
+// Experiment knob (off: 9 > max NF): from this many frequencies on, the (I, T) accumulators of a lane live in shared
+// memory ([2 NF][threads], conflict free) instead of registers.  Measured on B200 (cfg4, 8 frequencies): 40.1 ms
+// against 39.3 ms with register accumulators -- the ~200 B of spills of the 8-frequency kernel come from the RK4 /
+// emission temporaries under the 128-register cap, not from the accumulators.
+#ifndef MK_RENDER_SMEM_MIN
+#define MK_RENDER_SMEM_MIN 9
+#endif
 #ifdef MK_RENDER_MAXREG        // experiment: cap registers directly (any warp count per SM with small CTAs)
 #define MK_RENDER_BOUNDS __maxnreg__(MK_RENDER_MAXREG)
 #else
@@ -112,9 +119,13 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
             }
         }
         const bool valid = active;
-        double I[NF], T[NF];
+        constexpr bool SMEM_ACC = (NF >= MK_RENDER_SMEM_MIN);
+        __shared__ double sacc[SMEM_ACC ? 2 * NF * MK_RENDER_THREADS : 1];
+        double Ireg[SMEM_ACC ? 1 : NF], Treg[SMEM_ACC ? 1 : NF];
+        auto I = [&](int f) -> double& { return SMEM_ACC ? sacc[(2 * f) * MK_RENDER_THREADS + threadIdx.x] : Ireg[SMEM_ACC ? 0 : f]; };
+        auto T = [&](int f) -> double& { return SMEM_ACC ? sacc[(2 * f + 1) * MK_RENDER_THREADS + threadIdx.x] : Treg[SMEM_ACC ? 0 : f]; };
 #pragma unroll
-        for (int f = 0; f < NF; f++) { I[f] = 0.0; T[f] = 1.0; }
+        for (int f = 0; f < NF; f++) { I(f) = 0.0; T(f) = 1.0; }
         int it = 0;
         double dt = 0.0;
         KerrSchild::Cache cache, cache_new;
@@ -138,13 +149,15 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
                         double f, l[4], em[NF], ab[NF];
                         l[0] = 1.0;
                         A.g.fl(s, cache, f, l[1], l[2], l[3]);
-                        emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
+                        emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
+                                          [&](int fq, double e, double a) { em[fq] = e; ab[fq] = a; });
                         rk4_step(A.g, s, dt, cand, &cache);
                         dtn = A.rule(A.g.radius(cand, cache_new));
     #pragma unroll
                         for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
-                            I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
-                            T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
+                            const double Tf = T(fq);
+                            I(fq) = fma(Tf, wdt * em[fq], I(fq));
+                            T(fq) = Tf * fma(-wdt, ab[fq], 1.0);
                         }
                     } else {
                         rk4_step(A.g, s, dt, cand, &cache);
@@ -185,15 +198,17 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
                             double prims[8];
                             if (interp_prims(A.sn, s, prims)) {
                                 my_samples++;
-                                double f, l[4], em[NF], ab[NF];
+                                double f, l[4];
                                 l[0] = 1.0;
                                 A.g.fl(s, cache, f, l[1], l[2], l[3]);
-                                emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
-    #pragma unroll
-                                for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
-                                    I[fq] = fma(T[fq], wdt * em[fq], I[fq]);
-                                    T[fq] = T[fq] * fma(-wdt, ab[fq], 1.0);
-                                }
+                                // each frequency is folded into (I, T) as soon as its coefficients exist
+                                // (em = ab = 0 leaves them unchanged)
+                                emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
+                                                  [&](int fq, double e, double a) {
+                                                      const double Tf = T(fq);
+                                                      I(fq) = fma(Tf, wdt * e, I(fq));
+                                                      T(fq) = Tf * fma(-wdt, a, 1.0);
+                                                  });
                             }
                         }
                     }
@@ -202,7 +217,7 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
         }
         if (valid) {
 #pragma unroll
-            for (int fq = 0; fq < NF; fq++) A.image[(long)fq * A.npx + ray] = I[fq];
+            for (int fq = 0; fq < NF; fq++) A.image[(long)fq * A.npx + ray] = I(fq);
             if (A.nsteps) A.nsteps[ray] = it;
             my_steps += (unsigned long long)it;
         }
@@ -275,7 +290,8 @@ __global__ void __launch_bounds__(128, 3) render_refill_kernel(const RenderArgs 
             double f, l[4], em[1], ab[1];
             l[0] = 1.0;
             A.g.fl(s, cache, f, l[1], l[2], l[3]);
-            emission_fast<1>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs, em, ab);
+            emission_fast<1>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
+                             [&](int, double e, double a) { em[0] = e; ab[0] = a; });
             rk4_step(A.g, s, dt, cand, &cache);
             dtn = A.rule(A.g.radius(cand, cache_new));
             I = fma(T, wdt * em[0], I);

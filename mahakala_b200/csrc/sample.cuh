@@ -401,11 +401,12 @@ __host__ __device__ inline EmissionConsts make_emission_consts(const EmissionPar
     return c;
 }
 
-template <int NF>
+// `sink(fq, em, ab)` receives the invariant emissivity and absorptivity of frequency fq as soon as they are known, so
+// that a multi-frequency caller can fold them into its accumulators without holding 2 NF values in registers.
+template <int NF, class Sink>
 __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const EmissionConsts& C, double f,
                                               const double l[4], const double s[8], const double prims[8],
-                                              const double* nu_obs, const double* inv_nu_obs, double em[NF],
-                                              double ab[NF])
+                                              const double* nu_obs, const double* inv_nu_obs, Sink&& sink)
 {
     // Straight-line code: every validity test only feeds the final select (invalid lanes may carry NaN/inf
     // through the arithmetic, which is harmless on the GPU).  Early exits would make the compiler duplicate
@@ -492,8 +493,7 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
         e = e * irn2;
         a = a * rn;
         bool ok = valid & (X <= 1.e12) & (e == e) & (a == a);
-        em[fq] = ok ? e : 0.0;
-        ab[fq] = ok ? a : 0.0;
+        sink(fq, ok ? e : 0.0, ok ? a : 0.0);
     }
     return valid;
 }

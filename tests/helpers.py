@@ -95,3 +95,40 @@ def two_level_mesh(n=8, seed=0, fluid_gamma=13. / 9):
                LogicalLocations=np.array([[b[1], b[2], b[3]] for b in blocks]), Levels=np.array([b[0] for b in blocks]),
                VariableNames=('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'), fluid_gamma=fluid_gamma)
     return arr, expected
+
+
+def noncubic_mesh(nb=(2, 3, 2), n=(8, 6, 4), seed=3, fluid_gamma=13. / 9):
+    """Single-level mesh with NON-cubic meshblocks: nb = blocks along (x1, x2, x3), n = cells per block along
+    (x1, x2, x3) = (ni, nj, nk), cell size 0.5 on every axis.  Returns (arrays for from_arrays, global zero-padded
+    field array G (8, N3+2, N2+2, N1+2), global cell-centre coordinates) so that ghost zones and trilinear samples
+    can be checked by plain indexing of G."""
+    rng = np.random.default_rng(seed)
+    ni, nj, nk = n
+    N1, N2, N3 = nb[0] * ni, nb[1] * nj, nb[2] * nk
+    dx = 0.5
+    lo = (-N1 * dx / 2, -N2 * dx / 2, -N3 * dx / 2)
+    G = np.zeros((8, N3 + 2, N2 + 2, N1 + 2))
+    G[:, 1:-1, 1:-1, 1:-1] = rng.uniform(0.5, 1.5, (8, N3, N2, N1)).astype(np.float32)
+    nmb = nb[0] * nb[1] * nb[2]
+    uov = np.empty((5, nmb, nk, nj, ni)); B = np.empty((3, nmb, nk, nj, ni))
+    xv = [np.empty((nmb, m)) for m in n]
+    xf = [np.empty((nmb, m + 1)) for m in n]
+    loc = np.empty((nmb, 3), dtype=np.int64)
+    mb = 0
+    for lk in range(nb[2]):
+        for lj in range(nb[1]):
+            for li in range(nb[0]):
+                blk = G[:, 1 + lk * nk:1 + (lk + 1) * nk, 1 + lj * nj:1 + (lj + 1) * nj, 1 + li * ni:1 + (li + 1) * ni]
+                uov[:, mb] = blk[:5]
+                B[:, mb] = blk[5:]
+                for ax, (l, m) in enumerate(zip((li, lj, lk), n)):
+                    f = lo[ax] + (l * m + np.arange(m + 1)) * dx
+                    xf[ax][mb] = f
+                    xv[ax][mb] = f[:-1] + dx / 2
+                loc[mb] = (li, lj, lk)
+                mb += 1
+    arr = dict(uov=uov, B=B, x1v=xv[0], x2v=xv[1], x3v=xv[2], x1f=xf[0], x2f=xf[1], x3f=xf[2], LogicalLocations=loc,
+               Levels=np.zeros(nmb, dtype=np.int64),
+               VariableNames=('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'), fluid_gamma=fluid_gamma)
+    centres = [lo[ax] + (np.arange(-1, (N1, N2, N3)[ax] + 1) + 0.5) * dx for ax in range(3)]      # incl. the zero padding
+    return arr, G, centres
