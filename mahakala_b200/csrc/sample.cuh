@@ -72,11 +72,11 @@ __device__ __forceinline__ bool in_block(const BlockGeom& g, const double x[4])
 // Returns the block index (or -1) and its geometry record.
 __device__ __forceinline__ int locate_block(const SnapshotView& sn, const double x[4], BlockGeom& geo)
 {
-    // NaN-safe bounding-box rejection (comparisons with NaN are false -> outside)
-    if (!((sn.bbox_lo[0] < x[1]) & (x[1] <= sn.bbox_hi[0]) & (sn.bbox_lo[1] < x[2]) & (x[2] <= sn.bbox_hi[1]) &
-          (sn.bbox_lo[2] < x[3]) & (x[3] <= sn.bbox_hi[2])))
-        return -1;
     if (sn.grid == nullptr) {
+        // NaN-safe bounding-box rejection (comparisons with NaN are false -> outside), then the reference's scan
+        if (!((sn.bbox_lo[0] < x[1]) & (x[1] <= sn.bbox_hi[0]) & (sn.bbox_lo[1] < x[2]) & (x[2] <= sn.bbox_hi[1]) &
+              (sn.bbox_lo[2] < x[3]) & (x[3] <= sn.bbox_hi[2])))
+            return -1;
         int found = -1;
         for (int mb = 0; mb < sn.nmb; mb++) {
             BlockGeom g = load_geom(sn, mb);
@@ -84,17 +84,27 @@ __device__ __forceinline__ int locate_block(const SnapshotView& sn, const double
         }
         return found;
     }
+    // Grid cell of the point.  The range test on the integer cell index doubles as the bounding-box rejection:
+    // x below the lower domain face gives a negative quotient (x - g0 is negative exactly when x < g0), x above
+    // the upper face gives q >= gn.  q == gn is the one ambiguous value (x on the upper face, which is inside --
+    // right-closed extents -- or just beyond it), so only there the exact face is consulted.  NaN converts to 0
+    // and fails the exact membership test below.  Whatever passes is decided by in_block() on the stored faces.
     int c[3];
+    bool maybe = true;
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        int q = (int)floor((x[d + 1] - sn.g0[d]) * sn.ginv[d]);
-        c[d] = min(max(q, 0), sn.gn[d] - 1);
+        int q = __double2int_rd((x[d + 1] - sn.g0[d]) * sn.ginv[d]);
+        if (q == sn.gn[d]) q = (x[d + 1] <= sn.bbox_hi[d]) ? q - 1 : q;
+        maybe &= ((unsigned)q < (unsigned)sn.gn[d]);
+        c[d] = q;
     }
+    if (!maybe) return -1;
     int mb = sn.grid[(c[2] * sn.gn[1] + c[1]) * sn.gn[0] + c[0]];
     if (mb >= 0) {
         geo = load_geom(sn, mb);
         if (in_block(geo, x)) return mb;
     }
+    if (!((x[1] == x[1]) & (x[2] == x[2]) & (x[3] == x[3]))) return -1;          // NaN position: outside
     // a point within rounding distance of a face may land in the neighbouring grid cell: fix up with the
     // exact extents (x <= lo -> step down, x > hi -> step up), at most one step per axis
     int c2[3];
