@@ -426,6 +426,7 @@ extern "C" int mk_snapshot_unpack(const mk_snapshot* snap, const int* prim_index
 extern "C" int mk_snapshot_create_torus(const double* params9, mk_snapshot** out)
 {
     MK_REQUIRE(params9 && out, "null pointer");
+    MK_REQUIRE(params9[1] > 0.0 && params9[4] > 0.0 && params9[6] > 0.0, "torus parameters R0, h, beta0 must be positive");
     mk_snapshot* s = new mk_snapshot();
     memset(s, 0, sizeof *s);
     cudaGetDevice(&s->device);
@@ -433,7 +434,6 @@ extern "C" int mk_snapshot_create_torus(const double* params9, mk_snapshot** out
     TorusParams& t = s->view.torus;
     t.fluid_gamma = params9[0]; t.R0 = params9[1]; t.R_in = params9[2]; t.p = params9[3]; t.h = params9[4];
     t.u0 = params9[5]; t.beta0 = params9[6]; t.dens_scale = params9[7]; t.r_out = params9[8];
-    MK_REQUIRE(t.R0 > 0.0 && t.h > 0.0 && t.beta0 > 0.0, "torus parameters R0, h, beta0 must be positive");
     t.inv_R0 = 1.0 / t.R0; t.inv_2h2 = 1.0 / (2.0 * t.h * t.h); t.cB = 2.0 * (t.fluid_gamma - 1.0) / t.beta0;
     t.u0R0 = t.u0 * t.R0;
     t.p_is_three_halves = (t.p == 1.5);

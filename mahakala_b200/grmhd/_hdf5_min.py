@@ -16,13 +16,11 @@ the subset of the HDF5 file format that h5py / libhdf5 produce for such files:
 Anything else (dense link storage, version-4 layouts, compound types, ...) raises ``Hdf5FormatError`` naming the
 unsupported feature instead of returning wrong data.
 """
-import struct
 import zlib
 
 import numpy as np
 
 SIGNATURE = b"\x89HDF\r\n\x1a\n"
-UNDEF = 0xFFFFFFFFFFFFFFFF
 
 
 class Hdf5FormatError(ValueError):

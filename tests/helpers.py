@@ -132,3 +132,59 @@ def noncubic_mesh(nb=(2, 3, 2), n=(8, 6, 4), seed=3, fluid_gamma=13. / 9):
                VariableNames=('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'), fluid_gamma=fluid_gamma)
     centres = [lo[ax] + (np.arange(-1, (N1, N2, N3)[ax] + 1) + 0.5) * dx for ax in range(3)]      # incl. the zero padding
     return arr, G, centres
+
+
+def three_level_mesh(n=4, seed=1, fluid_gamma=13. / 9):
+    """Three refinement levels with 2:1 balance: 2x2x2 root blocks of n^3 cells on [-8, 8]^3; root block (1,1,1) is
+    replaced by its 8 children (level 1) and the level-1 child in the domain corner, (3,3,3), by its 8 children
+    (level 2): 7 + 7 + 8 = 22 meshblocks.  Level-l data are the 2x2x2 restriction of the level-(l+1) data, so every
+    ghost cell has a brute-force expectation: same-level / coarser leaf -> that level's array (injection), finer
+    leaves -> the restriction, outside the domain -> 0.  Returns (arrays for from_arrays, expected all_meshblocks)."""
+    rng = np.random.default_rng(seed)
+    L = 2
+    nf = 2 * n * 2 ** L
+    A = {L: rng.uniform(0.5, 1.5, (8, nf, nf, nf)).astype(np.float32).astype(np.float64)}
+    for lev in range(L - 1, -1, -1):
+        f = A[lev + 1]
+        m = f.shape[1] // 2
+        A[lev] = f.reshape(8, m, 2, m, 2, m, 2).mean(axis=(2, 4, 6))
+    leaves = [(0, li, lj, lk) for lk in range(2) for lj in range(2) for li in range(2) if (li, lj, lk) != (1, 1, 1)]
+    leaves += [(1, li, lj, lk) for lk in (2, 3) for lj in (2, 3) for li in (2, 3) if (li, lj, lk) != (3, 3, 3)]
+    leaves += [(2, li, lj, lk) for lk in (6, 7) for lj in (6, 7) for li in (6, 7)]
+    leafset = set(leaves)
+
+    def value_at(level, gk, gj, gi):
+        size = 2 * n * 2 ** level
+        if not (0 <= gk < size and 0 <= gj < size and 0 <= gi < size):
+            return None
+        for lev2 in range(level, -1, -1):                      # covered by a leaf of this or a coarser level
+            sh = level - lev2
+            ck, cj, ci = gk >> sh, gj >> sh, gi >> sh
+            if (lev2, ci // n, cj // n, ck // n) in leafset:
+                return A[lev2][:, ck, cj, ci]
+        return A[level][:, gk, gj, gi]                          # covered by finer leaves: their restriction
+
+    nmb = len(leaves)
+    uov = np.empty((5, nmb, n, n, n)); B = np.empty((3, nmb, n, n, n))
+    xv = [np.empty((nmb, n)) for _ in range(3)]
+    xf = [np.empty((nmb, n + 1)) for _ in range(3)]
+    expected = np.zeros((nmb, 8, n + 2, n + 2, n + 2))
+    for mb, (lev, li, lj, lk) in enumerate(leaves):
+        dx = 16.0 / (2 * n * 2 ** lev)
+        for ax, l in enumerate((li, lj, lk)):
+            f = -8 + (l * n + np.arange(n + 1)) * dx
+            xf[ax][mb] = f
+            xv[ax][mb] = f[:-1] + dx / 2
+        blk = A[lev][:, lk * n:(lk + 1) * n, lj * n:(lj + 1) * n, li * n:(li + 1) * n]
+        uov[:, mb] = blk[:5]
+        B[:, mb] = blk[5:]
+        for k in range(n + 2):
+            for j in range(n + 2):
+                for i in range(n + 2):
+                    v = value_at(lev, lk * n + k - 1, lj * n + j - 1, li * n + i - 1)
+                    if v is not None:
+                        expected[mb, :, k, j, i] = v
+    arr = dict(uov=uov, B=B, x1v=xv[0], x2v=xv[1], x3v=xv[2], x1f=xf[0], x2f=xf[1], x3f=xf[2],
+               LogicalLocations=np.array([[b[1], b[2], b[3]] for b in leaves]), Levels=np.array([b[0] for b in leaves]),
+               VariableNames=('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'), fluid_gamma=fluid_gamma)
+    return arr, expected

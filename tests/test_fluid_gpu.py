@@ -440,3 +440,31 @@ def test_noncubic_meshblocks(built):
             assert np.allclose(g, want[order[q]], rtol=1e-12, atol=1e-13), (kw, k)
         m.release()
     assert np.array_equal(device_model(arr, A).all_meshblocks, expected)          # host fill, non-cubic
+
+
+def test_three_level_mesh(built):
+    """Three refinement levels (22 blocks, 2:1 balanced): host and device ghost fills against the brute-force
+    expectation, and the level-aware block-grid lookup + sampling against the oracle's linear scan."""
+    from helpers import three_level_mesh
+    from oracle import c_oracle
+    arr, expected = three_level_mesh(n=4)
+    dm = device_model(arr, A)
+    assert np.abs(dm.all_meshblocks - expected).max() < 1e-15                       # host fill
+    got = np.asarray(dm.device_meshblocks())
+    assert np.array_equal(got, dm.all_meshblocks) and dm.storage == "f64"           # device fill, bit-identical
+    assert dm.lookup == "grid"
+    om = oracle_model(arr, A)
+    om.all_meshblocks = expected
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-8.5, 8.5, (6000, 3))
+    pts[:2000] = rng.uniform(3.0, 8.2, (2000, 3))                                    # the refined corner
+    faces = np.array([-8.0, 0.0, 4.0, 6.0, 7.0, 8.0])
+    pts[2000:2600] = rng.choice(faces, (600, 3))
+    S = np.concatenate([np.zeros((6000, 1)), pts, np.ones((6000, 1)), rng.normal(0, 0.5, (6000, 3))], 1)[None]
+    ref = c_oracle.sample(om, S, mode="prims")
+    out = dm.get_prims_from_geodesics(S)
+    for k in ref:
+        g = np.asarray(out[k])
+        assert np.array_equal(g == 0, ref[k] == 0), k
+        assert np.allclose(g, ref[k], rtol=1e-13, atol=1e-14 * np.abs(ref[k]).max()), k
+    assert set(np.unique(om._meshblock_indices(S)[0])) == set(range(-1, 22))        # every block is exercised
