@@ -242,14 +242,15 @@ def run_b200(args):
                 "nsteps": torch.empty((npx,), dtype=torch.int32, pin_memory=True),
                 "r_last": torch.empty((npx,), dtype=torch.float64, pin_memory=True)}
 
-    def step_e2e():
+    def step_e2e(chunks=None):
+        chunks = E2E_CHUNKS if chunks is None else chunks
         if store is not None:
             # public host-to-host call.  Default: zero-copy, the kernel reads s0 from pinned host memory and stores
             # the per-ray results into pinned host memory over PCIe (all bytes still move, inside the launch);
             # MK_E2E_CHUNKS > 0 selects the explicit chunked H2D / kernel / D2H pipeline instead
             store.reset()
-            if E2E_CHUNKS > 0:
-                geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=E2E_CHUNKS)
+            if chunks > 0:
+                geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=chunks)
             else:
                 geo.integrate_paged_host(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out)
             return int(host_out["nsteps"].sum())
@@ -303,15 +304,24 @@ def run_b200(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    # for comparison: the same host-to-host step with explicit cudaMemcpyAsync H2D / D2H copies (4-chunk pipeline)
+    step_e2e(chunks=4)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(chunks=4)
+    torch.cuda.synchronize()
+    e2e_copy_s = time.perf_counter() - t0
+    barrier()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     # ---- reduce over ranks: time = max, work = sum ----
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, e2e_copy_s], dtype=torch.float64, device=dev)
     w = torch.tensor([steps_per_pass, e2e_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    dev_ms_max, e2e_s_max, e2e_copy_s_max = float(t[0]), float(t[1]), float(t[2])
     work, e2e_work = float(w[0]), float(w[1])
     value = work * args.steps / (dev_ms_max * 1e-3)
     e2e_value = e2e_work * args.steps / e2e_s_max
@@ -336,6 +346,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "ray-steps/s", "h2d_bytes_per_step": int(npx * 64),
                     "d2h_bytes_per_step": int(npx * (64 + 4 + 8)), "ms_per_step": 1e3 * e2e_s_max / args.steps,
                     "host_numa_node": numa_node,
+                    "explicit_copy_pipeline": {"value": e2e_work * args.steps / e2e_copy_s_max, "unit": "ray-steps/s",
+                                               "ms_per_step": 1e3 * e2e_copy_s_max / args.steps,
+                                               "note": "same step with cudaMemcpyAsync H2D / D2H on side streams, 4 chunks"},
                     "transfer": ("zero-copy: the kernel reads s0 from / writes results to pinned host memory over PCIe"
                                  if E2E_CHUNKS <= 0 else f"{E2E_CHUNKS}-chunk H2D / kernel / D2H pipeline")},
             "gpu_launches": n_launch,

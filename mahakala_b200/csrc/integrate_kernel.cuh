@@ -52,24 +52,33 @@ constexpr int PAGE_SLOTS = 16;
 constexpr int PAGE_DOUBLES = PAGE_SLOTS * 32 * 9;
 enum { MODE_FINAL = 0, MODE_PADDED = 1, MODE_PAGED = 2 };
 
+// Per-lane ray bookkeeping that survives across steps (everything except the state vector and its point cache,
+// which ping-pong between two register sets, see integrate_body).
+struct LaneRay {
+    long ray;
+    double dt, r_cur, r_prev, best_dt, r_before_best;
+    int it, best_idx;
+};
+
 template <class Metric, int MODE>
 __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateArgs& A)
 {
     constexpr bool DUMP = (MODE == MODE_PADDED);
     int wpage = -1, wslot = 0, my_slot = 0;    // warp-uniform log position (MODE_PAGED)
     const unsigned lane = threadIdx.x & 31u;
-    long ray = -1;
     bool drained = false;           // queue exhausted (warp-uniform)
-    double s[8];
-    double dt = 0.0, r_cur = 0.0, r_prev = 0.0;
-    typename Metric::Cache cache, cache_new;
-    double best_dt = 0.0, r_before_best = 0.0;
-    int it = 0, best_idx = -1;
+    LaneRay L;
+    L.ray = -1; L.dt = 0.0; L.r_cur = 0.0; L.r_prev = 0.0; L.best_dt = 0.0; L.r_before_best = 0.0; L.it = 0; L.best_idx = -1;
     unsigned long long my_steps = 0;
 
-    for (;;) {
+    // One loop iteration of the reference's scan for every lane of the warp: refill idle lanes into (s, cache),
+    // take one step of the active lanes from (s, cache) into (sn, cn).  Returns false when the warp is done.
+    // The caller alternates the two register sets, so an accepted step needs no register-to-register copy of
+    // the 8-vector and its cache (the loop-carried moves were ~8 % of the issued instructions).
+    auto iteration = [&](double (&s)[8], typename Metric::Cache& cache, double (&sn)[8],
+                         typename Metric::Cache& cn) -> bool {
         // ---- refill idle lanes from the queue ----
-        unsigned idle = __ballot_sync(FULL_MASK, ray < 0);
+        unsigned idle = __ballot_sync(FULL_MASK, L.ray < 0);
         if (idle) {
             if (!drained) {
                 int cnt = __popc(idle);
@@ -78,24 +87,24 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 if ((int)lane == leader) base = atomicAdd(A.queue, (unsigned)cnt);
                 base = __shfl_sync(FULL_MASK, base, leader);
                 if ((long)base + cnt >= A.npx) drained = true;
-                if (ray < 0) {
+                if (L.ray < 0) {
                     long idx = (long)base + __popc(idle & ((1u << lane) - 1u));
                     if (idx < A.npx) {
-                        ray = idx;
+                        L.ray = idx;
                         const double4* p = reinterpret_cast<const double4*>(A.s0 + idx * 8);
                         double4 lo = p[0], hi = p[1];
                         s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
                         s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-                        r_cur = g.radius(s, cache);
-                        dt = A.rule(r_cur);
-                        r_prev = r_cur;
-                        it = 0; best_idx = -1; best_dt = -1.0e300; r_before_best = r_cur;
+                        L.r_cur = g.radius(s, cache);
+                        L.dt = A.rule(L.r_cur);
+                        L.r_prev = L.r_cur;
+                        L.it = 0; L.best_idx = -1; L.best_dt = -1.0e300; L.r_before_best = L.r_cur;
                     }
                 }
             }
-            if (__ballot_sync(FULL_MASK, ray >= 0) == 0) break;
+            if (__ballot_sync(FULL_MASK, L.ray >= 0) == 0) return false;
         }
-        const bool act = ray >= 0;
+        const bool act = L.ray >= 0;
 
         // ---- paged dump: the warp claims the next slot of its log (a new page every PAGE_SLOTS iterations) ----
         if (MODE == MODE_PAGED) {
@@ -116,28 +125,27 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
             }
             my_slot = wslot;
             wslot = (wslot + 1) & (PAGE_SLOTS - 1);
-            if (act && it == 0) {
-                A.page_first[2 * ray] = wpage;
-                A.page_first[2 * ray + 1] = my_slot * 32 + (int)lane;
+            if (act && L.it == 0) {
+                A.page_first[2 * L.ray] = wpage;
+                A.page_first[2 * L.ray + 1] = my_slot * 32 + (int)lane;
             }
         }
-        if (!act) continue;
+        if (!act) return true;
 
         // ---- one iteration of geodesic_step ----
-        double cand[8];
         double r_new = 0.0, dtn = 0.0;
-        if (dt != 0.0) {
-            rk4_step(g, s, dt, cand, &cache);
-            r_new = g.radius(cand, cache_new);
+        if (L.dt != 0.0) {
+            rk4_step(g, s, L.dt, sn, &cache);
+            r_new = g.radius(sn, cn);
             dtn = A.rule(r_new);
         }
-        bool frozen = (dt == 0.0) || (dtn == 0.0);
+        bool frozen = (L.dt == 0.0) || (dtn == 0.0);
         if (DUMP) {
-            if (it < A.nrows) {
-                double* p = A.S + ((long)it * A.npx + ray) * 8;
+            if (L.it < A.nrows) {
+                double* p = A.S + ((long)L.it * A.npx + L.ray) * 8;
                 store_256(p, s[0], s[1], s[2], s[3]);
                 store_256(p + 4, s[4], s[5], s[6], s[7]);
-                A.dt[(long)it * A.npx + ray] = frozen ? 0.0 : dt;
+                A.dt[(long)L.it * A.npx + L.ray] = frozen ? 0.0 : L.dt;
             }
         }
         if (MODE == MODE_PAGED) {
@@ -146,38 +154,47 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 int rr = my_slot * 32 + (int)lane;
                 store_256(pg + rr * 8, s[0], s[1], s[2], s[3]);
                 store_256(pg + rr * 8 + 4, s[4], s[5], s[6], s[7]);
-                pg[PAGE_SLOTS * 32 * 8 + rr] = frozen ? 0.0 : dt;
+                pg[PAGE_SLOTS * 32 * 8 + rr] = frozen ? 0.0 : L.dt;
             }
         }
         bool done = frozen;
         // geodesics.py:373: argmax(dt) is the first zero row (= it) unless some step size was positive (a ray
         // that jumped inside the horizon steps with dt > 0); the classifier row is argmax - 1, and -1 wraps to
         // the last row, a copy of the frozen state.
-        double rl = (best_dt > 0.0) ? ((best_idx >= 1) ? r_before_best : r_cur) : ((it >= 1) ? r_prev : r_cur);
+        double rl = (L.best_dt > 0.0) ? ((L.best_idx >= 1) ? L.r_before_best : L.r_cur)
+                                      : ((L.it >= 1) ? L.r_prev : L.r_cur);
+        bool capped = false;
         if (!frozen) {
-            if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
-            r_prev = r_cur; r_cur = r_new;
-            cache = cache_new;
-#pragma unroll
-            for (int i = 0; i < 8; i++) s[i] = cand[i];
-            dt = dtn;
-            it++;
-            if (it == A.N) {                        // never froze: argmax over the negative dts (:373)
+            if (L.dt > L.best_dt) { L.best_dt = L.dt; L.best_idx = L.it; L.r_before_best = L.r_prev; }
+            L.r_prev = L.r_cur; L.r_cur = r_new;
+            L.dt = dtn;
+            L.it++;
+            if (L.it == A.N) {                      // never froze: argmax over the negative dts (:373)
                 done = true;
-                rl = (best_idx >= 1) ? r_before_best : r_prev;
+                capped = true;
+                rl = (L.best_idx >= 1) ? L.r_before_best : L.r_prev;
             }
         }
         if (done) {
+            // a frozen ray ends at s (the rejected candidate is discarded); a capped ray at the accepted sn
             if (A.final_state) {
-                double4* p = reinterpret_cast<double4*>(A.final_state + ray * 8);
-                p[0] = make_double4(s[0], s[1], s[2], s[3]);
-                p[1] = make_double4(s[4], s[5], s[6], s[7]);
+                double4* p = reinterpret_cast<double4*>(A.final_state + L.ray * 8);
+                p[0] = capped ? make_double4(sn[0], sn[1], sn[2], sn[3]) : make_double4(s[0], s[1], s[2], s[3]);
+                p[1] = capped ? make_double4(sn[4], sn[5], sn[6], sn[7]) : make_double4(s[4], s[5], s[6], s[7]);
             }
-            if (A.nsteps) A.nsteps[ray] = it;
-            if (A.r_last) A.r_last[ray] = rl;
-            my_steps += (unsigned long long)it;
-            ray = -1;
+            if (A.nsteps) A.nsteps[L.ray] = L.it;
+            if (A.r_last) A.r_last[L.ray] = rl;
+            my_steps += (unsigned long long)L.it;
+            L.ray = -1;
         }
+        return true;
+    };
+
+    double sa[8], sb[8];
+    typename Metric::Cache ca, cb;
+    for (;;) {
+        if (!iteration(sa, ca, sb, cb)) break;      // live state: set A -> set B
+        if (!iteration(sb, cb, sa, ca)) break;      // live state: set B -> set A
     }
     if (A.total_steps) {
 #pragma unroll
