@@ -134,6 +134,9 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
 
         // Two loop shapes, chosen by measurement (scripts/variant_probe.py): with one or two frequencies the
         // software-pipelined form is ~2 % faster; with many frequencies its extra live registers spill.
+        // (The ping-pong register scheme of integrate_kernel.cuh, which removes the s = cand copies, was tried here
+        // too: it duplicates the whole sample + emission + RK4 body, and the kernel got 25 % SLOWER -- 34.2 vs
+        // 27.4 ms on cfg4 -- at any register budget: the doubled code no longer fits the instruction cache.)
         if constexpr (NF <= MK_RENDER_PIPE_MAX) {
             // Software-pipelined loop: the sample of state s (accepted in the previous iteration, weight wdt) and
             // the RK4 step that leaves s are independent, so they sit in ONE straight-line block and the scheduler
