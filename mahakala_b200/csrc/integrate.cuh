@@ -20,8 +20,10 @@ struct StepRule {
         double q = num * inv_div;                  // division by div, residual-corrected
         q = fma(fma(-q, div, num), inv_div, q);
         double m = fabs(q) * div;
-        bool zero = (q != q) || (m < tol) || (m > 1500.0);
-        return zero ? 0.0 : q;
+        // geodesics.py:250-252: zero if NaN, |dt| div < tol or |dt| div > 1500.  A NaN fails both ordered
+        // comparisons below, so the negated conjunction covers all three cases with two compares.
+        bool keep = (m >= tol) & (m <= 1500.0);
+        return keep ? q : 0.0;
     }
 };
 

@@ -158,21 +158,15 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
             }
         }
         bool done = frozen;
-        // geodesics.py:373: argmax(dt) is the first zero row (= it) unless some step size was positive (a ray
-        // that jumped inside the horizon steps with dt > 0); the classifier row is argmax - 1, and -1 wraps to
-        // the last row, a copy of the frozen state.
-        double rl = (L.best_dt > 0.0) ? ((L.best_idx >= 1) ? L.r_before_best : L.r_cur)
-                                      : ((L.it >= 1) ? L.r_prev : L.r_cur);
         bool capped = false;
         if (!frozen) {
             if (L.dt > L.best_dt) { L.best_dt = L.dt; L.best_idx = L.it; L.r_before_best = L.r_prev; }
             L.r_prev = L.r_cur; L.r_cur = r_new;
             L.dt = dtn;
             L.it++;
-            if (L.it == A.N) {                      // never froze: argmax over the negative dts (:373)
+            if (L.it == A.N) {                      // never froze
                 done = true;
                 capped = true;
-                rl = (L.best_idx >= 1) ? L.r_before_best : L.r_prev;
             }
         }
         if (done) {
@@ -183,7 +177,17 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 p[1] = capped ? make_double4(sn[4], sn[5], sn[6], sn[7]) : make_double4(s[4], s[5], s[6], s[7]);
             }
             if (A.nsteps) A.nsteps[L.ray] = L.it;
-            if (A.r_last) A.r_last[L.ray] = rl;
+            if (A.r_last) {
+                // geodesics.py:373: argmax(dt) is the first zero row (= it) unless some step size was positive (a
+                // ray that jumped inside the horizon steps with dt > 0); the classifier row is argmax - 1, and -1
+                // wraps to the last row, a copy of the frozen state.  A ray that never froze (capped) has no zero
+                // row: argmax over its negative dts.  (For a frozen ray r_prev / r_cur are still those of s.)
+                double rl;
+                if (capped) rl = (L.best_idx >= 1) ? L.r_before_best : L.r_prev;
+                else rl = (L.best_dt > 0.0) ? ((L.best_idx >= 1) ? L.r_before_best : L.r_cur)
+                                            : ((L.it >= 1) ? L.r_prev : L.r_cur);
+                A.r_last[L.ray] = rl;
+            }
             my_steps += (unsigned long long)L.it;
             L.ray = -1;
         }
