@@ -128,7 +128,7 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
         for (int f = 0; f < NF; f++) { I(f) = 0.0; T(f) = 1.0; }
         int it = 0;
         double dt = 0.0;
-        KerrSchild::Cache cache, cache_new;
+        KerrSchild::Cache cache;
         if (active) dt = A.rule(A.g.radius(s, cache));
         if (dt == 0.0) active = false;          // never moves: n = 0, no row pair contributes
 
@@ -145,7 +145,10 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
             bool pending = false;
             while (__any_sync(FULL_MASK, active)) {
                 if (active) {
-                    double cand[8], prims[8];
+                    // The RK4 step updates s IN PLACE: when the step is rejected the ray retires and its old state
+                    // is not needed any more (it was sampled above), so no candidate copy has to be kept.
+                    const double dt_used = dt;
+                    double prims[8];
                     double dtn;
                     if (pending && interp_prims(A.sn, s, prims)) {
                         my_samples++;
@@ -154,8 +157,8 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
                         A.g.fl(s, cache, f, l[1], l[2], l[3]);
                         emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
                                           [&](int fq, double e, double a) { em[fq] = e; ab[fq] = a; });
-                        rk4_step(A.g, s, dt, cand, &cache);
-                        dtn = A.rule(A.g.radius(cand, cache_new));
+                        rk4_step(A.g, s, dt, s, &cache);
+                        dtn = A.rule(A.g.radius(s, cache));
     #pragma unroll
                         for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
                             const double Tf = T(fq);
@@ -163,16 +166,13 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
                             T(fq) = Tf * fma(-wdt, ab[fq], 1.0);
                         }
                     } else {
-                        rk4_step(A.g, s, dt, cand, &cache);
-                        dtn = A.rule(A.g.radius(cand, cache_new));
+                        rk4_step(A.g, s, dt, s, &cache);
+                        dtn = A.rule(A.g.radius(s, cache));
                     }
                     if (dtn == 0.0) {
-                        active = false;             // step rejected; ray frozen at s (already sampled above)
+                        active = false;             // step rejected; the ray was frozen at the state sampled above
                     } else {
-                        wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
-    #pragma unroll
-                        for (int i = 0; i < 8; i++) s[i] = cand[i];
-                        cache = cache_new;
+                        wdt = -dt_used * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
                         dt = dtn;
                         it++;
                         pending = true;
@@ -183,16 +183,12 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
         } else {
             while (__any_sync(FULL_MASK, active)) {
                 if (active) {
-                    double cand[8];
-                    rk4_step(A.g, s, dt, cand, &cache);
-                    double dtn = A.rule(A.g.radius(cand, cache_new));
+                    rk4_step(A.g, s, dt, s, &cache);            // in place: a rejected step retires the ray
+                    double dtn = A.rule(A.g.radius(s, cache));
                     if (dtn == 0.0) {
-                        active = false;             // step rejected; ray frozen at s (geodesics.py:264-267)
+                        active = false;             // step rejected; ray frozen (geodesics.py:264-267)
                     } else {
                         const double wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0)
-    #pragma unroll
-                        for (int i = 0; i < 8; i++) s[i] = cand[i];
-                        cache = cache_new;
                         dt = dtn;
                         it++;
                         if (it == A.N) {
