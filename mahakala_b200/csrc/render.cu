@@ -66,7 +66,7 @@ struct RenderArgs {
 #define MK_RENDER_HI 4
 #endif
 #ifndef MK_RENDER_PIPE_MAX
-#define MK_RENDER_PIPE_MAX 2
+#define MK_RENDER_PIPE_MAX 0
 #endif
 // Experiment knob (off: 9 > max NF): from this many frequencies on, the (I, T) accumulators of a lane live in shared
 // memory ([2 NF][threads], conflict free) instead of registers.  Measured on B200 (cfg4, 8 frequencies): 40.1 ms
@@ -132,8 +132,13 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
         if (active) dt = A.rule(A.g.radius(s, cache));
         if (dt == 0.0) active = false;          // never moves: n = 0, no row pair contributes
 
-        // Two loop shapes, chosen by measurement (scripts/variant_probe.py): with one or two frequencies the
-        // software-pipelined form is ~2 % faster; with many frequencies its extra live registers spill.
+        // Two loop shapes (compile-time, MK_RENDER_PIPE_MAX = largest NF that uses the first): a software-pipelined
+        // form that samples the state accepted in the previous iteration next to the RK4 step that leaves it, and
+        // the plain form "step, then sample the new state".  Measured on B200 (scripts/dev/render_variants.py, cfg4,
+        // same-box A/B): while the loop still copied the candidate state the pipelined form was ~2 % ahead for one
+        // or two frequencies; with the in-place RK4 update the plain form wins everywhere (1 / 2 / 8 frequencies:
+        // 25.6 / 27.5 / 37.3 ms against 25.8 / 27.9 ms pipelined, and 33.5 / 40.5 ms when 4 / 8 frequencies are
+        // pipelined: its extra live registers spill), with one RK4 copy less in the instruction stream.
         // (The ping-pong register scheme of integrate_kernel.cuh, which removes the s = cand copies, was tried here
         // too: it duplicates the whole sample + emission + RK4 body, and the kernel got 25 % SLOWER -- 34.2 vs
         // 27.4 ms on cfg4 -- at any register budget: the doubled code no longer fits the instruction cache.)
