@@ -119,3 +119,51 @@ def write_hdf5(path, datasets, attrs=None, chunked=(), userblock=0):
     with open(path, "wb") as fh:
         fh.write(b"\x00" * userblock)
         fh.write(bytes(out))
+
+
+def write_hdf5_v2(path, datasets, attrs=None):
+    """The same content in the 'latest' file-format flavour (h5py libver='latest'): superblock version 2, version-2
+    object headers ("OHDR", 2-byte chunk size, no times), a new-style root group with compact link messages,
+    version-2 dataspaces, version-3 attribute messages, contiguous version-3 layouts.  Checksums are written as
+    zero (the reader does not verify them)."""
+    attrs = attrs or {}
+    out = bytearray(b"\x00" * 48)                              # superblock: 12 + 4 * 8 + 4 bytes
+
+    def append(b, align=8):
+        out.extend(b"\x00" * (-len(out) % align))
+        pos = len(out)
+        out.extend(b)
+        return pos
+
+    def dataspace2(shape):
+        return struct.pack("<BBBB", 2, len(shape), 0, 1 if len(shape) else 0) + b"".join(struct.pack("<Q", int(n)) for n in shape)
+
+    def msg2(mtype, body):
+        return struct.pack("<BHB", mtype, len(body), 0) + body
+
+    def ohdr2(messages):
+        body = b"".join(messages)
+        return b"OHDR" + struct.pack("<BB", 2, 0x01) + struct.pack("<H", len(body)) + body + b"\x00" * 4
+
+    def attribute3(name, value):
+        value = np.asarray(value)
+        nm = name.encode() + b"\x00"
+        dt, ds = _datatype(value.dtype), dataspace2(value.shape)
+        body = struct.pack("<BBHHHB", 3, 0, len(nm), len(dt), len(ds), 0) + nm + dt + ds
+        return msg2(0x0C, body + np.ascontiguousarray(value).tobytes())
+
+    links = []
+    for n in sorted(datasets):
+        a = np.ascontiguousarray(datasets[n])
+        data = append(a.tobytes())
+        layout = struct.pack("<BB", 3, 1) + struct.pack("<QQ", data, a.nbytes)
+        hdr = append(ohdr2([msg2(0x01, dataspace2(a.shape)), msg2(0x03, _datatype(a.dtype)), msg2(0x08, layout)]))
+        nm = n.encode()
+        links.append(msg2(0x06, struct.pack("<BBB", 1, 0, len(nm)) + nm + struct.pack("<Q", hdr)))
+    # link info message: version 0, flags 0, fractal heap address and name-index B-tree address undefined (compact)
+    linfo = msg2(0x02, struct.pack("<BB", 0, 0) + struct.pack("<QQ", UNDEF, UNDEF))
+    root = append(ohdr2([linfo] + links + [attribute3(k, v) for k, v in attrs.items()]))
+    sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", 0, UNDEF, len(out), root) + b"\x00" * 4
+    out[0:len(sb)] = sb
+    with open(path, "wb") as fh:
+        fh.write(bytes(out))

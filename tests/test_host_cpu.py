@@ -257,6 +257,24 @@ def test_minimal_hdf5_reader_on_a_third_party_file():
         f["nope"]
 
 
+def test_minimal_hdf5_reader_latest_format_flavour(tmp_path):
+    """Superblock 2, version-2 object headers, compact link messages, version-2 dataspaces, version-3 attributes
+    (what h5py writes with libver='latest'); dense link storage is refused loudly."""
+    from hdf5_writer import write_hdf5_v2
+    from mahakala_b200.grmhd._hdf5_min import Hdf5File
+    rng = np.random.default_rng(0)
+    data = {"uov": rng.normal(size=(5, 3, 4, 4, 4)).astype(np.float32), "Levels": np.arange(3, dtype=np.int32),
+            "x1f": rng.normal(size=(3, 5)), "LogicalLocations": rng.integers(0, 9, (3, 3)).astype(np.int64)}
+    fn = str(tmp_path / "latest.h5")
+    write_hdf5_v2(fn, data, attrs={"VariableNames": np.array(["dens", "velx"], dtype="S"), "Time": np.float64(3.25)})
+    f = Hdf5File(fn)
+    assert sorted(f.keys()) == sorted(data) and f.attrs["Time"] == 3.25
+    assert [n.decode() for n in f.attrs["VariableNames"]] == ["dens", "velx"]
+    for k, v in data.items():
+        got = f[k]
+        assert got.dtype == v.dtype and np.array_equal(got, v), k
+
+
 @pytest.mark.parametrize("variant", ["contiguous_f32", "chunked_userblock_f64"])
 def test_file_constructor_reads_athdf_without_h5py(tmp_path, variant):
     """AthenakFluidModel("x.athdf", bhspin, fluid_gamma) (athenak.py:50, :79-103) through the built-in reader: an
