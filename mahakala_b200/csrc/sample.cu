@@ -37,7 +37,8 @@ __global__ void repack_kernel(const double* __restrict__ src, CellT* __restrict_
 // d = (di, dj, dk) takes
 //   the edge cell of the same-level neighbour at LogicalLocation + d if that block exists, else
 //   (refined meshes) the coarse cell that contains it (injection) if the coarser neighbour exists, else
-//   the mean of the 8 finer cells it covers (summed in the order k, j, i with i fastest, then / 8) if all 8 exist,
+//   the mean of the 8 finer cells it covers (summed in the reference's order: i offset outermost, k innermost,
+//   then / 8; athenak.py:339-349, 405-422, 497-512) if all 8 exist,
 //   else zero (domain boundary).
 // Blocks are found by binary search in a table of (level, lk, lj, li) keys sorted on the host.
 // ---------------------------------------------------------------------------------------------------------
@@ -139,8 +140,8 @@ __global__ void ghost_fill_repack_kernel(InteriorSrc src, BlockTable tab, const 
 #pragma unroll
                     for (int q = 0; q < 8; q++) acc[q] = 0.0;
                     int cnt = 0;
-                    for (int o = 0; o < 8; o++) {    // o = ok*4 + oj*2 + oi: i fastest, as the host loop nests
-                        long f[3] = {2 * g[0] + (o & 1), 2 * g[1] + ((o >> 1) & 1), 2 * g[2] + ((o >> 2) & 1)};
+                    for (int o = 0; o < 8; o++) {    // o = oi*4 + oj*2 + ok: the reference's summation order
+                        long f[3] = {2 * g[0] + ((o >> 2) & 1), 2 * g[1] + ((o >> 1) & 1), 2 * g[2] + (o & 1)};
                         long fb[3], fc[3];
 #pragma unroll
                         for (int ax = 0; ax < 3; ax++) { fb[ax] = floor_div(f[ax], n[ax]); fc[ax] = f[ax] - fb[ax] * n[ax]; }

@@ -117,7 +117,8 @@ def _fill_from_other_levels(out, uov, B, index, mb, lev, loc, d):
     """Ghost cells across a refinement boundary (athenak.py:231-514).
 
     Coarser neighbour: injection (each ghost cell takes the value of the coarse cell that contains it).
-    Finer neighbour: each ghost cell is the average of the 8 fine cells it covers.
+    Finer neighbour: each ghost cell is the average of the 8 fine cells it covers, summed in the reference's order
+    (so that faces and corners, where the reference is correct, agree with it bit for bit).
     """
     nprim = uov.shape[0]
     n = (uov.shape[4], uov.shape[3], uov.shape[2])          # (ni, nj, nk)
@@ -144,9 +145,10 @@ def _fill_from_other_levels(out, uov, B, index, mb, lev, loc, d):
     # --- finer neighbours ---
     acc = np.zeros((8, len(tgt[2]), len(tgt[1]), len(tgt[0])))
     cnt = np.zeros((len(tgt[2]), len(tgt[1]), len(tgt[0])))
-    for ok in (0, 1):
+    # accumulation order of the reference (athenak.py:339-349, :405-422, :497-512): i offset outermost, k innermost
+    for oi in (0, 1):
         for oj in (0, 1):
-            for oi in (0, 1):
+            for ok in (0, 1):
                 off = (oi, oj, ok)
                 fine = [2 * gcell[ax] + off[ax] for ax in range(3)]
                 fb = [np.floor_divide(fine[ax], n[ax]) for ax in range(3)]

@@ -147,3 +147,40 @@ def test_notebook_trajectory_shape_pin(oracles):
     assert S.shape == (819, 60, 8) and dt.shape == (819, 60)
     S2, dt2 = onp.geodesic_integrator(10000, s0[::12], 40, 1e-4, 0.0)
     assert S2.shape[0] <= 819 and np.array_equal(dt2 == 0, dt[:S2.shape[0], ::12] == 0)
+
+
+@pytest.mark.parametrize("mesh", ["two_level", "three_level"])
+def test_amr_ghost_fill_matches_the_reference_algorithm(mesh):
+    """The loader's ghost-zone fill across refinement levels (athenak.py:208-514), restated literally in
+    oracle/athenak_ghost_literal.py, against the product's host fill (the device fill is bit-identical to it,
+    tests/test_fluid_gpu.py): same-level copies, coarse -> fine injection and the fine -> coarse 8-cell mean on faces
+    and corners agree BIT FOR BIT (same accumulation order); the reference's buggy edge branch is excluded and those
+    cells are pinned by the brute-force expectation instead."""
+    from helpers import three_level_mesh, two_level_mesh
+    from mahakala_b200.grmhd.athenak import fill_ghost_zones
+    from oracle.athenak_ghost_literal import fill_direction
+    arr, expected = (two_level_mesh(n=8) if mesh == "two_level" else three_level_mesh(n=4))
+    amb, index = fill_ghost_zones(arr["uov"], arr["B"], arr["LogicalLocations"], arr["Levels"])
+    assert np.abs(amb - expected).max() < 1e-15
+    data = np.concatenate([arr["uov"], arr["B"]], axis=0)
+    pinned = skipped = averaged = 0
+    for (lev, li, lj, lk), mb in index.items():
+        for dk in (-1, 0, 1):
+            for dj in (-1, 0, 1):
+                for di in (-1, 0, 1):
+                    if (di, dj, dk) == (0, 0, 0):
+                        continue
+                    r = fill_direction(data, index, mb, lev, (li, lj, lk), (di, dj, dk))
+                    if r is None:
+                        skipped += 1
+                        continue
+                    tgt, vals = r
+                    got = amb[mb][(slice(None),) + tgt]
+                    assert got.shape == vals.shape and np.array_equal(got, vals), (mb, lev, (li, lj, lk), (di, dj, dk))
+                    pinned += 1
+                    fine = (lev + 1, 2 * (li + di), 2 * (lj + dj), 2 * (lk + dk)) in index
+                    same = (lev, li + di, lj + dj, lk + dk) in index
+                    coarse = (lev - 1, (li + di) // 2, (lj + dj) // 2, (lk + dk) // 2) in index
+                    averaged += int(fine and not same and not coarse)
+    # a refined corner block shows 3 faces + 1 corner (pinned here) and 3 edges (skipped) to its coarse neighbours
+    assert pinned > 20 * len(index) and averaged >= 4 and 0 < skipped <= averaged, (pinned, averaged, skipped)
