@@ -468,3 +468,32 @@ def test_three_level_mesh(built):
         assert np.array_equal(g == 0, ref[k] == 0), k
         assert np.allclose(g, ref[k], rtol=1e-13, atol=1e-14 * np.abs(ref[k]).max()), k
     assert set(np.unique(om._meshblock_indices(S)[0])) == set(range(-1, 22))        # every block is exercised
+
+
+def test_kernels_match_vectors_from_the_reference_source(built):
+    """The thermodynamics / synchrotron / transfer kernels against tests/golden/reference_golden.npz, the vectors
+    obtained by executing the reference's own electrons.py / transfer.py (see tests/golden/make_reference_golden.py):
+    values to 1e-12, zero / NaN patterns exactly, the transfer scans bit for bit (same operation order)."""
+    import os
+    from mahakala_b200 import electrons, transfer
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.npz"))
+
+    def eq(a, b, rtol):
+        a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+        fin = np.isfinite(b)
+        return (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~fin & ~np.isnan(b)], b[~fin & ~np.isnan(b)])
+                and np.array_equal(a[fin] == 0, b[fin] == 0) and np.allclose(a[fin], b[fin], rtol=rtol, atol=0))
+
+    dens, u, beta = g["theta_in"]
+    assert eq(electrons.rlow_rhigh_model(dens, u, beta), g["theta_default"], 1e-14)
+    assert eq(electrons.rlow_rhigh_model(dens, u, beta, r_low=10, r_high=160), g["theta_r10_r160"], 1e-14)
+    Ne, Th, B, pitch, nu = g["syn_in"]
+    for tag, kw in {"inv": dict(invariant=True, rescale_nu=1. / 230e9), "inv1": dict(invariant=True),
+                    "plain": dict(invariant=False)}.items():
+        em, ab = transfer.synchrotron_coefficients(Ne, Th, B, pitch, nu, **kw)
+        assert eq(em, g["syn_em_" + tag], 1e-12) and eq(ab, g["syn_ab_" + tag], 1e-12), tag
+    em2, ab2, dt, L = g["tr_in_em"], g["tr_in_ab"], g["tr_in_dt"], float(g["tr_in_L"])
+    assert np.array_equal(np.asarray(transfer.solve_specific_intensity(em2, ab2, dt, L)), g["tr_I"])
+    I2, dIs = transfer.solve_specific_intensity(em2, ab2, dt, L, dIs=True)
+    assert np.array_equal(np.asarray(I2), g["tr_I_dIs"]) and np.array_equal(np.asarray(dIs), g["tr_dIs"])
+    assert eq(transfer.solve_attenuated_emissivity(em2, ab2, dt, L), g["tr_attenuated"], 1e-13)

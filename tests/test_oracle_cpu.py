@@ -184,3 +184,51 @@ def test_amr_ghost_fill_matches_the_reference_algorithm(mesh):
                     averaged += int(fine and not same and not coarse)
     # a refined corner block shows 3 faces + 1 corner (pinned here) and 3 edges (skipped) to its coarse neighbours
     assert pinned > 20 * len(index) and averaged >= 4 and 0 < skipped <= averaged, (pinned, averaged, skipped)
+
+
+REF_GOLDEN = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden",
+                                          "reference_golden.npz")
+
+
+def _eq(a, b, rtol):
+    """agreement incl. identical zero / NaN / inf patterns"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    fin = np.isfinite(b)
+    return (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~fin & ~np.isnan(b)], b[~fin & ~np.isnan(b)])
+            and np.array_equal(a[fin] == 0, b[fin] == 0) and np.allclose(a[fin], b[fin], rtol=rtol, atol=0))
+
+
+def test_oracle_matches_vectors_from_the_reference_source(oracles):
+    """tests/golden/reference_golden.npz was produced by executing the reference's OWN files (constants.py,
+    electrons.py, grmhd/grmhd.py, transfer.py) against a NumPy stand-in for jax.numpy / lax
+    (tests/golden/make_reference_golden.py).  The oracle restatement, the product's constant table and its host-side
+    get_units must reproduce those vectors: constants digit for digit, arithmetic to rounding (1e-13), zero / NaN
+    patterns exactly."""
+    onp, _ = oracles
+    g = np.load(REF_GOLDEN)
+    from mahakala_b200 import constants as C
+    from mahakala_b200.grmhd import GRMHDFluidModel
+    for k in ("EE", "KB", "CL", "ME", "HPL", "GNEWT", "Msun", "MP", "EC"):
+        assert getattr(C, k) == float(g["const_" + k]), k
+    for tag in ("a", "b"):
+        M, ms = g["units_%s_in" % tag]
+        for model in (onp.GRMHDFluidModel(), GRMHDFluidModel()):
+            u = model.get_units(M, ms)
+            got = np.array([u[k] for k in ("L_unit", "T_unit", "dens_unit", "Ne_unit", "B_unit")])
+            assert np.allclose(got, g["units_%s_out" % tag], rtol=1e-15, atol=0)
+    with np.errstate(all="ignore"):
+        dens, u, beta = g["theta_in"]
+        assert _eq(onp.rlow_rhigh_model(dens, u, beta), g["theta_default"], 1e-14)
+        assert _eq(onp.rlow_rhigh_model(dens, u, beta, r_low=10, r_high=160), g["theta_r10_r160"], 1e-14)
+        Ne, Th, B, pitch, nu = g["syn_in"]
+        for tag, kw in {"inv": dict(invariant=True, rescale_nu=1. / 230e9), "inv1": dict(invariant=True),
+                        "plain": dict(invariant=False)}.items():
+            em, ab = onp.synchrotron_coefficients(Ne, Th, B, pitch, nu, **kw)
+            assert _eq(em, g["syn_em_" + tag], 1e-13) and _eq(ab, g["syn_ab_" + tag], 1e-13), tag
+        assert (g["syn_em_inv"] > 0).sum() > 1000 and (g["syn_em_inv"] == 0).sum() > 100
+        em2, ab2, dt, L = g["tr_in_em"], g["tr_in_ab"], g["tr_in_dt"], float(g["tr_in_L"])
+        # same operations in the same order under the same libm: bit-identical
+        assert np.isfinite(g["tr_I"]).all() and np.array_equal(onp.solve_specific_intensity(em2, ab2, dt, L), g["tr_I"])
+        I2, dIs = onp.solve_specific_intensity(em2, ab2, dt, L, dIs=True)
+        assert np.array_equal(I2, g["tr_I_dIs"]) and np.array_equal(dIs, g["tr_dIs"])
+        assert np.array_equal(onp.solve_attenuated_emissivity(em2, ab2, dt, L), g["tr_attenuated"])
