@@ -465,3 +465,55 @@ def test_zero_copy_host_to_host_matches_device_path(ma):
         assert torch.equal(S, S_ref) and torch.equal(dt, dt_ref)
     with pytest.raises(ValueError):
         geo.integrate_paged_host(N, s0_host.clone(), 40, 1e-4, a, geo.TrajectoryStore.allocate(npx, N), outs())   # not pinned
+
+
+def test_cuda_path_matches_the_reference_geodesics_source(ma):
+    """The CUDA geodesic path against tests/golden/reference_geodesics_golden.npz, the outputs of the reference's OWN
+    geodesics.py under a NumPy stand-in for JAX (tests/golden/make_reference_geodesics_golden.py): metric, inverse,
+    rhs, one RK4 step, the three cameras, stored trajectories (same shape after the +2 truncation, same freeze
+    pattern and step counts, end states within the north-star 1e-9 on escaped rays), the iteration cap, the shadow
+    radii."""
+    import os
+    from mahakala_b200 import geodesics as geo
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_geodesics_golden.npz"))
+    a = 0.94
+    st = g["pt_states"]
+    rel = lambda x, y: np.abs(np.asarray(x) - y).max() / np.abs(y).max()
+    assert rel(geo.metric(st[:, :4], a), g["pt_metric"]) < 1e-12
+    assert rel(geo.imetric(st[:, :4], a), g["pt_imetric"]) < 1e-11
+    assert rel(geo.radius_cal(st[:, :4], a), g["pt_radius"]) < 1e-14
+    r = np.asarray(geo.rhs(st, a))
+    assert max(np.abs(r[i] - g["pt_rhs"][i]).max() / np.abs(g["pt_rhs"][i]).max() for i in range(len(st))) < 1e-11
+    k = np.asarray(geo.RK4_gen(st, g["pt_rk4_dt"], a))
+    assert max(np.abs(k[i] - g["pt_rk4"][i]).max() / np.abs(g["pt_rk4"][i]).max() for i in range(len(st))) < 1e-11
+    s0_ref = g["cam_grid_a094_i60_res6"]
+    s0 = np.asarray(ma.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 6))
+    assert np.array_equal(s0[:, :4], s0_ref[:, :4]) and np.allclose(s0[:, 4:], s0_ref[:, 4:], rtol=1e-13, atol=1e-300)
+    eq = np.asarray(ma.initialize_geodesics_at_camera(0.0, 60, 1000, -15, 15, 8, camera_type='Equator'))
+    assert np.allclose(eq, g["cam_equator_a0_res8"], rtol=1e-13, atol=1e-300)
+    x, v = geo.get_camera_pixel(52, 1000, np.array([3.0, 5.2, 7.5]), np.array([0.3, 2.0, 4.4]))
+    assert np.allclose(np.asarray(x), g["cam_pixel_x"], rtol=1e-13, atol=1e-12)
+    assert np.allclose(np.asarray(v), g["cam_pixel_v"], rtol=1e-12, atol=1e-9)
+    # trajectories
+    S, dt = ma.geodesic_integrator(2000, s0_ref, 40, 1e-2, a)
+    S, dt = np.asarray(S), np.asarray(dt)
+    n = (g["traj_dt"] != 0).sum(0)
+    assert S.shape == g["traj_S"].shape == (610, 36, 8) and np.array_equal(dt == 0, g["traj_dt"] == 0)
+    fin_ref = g["traj_S"][n, np.arange(36)]
+    captured = np.asarray(geo.radius_cal(g["traj_S"][np.maximum(n - 1, 0), np.arange(36)][:, :4], a)) < 100
+    err = np.abs(S[n, np.arange(36)] - fin_ref).max(1) / np.abs(fin_ref).max(1)
+    assert captured.sum() == 8 and err[~captured].max() < 1e-9
+    assert np.allclose(dt[:, ~captured], g["traj_dt"][:, ~captured], rtol=1e-8, atol=0)
+    f, ns, rl = geo.integrate_final(2000, s0_ref, 40, 1e-2, a)
+    assert np.array_equal(np.asarray(ns.cpu()), n) and np.array_equal(np.asarray(rl.cpu()) < 100, captured)
+    # iteration cap: N rows, no truncation, last row still moving
+    S2, dt2 = ma.geodesic_integrator(450, s0_ref[[0, 14, 15, 21]], 40, 1e-4, a)
+    S2, dt2 = np.asarray(S2), np.asarray(dt2)
+    assert S2.shape == (450, 4, 8) and np.array_equal(dt2 == 0, g["traj_cap_dt"] == 0)
+    moving = g["traj_cap_dt"][-1] != 0
+    assert moving.any() and rel(S2[-1][moving], g["traj_cap_S"][-1][moving]) < 1e-8
+    # last-point rule and the bisection
+    sel = np.asarray(geo.select_photons_integrator(60, g["shadow_angles"], np.array([2.0, 4.0, 5.0, 5.5, 6.0, 8.0]), a))
+    assert np.array_equal(sel < 100, g["select_r"] < 100) and np.allclose(sel, g["select_r"], rtol=1e-4)
+    radii = np.asarray(ma.find_shadow_bisection_angles(a, 60, g["shadow_angles"]))
+    assert np.allclose(radii, g["shadow_radii_a094_i60"], rtol=0, atol=2e-3)

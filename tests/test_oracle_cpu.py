@@ -232,3 +232,59 @@ def test_oracle_matches_vectors_from_the_reference_source(oracles):
         I2, dIs = onp.solve_specific_intensity(em2, ab2, dt, L, dIs=True)
         assert np.array_equal(I2, g["tr_I_dIs"]) and np.array_equal(dIs, g["tr_dIs"])
         assert np.array_equal(onp.solve_attenuated_emissivity(em2, ab2, dt, L), g["tr_attenuated"])
+
+
+REF_GEO_GOLDEN = REF_GOLDEN.replace("reference_golden", "reference_geodesics_golden")
+
+
+def test_oracle_matches_the_reference_geodesics_source(oracles):
+    """tests/golden/reference_geodesics_golden.npz = outputs of the reference's OWN geodesics.py executed against a
+    NumPy stand-in for jit / vmap / lax.scan / inv, with jacfwd replaced by a complex-step derivative of the
+    reference's metric (tests/golden/make_reference_geodesics_golden.py).  The restatements (NumPy and C) must agree:
+    metric, inverse, radius and cameras to the last bit or two, rhs to 1e-13, trajectories with IDENTICAL shape
+    (the +2 truncation), freeze pattern and step counts, end states at the noise floor, shadow radii bit for bit."""
+    onp, c_oracle = oracles
+    g = np.load(REF_GEO_GOLDEN)
+    a = 0.94
+    st = g["pt_states"]
+    rel = lambda x, y: np.abs(np.asarray(x) - y).max() / np.abs(y).max()
+    assert rel(np.stack([onp.metric(p[:4], a) for p in st]), g["pt_metric"]) < 1e-15
+    assert rel(np.stack([onp.imetric(p[:4], a) for p in st]), g["pt_imetric"]) < 1e-14
+    assert rel(onp.radius_cal(st[:, :4], a), g["pt_radius"]) < 1e-15
+    for rhs in (onp.rhs, c_oracle.rhs):
+        r = rhs(st, a)
+        assert max(np.abs(r[i] - g["pt_rhs"][i]).max() / np.abs(g["pt_rhs"][i]).max() for i in range(len(st))) < 1e-13
+    assert rel(onp.RK4_gen(st, g["pt_rk4_dt"], a), g["pt_rk4"]) < 1e-14
+    s0 = g["cam_grid_a094_i60_res6"]
+    mine = onp.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 6)
+    assert np.array_equal(mine[:, :4], s0[:, :4]) and rel(mine, s0) < 1e-15
+    assert rel(onp.initialize_geodesics_at_camera(0.0, 60, 1000, -15, 15, 8, camera_type='Equator'), g["cam_equator_a0_res8"]) < 1e-15
+    x, v = onp.get_camera_pixel(52, 1000, np.array([3.0, 5.2, 7.5]), np.array([0.3, 2.0, 4.4]))
+    assert rel(x, g["cam_pixel_x"]) < 1e-15 and rel(v, g["cam_pixel_v"]) < 1e-15
+    n = (g["traj_dt"] != 0).sum(0)
+    fin = g["traj_S"][n, np.arange(n.size)]
+    captured = onp.radius_cal(g["traj_S"][np.maximum(n - 1, 0), np.arange(n.size)][:, :4], a) < 100
+    assert 0 < captured.sum() < n.size
+    for integ in (onp.geodesic_integrator, c_oracle.geodesic_integrator):
+        rays = slice(0, 36, 3) if integ is onp.geodesic_integrator else slice(None)      # NumPy: a third of the rays
+        if integ is onp.geodesic_integrator:
+            S, dt = integ(2000, s0[rays], 40, 1e-2, a)
+            assert S.shape[0] <= g["traj_S"].shape[0]
+            nn = (dt != 0).sum(0)
+            assert np.array_equal(nn, n[rays]) and np.array_equal(dt[:nn.max() + 1] == 0, g["traj_dt"][:nn.max() + 1, rays] == 0)
+            e = np.abs(S[nn, np.arange(nn.size)] - fin[rays]).max(1) / np.abs(fin[rays]).max(1)
+            assert e[~captured[rays]].max() < 1e-12 and e[captured[rays]].max() < 1e-10
+            continue
+        S, dt = integ(2000, s0, 40, 1e-2, a)
+        assert S.shape == g["traj_S"].shape and np.array_equal(dt == 0, g["traj_dt"] == 0)
+        err = np.abs(S[n, np.arange(n.size)] - fin).max(1) / np.abs(fin).max(1)
+        assert err[~captured].max() < 1e-12 and err[captured].max() < 1e-10
+        assert np.allclose(dt, g["traj_dt"], rtol=1e-10, atol=0)
+        S2, dt2 = integ(450, s0[[0, 14, 15, 21]], 40, 1e-4, a)
+        assert S2.shape == g["traj_cap_S"].shape == (450, 4, 8) and np.array_equal(dt2 == 0, g["traj_cap_dt"] == 0)
+        assert (g["traj_cap_dt"][-1] != 0).any() and rel(S2[-1], g["traj_cap_S"][-1]) < 1e-10
+    got = onp.select_photons_integrator(60, g["shadow_angles"], np.array([2.0, 4.0, 5.0, 5.5, 6.0, 8.0]), a,
+                                        integrator=c_oracle.geodesic_integrator)
+    assert np.allclose(got, g["select_r"], rtol=1e-9)
+    assert np.array_equal(onp.find_shadow_bisection_angles(a, 60, g["shadow_angles"], integrator=c_oracle.geodesic_integrator),
+                          g["shadow_radii_a094_i60"])
