@@ -14,10 +14,20 @@ network), so this oracle is pinned against
 * a line-for-line ``torch.func.jacfwd``/``vmap``/``linalg.inv`` transliteration of ``geodesics.py:294-347``
   (``oracle/literal_torch.py``) and 50-digit mpmath evaluation of the metric derivatives.
 
-Everything else on the path (trajectory values, grid camera, sampling, Theta_e, j/alpha, transfer,
-images) has NO golden vector in the reference: for those rows parity is "unpinned by the reference's own
-tests" and rests on this restatement being auditable line by line.  Each function cites the reference
-file:line (relative to /root/reference/mahakala/) it follows.
+* OUTPUTS OF THE REFERENCE'S OWN SOURCE FILES run in the build container against a NumPy stand-in for the JAX
+  names they import (``tests/golden/make_reference_golden.py``: constants.py, electrons.py, grmhd/grmhd.py,
+  transfer.py; ``tests/golden/make_reference_geodesics_golden.py``: the whole of geodesics.py, with ``jacfwd``
+  replaced by a complex-step derivative of the reference's metric).  Frozen in ``tests/golden/reference_golden.npz``
+  and ``reference_geodesics_golden.npz`` and checked in ``tests/test_oracle_cpu.py``: metric, inverse, radius and the
+  three cameras agree to the last bit or two, rhs to 1e-15, stored trajectories have the identical shape, freeze
+  pattern and step counts with end states at 3e-15 (escaped) / 9e-14 (captured), the shadow radii and the transfer
+  scans are bit-identical, Theta_e / j / alpha agree to 1e-13 with identical zero / NaN patterns.
+
+What still has NO vector produced by reference code: the AthenaK sampling / fluid-frame algebra of
+``athenak.py:639-812`` and whole images (``images.py``), which need h5py + a real JAX to execute; for those rows parity
+is "unpinned by the reference" and rests on this restatement being auditable line by line (the ghost-zone fill is
+checked bit for bit against a literal restatement, ``oracle/athenak_ghost_literal.py``).  Each function cites the
+reference file:line (relative to /root/reference/mahakala/) it follows.
 
 Forward-mode differentiation (``jacfwd(metric)``, geodesics.py:305) is restated with an explicit jet
 (value + 4 tangents) pushed through the *same* metric expression, the matrix inverse (geodesics.py:347)

@@ -7,10 +7,12 @@
  * (cpu_baseline.kind = "port"; JAX itself is not installable in this image).
  * Build:  make -C oracle   (gcc -O2 -ffp-contract=off -fopenmp; no FMA contraction, IEEE semantics)
  *
- * Parity pinning: validated against oracle/mahakala_oracle.py (NumPy restatement) which in turn passes
- * the reference's golden shadow vectors (tests/golden/shadow_golden.npz) — tests/test_oracle_*.py.
- * Rows with no golden vector in the reference (trajectories, sampling, transfer, images) are
- * "parity unpinned by the reference's own tests".
+ * Parity pinning: validated against oracle/mahakala_oracle.py (NumPy restatement), against the reference's golden
+ * shadow vectors (tests/golden/shadow_golden.npz) and against outputs of the reference's own geodesics.py executed
+ * with a NumPy stand-in for JAX (tests/golden/reference_geodesics_golden.npz: identical trajectory shapes, freeze
+ * patterns and step counts, end states at 1e-14, bit-identical shadow radii) -- tests/test_oracle_cpu.py.
+ * The AthenaK sampling / fluid-frame algebra and whole images have no vector produced by reference code:
+ * "parity unpinned by the reference" for those rows.
  *
  * Citations are to /root/reference/mahakala/<file>:<line>.
  */
