@@ -23,11 +23,15 @@ network), so this oracle is pinned against
   pattern and step counts with end states at 3e-15 (escaped) / 9e-14 (captured), the shadow radii and the transfer
   scans are bit-identical, Theta_e / j / alpha agree to 1e-13 with identical zero / NaN patterns.
 
-What still has NO vector produced by reference code: the AthenaK sampling / fluid-frame algebra of
-``athenak.py:639-812`` and whole images (``images.py``), which need h5py + a real JAX to execute; for those rows parity
-is "unpinned by the reference" and rests on this restatement being auditable line by line (the ghost-zone fill is
-checked bit for bit against a literal restatement, ``oracle/athenak_ghost_literal.py``).  Each function cites the
-reference file:line (relative to /root/reference/mahakala/) it follows.
+* OUTPUTS OF THE WHOLE REFERENCE PACKAGE (real ``__init__``, athenak.py loader and sampling, images.make_image)
+  imported with the same stand-in plus an in-memory ``h5py`` (``tests/golden/make_reference_fluid_golden.py`` ->
+  ``reference_fluid_golden.npz``): ghost-zone fill bit-identical on a single-level snapshot (and different from the
+  reference only in the edge ghost cells its AMR branch gets wrong), sampled primitives bit-identical, fluid scalars
+  1e-16, images 1e-13 per pixel.
+
+What no vector covers is XLA itself (its libm and optional FMA contraction): the stand-in evaluates the reference's
+text under NumPy's IEEE double arithmetic.  Each function cites the reference file:line (relative to
+/root/reference/mahakala/) it follows.
 
 Forward-mode differentiation (``jacfwd(metric)``, geodesics.py:305) is restated with an explicit jet
 (value + 4 tangents) pushed through the *same* metric expression, the matrix inverse (geodesics.py:347)
