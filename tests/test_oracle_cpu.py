@@ -346,3 +346,21 @@ def test_oracle_matches_the_reference_package_on_snapshots_and_images(oracles):
     ref2i = g["image_res6_345GHz_i30"]
     err2 = np.abs(img2[0].reshape(6, 6) - ref2i) / np.maximum(np.abs(ref2i), 1e-6 * ref2i.max())
     assert ref2i.max() > 0 and err2.max() < 1e-12
+
+
+def test_stand_in_reproduces_numbers_made_by_real_jax(oracles):
+    """The vectors of the three reference_*_golden files come from the reference's source run under a NumPy stand-in
+    for JAX.  tests/golden/validate_stand_in.py checks that stand-in against the two numbers in the reference repo
+    that REAL JAX produced: the (819, 60, 8) trajectory shape of demos/shadows.ipynb and the golden shadow radii of
+    tests/data/shadow_data.npy (case test4).  Its frozen output must show both, and the oracle must agree with it."""
+    import os
+    onp, c_oracle = oracles
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    v = np.load(os.path.join(here, "standin_validation.npz"))
+    gold = np.load(os.path.join(here, "shadow_golden.npz"))
+    assert tuple(v["notebook_shape"]) == (819, 60, 8)
+    assert np.allclose(v["test4_radii"], gold["test4__radii"], rtol=1e-2)           # the reference's own criterion
+    assert np.max(np.abs(v["test4_radii"] - gold["test4__radii"]) / gold["test4__radii"]) < 2e-4
+    mine = onp.find_shadow_bisection_angles(float(gold["test4__bhspin"]), float(gold["test4__inclination"]),
+                                            gold["test4__angles"], integrator=c_oracle.geodesic_integrator)
+    assert np.array_equal(mine, v["test4_radii"])                                   # bit for bit
