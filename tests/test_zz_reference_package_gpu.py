@@ -1,0 +1,48 @@
+"""CUDA path against the vectors produced by the whole reference package (tests/golden/reference_fluid_golden.npz).
+
+Kept in its own module, collected last: it was written after the round's GPU budget was spent, so unlike every other
+`-m gpu` test it had not run on a B200 when it was committed (it follows the validated smoke / sampling / image tests).
+"""
+import numpy as np
+import pytest
+
+from helpers import device_model
+
+pytestmark = pytest.mark.gpu
+A = 0.94
+
+
+def test_cuda_path_matches_the_reference_package_on_snapshots_and_images(built):
+    """The CUDA sampling / image path against tests/golden/reference_fluid_golden.npz, produced by the whole reference
+    package (its own loader, get_prims_from_geodesics, get_fluid_scalars_from_geodesics and make_image) running under a
+    NumPy-backed `jax` (tests/golden/make_reference_fluid_golden.py): device ghost fill bit for bit, sampled
+    primitives to 1e-13 with the exact zero pattern, fluid scalars to 1e-10, images to the north-star 1e-6 per pixel
+    and 1e-8 in flux."""
+    import os
+    from mahakala_b200 import images
+    from mahakala_b200.synthetic import make_synthetic_snapshot
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_fluid_golden.npz"))
+    single = make_synthetic_snapshot(ncells=16, block=8, extent=16.0, seed=0)
+    dm = device_model(single, A)
+    assert np.array_equal(np.asarray(dm.device_meshblocks()), g["single_all_meshblocks"])
+    S = g["sample_S"]
+    got = dm.get_prims_from_geodesics(S)
+    for q, k in enumerate(('dens', 'u', 'U1', 'U2', 'U3', 'B1', 'B2', 'B3')):
+        ref = g["sample_prims"][q]
+        v = np.asarray(got[k])
+        assert np.array_equal(v == 0, ref == 0), k
+        assert np.abs(v - ref).max() <= 1e-13 * np.abs(ref).max(), k
+    sc = dm.get_fluid_scalars_from_geodesics(S)
+    for q, k in enumerate(('dens', 'u', 'pitch_angle', 'kdotu', 'b')):
+        ref = g["sample_scalars"][q]
+        assert np.abs(np.asarray(sc[k]) - ref).max() <= 1e-10 * np.abs(ref).max(), k
+
+    def check(img, ref):
+        err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * ref.max())
+        assert ref.max() > 0 and err.max() < 1e-6 and abs(img.sum() - ref.sum()) / ref.sum() < 1e-8, (err.max(),)
+
+    check(images.make_image(dm, resolution=6), g["image_res6"])
+    check(images.make_image_unfused(dm, resolution=6, max_chunk_bytes=12 * 4 * 20 * 10000), g["image_res6_chunked"])
+    check(images.make_image(dm, camera_inclination=30, observing_frequency=345e9, r_high=10, resolution=6, max_nsteps=3000),
+          g["image_res6_345GHz_i30"])
+    dm.release()
