@@ -368,3 +368,24 @@ def test_stand_in_reproduces_numbers_made_by_real_jax(oracles):
                                                 gold[case + "__angles"], integrator=c_oracle.geodesic_integrator)
         assert np.array_equal(mine, radii), case                             # oracle == reference source, bit for bit
     assert worst["test1"] < 2.2e-3 and max(worst[c] for c in ("test2", "test3", "test4")) < 3.3e-4
+
+
+def test_cfg1_grid_by_the_reference_source(oracles):
+    """BASELINE config 1 (a = 0.94, i = 60 deg, 64x64 grid, tol 1e-2, N 2000) computed by the reference's OWN
+    geodesics.py under the NumPy stand-in (tests/golden/make_reference_cfg1_golden.py): 792 captured rays and
+    2 079 364 ray-steps.  The C oracle must agree ray by ray: identical step counts (captured rays included),
+    bit-exact captured / escaped classification, end states at the noise floor."""
+    import os
+    onp, c_oracle = oracles
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cfg1_golden.npz"))
+    a = 0.94
+    s0 = onp.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 64)
+    assert np.array_equal(s0[:, :4], g["s0"][:, :4]) and np.allclose(s0, g["s0"], rtol=1e-15, atol=0)
+    cap = g["r_last"] < 100
+    assert cap.sum() == 792 and int(g["nsteps"].sum()) == 2079364
+    o = c_oracle.integrate(2000, g["s0"], 40, 1e-2, a)
+    assert np.array_equal(o["nsteps"], g["nsteps"])
+    assert np.array_equal(o["r_last"] < 100, cap)
+    err = np.abs(o["final"] - g["final"]).max(1) / np.abs(g["final"]).max(1)
+    assert err[~cap].max() < 1e-11 and np.median(err[~cap]) < 1e-14 and err[cap].max() < 1e-6
+    assert np.allclose(o["r_last"][~cap], g["r_last"][~cap], rtol=1e-10)

@@ -46,3 +46,24 @@ def test_cuda_path_matches_the_reference_package_on_snapshots_and_images(built):
     check(images.make_image(dm, camera_inclination=30, observing_frequency=345e9, r_high=10, resolution=6, max_nsteps=3000),
           g["image_res6_345GHz_i30"])
     dm.release()
+
+
+def test_cuda_cfg1_grid_against_the_reference_source(built):
+    """BASELINE config 1 against tests/golden/reference_cfg1_golden.npz (the reference's own geodesics.py on the full
+    64x64 grid under the NumPy stand-in): captured / escaped classification bit-exact (792 captured), step counts
+    identical on escaped rays, end states of escaped rays within the north-star 1e-9.  Mirrors
+    test_geodesics_gpu.py::test_cfg1_grid_classification_and_states with the oracle replaced by reference output."""
+    import os
+    import mahakala_b200 as ma
+    from mahakala_b200 import geodesics as geo
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cfg1_golden.npz"))
+    s0 = np.asarray(ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 64))
+    assert np.array_equal(s0[:, :4], g["s0"][:, :4]) and np.allclose(s0[:, 4:], g["s0"][:, 4:], rtol=1e-13, atol=1e-300)
+    final, nsteps, r_last = (np.asarray(q.cpu()) for q in geo.integrate_final(2000, g["s0"], 40, 1e-2, A))
+    cap_ref = g["r_last"] < 100
+    assert cap_ref.sum() == 792 and np.array_equal(r_last < 100, cap_ref)
+    esc = ~cap_ref
+    assert np.array_equal(nsteps[esc], g["nsteps"][esc])
+    assert abs(int(nsteps.sum()) - 2079364) <= 64          # captured rays may differ by a step in the chaotic tail
+    err = np.abs(final[esc] - g["final"][esc]).max(axis=1) / np.abs(g["final"][esc]).max(axis=1)
+    assert np.median(err) < 1e-12 and err.max() < 1e-9, err.max()
