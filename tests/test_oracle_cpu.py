@@ -389,3 +389,23 @@ def test_cfg1_grid_by_the_reference_source(oracles):
     err = np.abs(o["final"] - g["final"]).max(1) / np.abs(g["final"]).max(1)
     assert err[~cap].max() < 1e-11 and np.median(err[~cap]) < 1e-14 and err[cap].max() < 1e-6
     assert np.allclose(o["r_last"][~cap], g["r_last"][~cap], rtol=1e-10)
+
+
+def test_cfg2_sublattice_by_the_reference_source(oracles):
+    """BASELINE config 2 settings (1024x1024 grid, a = 0.94, i = 60 deg, tol 1e-4, N 10000) on the every-16th-pixel
+    64x64 sub-lattice, computed by the reference's OWN geodesics.py under the NumPy stand-in
+    (tests/golden/make_reference_cfg2_golden.py): 799 captured rays, 2 177 333 ray-steps, longest ray 2280 steps.
+    The C oracle agrees ray by ray: identical step counts on all 4096 rays, bit-exact classification, end states of
+    escaped rays at 4e-12, of captured rays (chaotic tail, SURVEY 2.2 #8) at 5e-8."""
+    import os
+    onp, c_oracle = oracles
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cfg2_golden.npz"))
+    a = 0.94
+    s0 = onp.initialize_geodesics_at_camera(a, 60, 1000, -10, 10, 1024)[g["pixel"]]
+    assert np.array_equal(s0[:, :4], g["s0"][:, :4]) and np.allclose(s0, g["s0"], rtol=1e-15, atol=0)
+    cap = g["r_last"] < 100
+    assert cap.sum() == 799 and int(g["nsteps"].sum()) == 2177333 and int(g["nsteps"].max()) == 2280
+    o = c_oracle.integrate(10000, g["s0"], 40, 1e-4, a)
+    assert np.array_equal(o["nsteps"], g["nsteps"]) and np.array_equal(o["r_last"] < 100, cap)
+    err = np.abs(o["final"] - g["final"]).max(1) / np.abs(g["final"]).max(1)
+    assert err[~cap].max() < 1e-10 and np.median(err[~cap]) < 1e-14 and err[cap].max() < 1e-5

@@ -67,3 +67,20 @@ def test_cuda_cfg1_grid_against_the_reference_source(built):
     assert abs(int(nsteps.sum()) - 2079364) <= 64          # captured rays may differ by a step in the chaotic tail
     err = np.abs(final[esc] - g["final"][esc]).max(axis=1) / np.abs(g["final"][esc]).max(axis=1)
     assert np.median(err) < 1e-12 and err.max() < 1e-9, err.max()
+
+
+def test_cuda_cfg2_sublattice_against_the_reference_source(built):
+    """BASELINE config 2 settings on the every-16th-pixel sub-lattice against tests/golden/reference_cfg2_golden.npz
+    (the reference's own geodesics.py under the NumPy stand-in; 799 captured rays, 2 177 333 ray-steps): classification
+    bit-exact, step counts identical on escaped rays, end states of escaped rays within the north-star 1e-9."""
+    import os
+    from mahakala_b200 import geodesics as geo
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cfg2_golden.npz"))
+    final, nsteps, r_last = (np.asarray(q.cpu()) for q in geo.integrate_final(10000, g["s0"], 40, 1e-4, A))
+    cap_ref = g["r_last"] < 100
+    assert cap_ref.sum() == 799 and np.array_equal(r_last < 100, cap_ref)
+    esc = ~cap_ref
+    assert np.array_equal(nsteps[esc], g["nsteps"][esc])
+    assert abs(int(nsteps.sum()) - 2177333) <= 4 * 799          # captured rays: chaotic tail, a few steps either way
+    err = np.abs(final[esc] - g["final"][esc]).max(axis=1) / np.abs(g["final"][esc]).max(axis=1)
+    assert np.median(err) < 1e-12 and err.max() < 1e-9, err.max()
