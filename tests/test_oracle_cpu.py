@@ -409,3 +409,19 @@ def test_cfg2_sublattice_by_the_reference_source(oracles):
     assert np.array_equal(o["nsteps"], g["nsteps"]) and np.array_equal(o["r_last"] < 100, cap)
     err = np.abs(o["final"] - g["final"]).max(1) / np.abs(g["final"]).max(1)
     assert err[~cap].max() < 1e-10 and np.median(err[~cap]) < 1e-14 and err[cap].max() < 1e-5
+
+
+def test_image12_by_the_reference_package(oracles):
+    """A 12x12 230 GHz image by the reference's own make_image (whole package under the stand-ins) on the 32^3
+    snapshot the GPU tests use as fixture (tests/golden/make_reference_image_golden.py): the oracle agrees to 1e-12
+    per pixel (north-star: 1e-6) and 1e-13 in flux."""
+    import os
+    onp, c_oracle = oracles
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_image12_golden.npz"))["image_res12"]
+    om = oracle_model(snapshot_arrays(ncells=32, block=16, extent=16.0), 0.94)
+    img, _, _ = c_oracle.render(om, onp.initialize_geodesics_at_camera(0.94, 60, 1000, -10, 10, 12),
+                                om.get_units(M_BH, MASS_SCALE), [230e9])
+    img = img[0].reshape(12, 12)
+    err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * ref.max())
+    assert ref.max() > 1e-4 and (ref > 0).sum() > 100 and err.max() < 1e-12
+    assert abs(img.sum() - ref.sum()) / ref.sum() < 1e-13

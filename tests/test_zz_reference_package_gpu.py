@@ -84,3 +84,17 @@ def test_cuda_cfg2_sublattice_against_the_reference_source(built):
     assert abs(int(nsteps.sum()) - 2177333) <= 4 * 799          # captured rays: chaotic tail, a few steps either way
     err = np.abs(final[esc] - g["final"][esc]).max(axis=1) / np.abs(g["final"][esc]).max(axis=1)
     assert np.median(err) < 1e-12 and err.max() < 1e-9, err.max()
+
+
+def test_cuda_image12_against_the_reference_package(built):
+    """The fused and the stage-by-stage CUDA image paths against the 12x12 image produced by the reference's own
+    make_image (tests/golden/reference_image12_golden.npz): north-star tolerances, 1e-6 per pixel and 1e-8 in flux."""
+    import os
+    from helpers import snapshot_arrays
+    from mahakala_b200 import images
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_image12_golden.npz"))["image_res12"]
+    dm = device_model(snapshot_arrays(ncells=32, block=16, extent=16.0), A)
+    for img in (images.make_image(dm, resolution=12), images.make_image_unfused(dm, resolution=12)):
+        err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * ref.max())
+        assert img.shape == (12, 12) and err.max() < 1e-6 and abs(img.sum() - ref.sum()) / ref.sum() < 1e-8, err.max()
+    dm.release()
