@@ -230,8 +230,7 @@ def run_b200(args):
 
     def step_device():
         if store is not None:
-            store.reset()
-            out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)
+            out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)   # resets the store
             launches[0] += 1
             return out.total_steps
         final, nsteps, r_last, total = geo.integrate_final(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, want_total=True)
@@ -248,7 +247,6 @@ def run_b200(args):
             # public host-to-host call.  Default: zero-copy, the kernel reads s0 from pinned host memory and stores
             # the per-ray results into pinned host memory over PCIe (all bytes still move, inside the launch);
             # MK_E2E_CHUNKS > 0 selects the explicit chunked H2D / kernel / D2H pipeline instead
-            store.reset()
             if chunks > 0:
                 geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=chunks)
             else:

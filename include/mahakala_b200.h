@@ -221,6 +221,14 @@ int mk_solve_attenuated_emissivity(const double* em, const double* ab, const dou
 int mk_emission_from_states(const mk_snapshot* snap, const mk_emission_params* params, double bhspin,
                             const double* S, long n, double nu_obs, double* em, double* ab, void* stream);
 
+/* Probe of the emission code on arbitrary inputs: S (n, 8) states, prims (n, 8) primitives in canonical order dens,
+   eint, U1..3, B1..3 (no snapshot lookup) -> invariant em, ab (nfreq, n) at the HOST frequencies nu_obs[nfreq <= 8].
+   fast != 0 runs emission_fast<nfreq>, the straight-line code of the fused render kernel; fast == 0 the literal IEEE
+   chain of images.py:87-118 + athenak.py:760-794 + transfer.py:56-86.  Lets the tests hold the fused path to the
+   reference's special cases (sigma cut, Theta_e floor, X limit, Planck series switch, pitch clamp, NaN -> 0). */
+int mk_emission_probe(const mk_emission_params* params, double bhspin, const double* S, const double* prims, long n,
+                      int nfreq, const double* nu_obs, int fast, double* em, double* ab, void* stream);
+
 /* ---- fused render: images.py:30-144 make_image ------------------------------------------------ */
 /*
  * One persistent kernel: camera ray -> RK4 geodesic -> snapshot sample -> j, alpha -> intensity, all in

@@ -47,6 +47,7 @@ SIGNATURES = {
     "mk_solve_specific_intensity": "pppll" "d" "ppp",
     "mk_solve_attenuated_emissivity": "pppll" "d" "pp",
     "mk_emission_from_states": "ppdpl" "d" "ppp",
+    "mk_emission_probe": "pdppl" "ip" "i" "ppp",
     "mk_render": "dddddd" "l" "p" "ll" "dd" "pp" "i" "p" "ppppp" "lll" "pp",
     "mk_ipc_alloc": "lpp",
     "mk_ipc_open": "pp",

@@ -42,6 +42,34 @@ __global__ void fill_frozen_rows_kernel(double* S, double* dt, const double* fin
     }
 }
 
+// N == 0: the scan has no iterations (geodesics.py:272).  Every ray "ends" where it started: final = s0, no steps,
+// classifier radius = the Kerr-Schild radius of s0.
+__global__ void zero_steps_kernel(KerrSchild g, const double* __restrict__ s0, long npx, double* final_state,
+                                  int32_t* nsteps, double* r_last)
+{
+    for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < npx; p += (long)gridDim.x * blockDim.x) {
+        double s[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) s[m] = s0[p * 8 + m];
+        if (final_state)
+#pragma unroll
+            for (int m = 0; m < 8; m++) final_state[p * 8 + m] = s[m];
+        if (nsteps) nsteps[p] = 0;
+        if (r_last) r_last[p] = g.radius(s);
+    }
+}
+
+static int launch_zero_steps(double bhspin, const double* s0, long npx, double* final_state, int32_t* nsteps,
+                             double* r_last, cudaStream_t stream)
+{
+    if (npx == 0 || (!final_state && !nsteps && !r_last)) return 0;
+    KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
+    long blocks = (npx + 127) / 128, cap = (long)sm_count() * 16;
+    zero_steps_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, stream>>>(g, s0, npx, final_state, nsteps, r_last);
+    MK_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 int strict_integrate(double bhspin, long N, long npx, const double* s0, double div, double tol, double* final_state,
                      int* nsteps, double* r_last, unsigned long long* total_steps, cudaStream_t stream);
 
@@ -79,7 +107,8 @@ extern "C" int mk_integrate(int metric_id, double bhspin, long N, long npx, cons
     MK_REQUIRE((S == nullptr) == (dt == nullptr), "S and dt dump buffers must be given together");
     MK_REQUIRE(npx == 0 || s0 != nullptr, "s0 is null");
     MK_REQUIRE(div != 0.0, "div must be non-zero");
-    if (npx == 0 || N == 0) return 0;
+    if (npx == 0) return 0;
+    if (N == 0) return launch_zero_steps(bhspin, s0, npx, final_state, nsteps, r_last, stream);
     IntegrateArgs A;
     A.s0 = s0; A.npx = npx; A.N = (int)N;
     A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol;
@@ -149,7 +178,8 @@ extern "C" int mk_integrate_paged(int metric_id, double bhspin, long N, long npx
     MK_REQUIRE(max_pages > 0 && max_pages < (1L << 31), "max_pages out of range");
     MK_REQUIRE(npx == 0 || s0 != nullptr, "s0 is null");
     MK_REQUIRE(div != 0.0, "div must be non-zero");
-    if (npx == 0 || N == 0) return 0;
+    if (npx == 0) return 0;
+    if (N == 0) return launch_zero_steps(bhspin, s0, npx, final_state, nsteps, r_last, stream);   // no rows, no pages
     IntegrateArgs A;
     A.s0 = s0; A.npx = npx; A.N = (int)N;
     A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol;

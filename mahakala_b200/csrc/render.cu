@@ -89,7 +89,9 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
     for (;;) {
         // ---- next patch ----
         unsigned pq = 0;
-        if (lane == 0) pq = atomicAdd(A.queue, 1u);
+        // system scope: the counter may live in a peer GPU's memory (one queue shared by all GPUs of the node), and
+        // only system-scope atomics are guaranteed atomic across devices; one atomic per 32-ray patch either way
+        if (lane == 0) pq = atomicAdd_system(A.queue, 1u);
         pq = __shfl_sync(FULL_MASK, pq, 0);
         long patch = A.patch_begin + (long)pq * A.patch_stride;
         if (patch >= A.patch_end) break;

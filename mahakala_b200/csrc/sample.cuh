@@ -422,7 +422,9 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
     // through the arithmetic, which is harmless on the GPU).  Early exits would make the compiler duplicate
     // the copies of all loop-carried registers on every exit edge (~200 MOVs per sample in SASS).
     const double dens = prims[0], u = prims[1];
-    bool valid = (dens > 0.0) & (u > 0.0);
+    // Theta_e = (const > 0) u / dens must reach 0.3, so dens and u have the same sign; both positive in any physical
+    // snapshot, both negative (Ne < 0: negative j and alpha in the reference too) kept for input-for-input parity
+    bool valid = ((dens > 0.0) & (u > 0.0)) | ((dens < 0.0) & (u < 0.0));
     const double* U = prims + 2;
     const double* Bp = prims + 5;
     // ---- fluid frame (athenak.py:760-786) ----

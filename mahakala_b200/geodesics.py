@@ -14,6 +14,7 @@ from ._device import DeviceArray, as_device, empty, require_gpu, stream_ptr
 KERR_SCHILD = 0
 KERR_SCHILD_DUAL = 1
 KERR_SCHILD_STRICT = 2       # literal IEEE evaluation (integrate_final only), bit-identical to the CPU restatement
+PLUGIN_BASE = 16             # MK_METRIC_PLUGIN_BASE: ids of run-time registered spacetimes start here
 
 _METRICS = {"kerr_schild": KERR_SCHILD, "kerr_schild_dual": KERR_SCHILD_DUAL, "kerr_schild_strict": KERR_SCHILD_STRICT}
 _active_metric = KERR_SCHILD
@@ -69,13 +70,16 @@ def _cos_sin_deg(inclination):
 def initialize_geodesics_at_camera(bhspin, inclination, distance, fov_lower, fov_upper, pixels_per_side,
                                    camera_type='grid'):
     """geodesics.py:29-55.  Returns s0 (npx, 8) = [t, x, y, z, k^t, k^x, k^y, k^z]."""
-    if camera_type.lower() == 'grid':
+    if camera_type.lower() == 'grid' and _active_metric < PLUGIN_BASE:
+        # one kernel: image-plane geometry + nullification with the built-in Kerr-Schild metric
         n = int(pixels_per_side)
         ci, si = _cos_sin_deg(inclination)
         s0 = empty((n * n, 8))
         _cabi.call("mk_camera_grid", float(bhspin), ci, si, float(distance), float(fov_lower),
                    float(fov_upper), n, 1, s0, stream_ptr())
         return DeviceArray.wrap(s0)
+    # a user-registered spacetime is active: the wavevectors must be null in THAT metric (the reference's
+    # initial_condition takes the module-level metric, geodesics.py:225-230)
     grid = get_initial_grid(inclination, distance, fov_lower, fov_upper, pixels_per_side, camera_type)
     if grid is None:
         return None
@@ -133,7 +137,11 @@ def initial_condition(s0_x, s0_v, bhspin):
 
 
 def _camera_pixels_state(inclination, distance, radius, angle, bhspin):
-    """get_camera_pixel + initial_condition in one kernel launch."""
+    """get_camera_pixel + initial_condition in one kernel launch (built-in spacetimes; a registered spacetime goes
+    through its own initial_condition so that the rays are null in the user's metric)."""
+    if _active_metric >= PLUGIN_BASE:
+        sx, sv = get_camera_pixel(inclination, distance, radius, angle)
+        return as_device(initial_condition(sx, sv, bhspin))
     x, y = _image_points(np.asarray(radius, dtype=np.float64), np.asarray(angle, dtype=np.float64))
     ci, si = _cos_sin_deg(inclination)
     s0 = empty((x.size, 8))
@@ -248,8 +256,8 @@ def geodesic_integrator(N, s0, div, tol, bhspin):
     s = as_device(s0)
     npx = s.shape[0]
     N = int(N)
-    if npx == 0:
-        return DeviceArray.wrap(empty((min(N, 2 + N), 0, 8))), DeviceArray.wrap(empty((N, 0)))
+    if npx == 0 or N == 0:       # lax.scan over zero rays / zero iterations: empty outputs of the reference's shapes
+        return DeviceArray.wrap(empty((N, npx, 8))), DeviceArray.wrap(empty((N, npx)))
     free, _total = torch.cuda.mem_get_info()
     # typical rays take a few hundred to a few thousand steps; size the pool for min(N, 4096) rows per ray
     want_pages = 2 * (-(-npx // 32)) * (-(-(min(N, 4096) + 1) // TrajectoryStore.PAGE_SLOTS)) + 64
@@ -364,7 +372,7 @@ def integrate_paged(N, s0, div, tol, bhspin, store=None):
         store = TrajectoryStore.allocate(npx, N)
     if store.npx != npx or store.N != int(N):
         raise ValueError("TrajectoryStore was allocated for a different bundle")
-    store._host_results = None
+    store.reset()                 # a reused store starts from an empty page pool (page counter, overflow flag, total)
     _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
                store.final, store.nsteps, store.r_last, store.pages, store.page_next, store.page_first,
                store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps, stream_ptr())
@@ -403,6 +411,7 @@ def integrate_paged_host(N, s0_host, div, tol, bhspin, store, host_out):
     if (s0_host.dtype, host_out["final"].dtype, host_out["nsteps"].dtype, host_out["r_last"].dtype) != \
             (torch.float64, torch.float64, torch.int32, torch.float64):
         raise ValueError("s0 / final / r_last must be float64 and nsteps int32")
+    store.reset()
     _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s0_host, float(div), float(tol),
                host_out["final"], host_out["nsteps"], host_out["r_last"], store.pages, store.page_next,
                store.page_first, store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps, stream_ptr())
@@ -428,6 +437,7 @@ def integrate_paged_streamed(N, s0_host, div, tol, bhspin, store, host_out, chun
         raise ValueError("TrajectoryStore was allocated for a different bundle")
     if not hasattr(store, "s0_dev") or store.s0_dev.shape[0] != npx:
         store.s0_dev = torch.empty((npx, 8), dtype=torch.float64, device=dev)
+    store.reset()
     cin, c0, c1, cout = _side_streams(dev)
     cur = torch.cuda.current_stream()
     for st in (cin, c0, c1, cout):

@@ -16,8 +16,14 @@ VARIABLE_NAMES = ('dens', 'velx', 'vely', 'velz', 'eint', 'bcc1', 'bcc2', 'bcc3'
 
 
 def torus_fields(x, y, z, fluid_gamma=13. / 9, R0=8.0, R_in=2.5, p=1.5, h=0.3, u0=0.25, beta0=3.0,
-                 waves=None, amp=0.3, dens_scale=1.0):
-    """Analytic thin torus evaluated at Cartesian KS points -> (dens, velx, vely, velz, eint, b1, b2, b3)."""
+                 waves=None, amp=0.3, dens_scale=1.0, funnel=None):
+    """Analytic thin torus evaluated at Cartesian KS points -> (dens, velx, vely, velz, eint, b1, b2, b3).
+
+    ``funnel`` (dict or None) adds a magnetised polar funnel, the region real GRMHD snapshots have and the smooth
+    torus lacks: inside the cone |z| > slope * R a tenuous, hot, vertically magnetised plasma whose magnetisation
+    sigma = b^2 / dens rises from 0 at the funnel wall to ``sigma0`` on the axis, so that rays cross the
+    sigma = 100 cut of images.py:116-118 on both sides.  Keys: slope (1.2), width (0.35), dens0 (1e-2), theta_u
+    (u / dens, 0.5), sigma0 (400), index (1.5)."""
     R2 = x * x + y * y
     R = np.sqrt(R2) + 1e-12
     r = np.sqrt(R2 + z * z) + 1e-12
@@ -34,6 +40,15 @@ def torus_fields(x, y, z, fluid_gamma=13. / 9, R0=8.0, R_in=2.5, p=1.5, h=0.3, u
     b1 = -bmag * y / R
     b2 = bmag * x / R
     b3 = 0.1 * bmag
+    if funnel is not None:
+        fp = dict(slope=1.2, width=0.35, dens0=1e-2, theta_u=0.5, sigma0=400.0, index=1.5)
+        fp.update(funnel)
+        q = np.clip((np.abs(z) - fp["slope"] * R) / (fp["width"] * r), 0., 1.)
+        w = q * q * (3. - 2. * q)                       # smoothstep: 0 at the wall, 1 well inside the cone
+        dens_f = fp["dens0"] * (1. + r)**(-fp["index"])
+        dens = dens + dens_f * w
+        eint = eint + fp["theta_u"] * dens_f * w
+        b3 = b3 + np.sqrt(fp["sigma0"] * dens_f) * w * np.where(z >= 0, 1., -1.)
     if waves is not None:
         kvec, phase = waves
         G1 = np.zeros_like(x)
@@ -55,7 +70,7 @@ def torus_fields(x, y, z, fluid_gamma=13. / 9, R0=8.0, R_in=2.5, p=1.5, h=0.3, u
 
 
 def make_synthetic_snapshot(ncells=64, block=16, extent=32.0, seed=0, fluid_gamma=13. / 9, amp=0.3,
-                            dens_scale=1.0, dtype=np.float64):
+                            dens_scale=1.0, dtype=np.float64, funnel=None):
     """Single-level cube ``[-extent, extent]^3`` of ``ncells^3`` cells in ``(ncells/block)^3`` meshblocks.
 
     Returns a dict with the AthenaK arrays plus ``VariableNames`` and ``fluid_gamma``.  Fields are evaluated
@@ -80,7 +95,8 @@ def make_synthetic_snapshot(ncells=64, block=16, extent=32.0, seed=0, fluid_gamm
     x1f = np.empty((nmb, block + 1)); x2f = np.empty((nmb, block + 1)); x3f = np.empty((nmb, block + 1))
     def slab(lk, lj):
         zz, yy, xx = np.meshgrid(centres[lk], centres[lj], gx, indexing='ij')      # [k, j, I] pencil of blocks
-        fl = torus_fields(xx, yy, zz, fluid_gamma=fluid_gamma, waves=(kvec, phase), amp=amp, dens_scale=dens_scale)
+        fl = torus_fields(xx, yy, zz, fluid_gamma=fluid_gamma, waves=(kvec, phase), amp=amp, dens_scale=dens_scale,
+                          funnel=funnel)
         m0 = (lk * nb + lj) * nb
         for q in range(8):
             # (k, j, li, i) -> (li, k, j, i)

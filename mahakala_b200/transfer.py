@@ -68,3 +68,23 @@ def solve_attenuated_emissivity(emissivity, absorptivity, dt, L_unit):
     out = empty((max(nsteps - 1, 0), npx))
     _cabi.call("mk_solve_attenuated_emissivity", em, ab, d, nsteps, npx, float(L_unit), out, stream_ptr())
     return DeviceArray.wrap(out)
+
+
+def emission_probe(S, prims, bhspin, params, observing_frequencies, fast=True):
+    """Invariant (j, alpha) of arbitrary (state, primitives) pairs through the emission code of the fused render
+    kernel (``fast=True``: ``emission_fast<NF>``) or through the literal IEEE chain of images.py:87-118 +
+    athenak.py:760-794 + transfer.py:56-86 (``fast=False``).  ``S`` (n, 8), ``prims`` (n, 8) in canonical order
+    dens, eint, U1..3, B1..3; ``params`` from ``emission_params``.  Returns em, ab of shape (nfreq, n).  A test and
+    diagnosis hook: the special cases of the reference (sigma cut, Theta_e floor, X limit, NaN -> 0) can be put in
+    front of the kernel code directly instead of hoping a snapshot contains them."""
+    import numpy as np
+    s = as_device(S).contiguous()
+    p = as_device(prims).contiguous()
+    nus = np.atleast_1d(np.asarray(observing_frequencies, dtype=np.float64))
+    n = s.shape[0]
+    em = empty((nus.size, n))
+    ab = empty((nus.size, n))
+    c_nu = (ctypes.c_double * nus.size)(*nus)
+    _cabi.call("mk_emission_probe", params, float(bhspin), s, p, n, int(nus.size), c_nu, 1 if fast else 0, em, ab,
+               stream_ptr())
+    return DeviceArray.wrap(em), DeviceArray.wrap(ab)

@@ -122,6 +122,27 @@ def sample(model, S, mode="scalars", fallback_pitch_angle=np.pi / 3.):
     return {k: out[i].reshape(shape) for i, k in enumerate(names)}
 
 
+def set_sigma_cut(cut=100.):
+    """images.py:116 uses 100; other values only for what-if checks of fixtures (does the cut matter here?)."""
+    lib().orc_set_sigma_cut(ctypes.c_double(cut))
+
+
+def emission(S, prims, bhspin, fluid_gamma, r_high, units, nu_obs):
+    """athenak.py:760-794 + images.py:87-118 on arbitrary (state, primitives) pairs: S (n, 8), prims (n, 8) in file
+    order dens, velx, vely, velz, eint, bcc1..3 -> invariant em, ab (nfreq, n) and sigma (n,)."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    prims = np.ascontiguousarray(prims, dtype=np.float64)
+    nu = np.ascontiguousarray(np.atleast_1d(nu_obs), dtype=np.float64)
+    n = S.shape[0]
+    em = np.empty((nu.size, n))
+    ab = np.empty((nu.size, n))
+    sigma = np.empty(n)
+    lib().orc_emission(ctypes.c_long(n), _d(S), _d(prims), ctypes.c_double(bhspin), ctypes.c_double(fluid_gamma),
+                       ctypes.c_double(r_high), ctypes.c_double(units["Ne_unit"]), ctypes.c_double(units["B_unit"]),
+                       ctypes.c_int(nu.size), _d(nu), _d(em), _d(ab), _d(sigma))
+    return em, ab, sigma
+
+
 def render(model, s0, units, nu_obs, r_high=40., N=10000, div=40., tol=1e-4):
     """images.py:56-144 per ray -> (image (nfreq, npx), nsteps (npx,), n_in_domain)."""
     s0 = np.ascontiguousarray(s0, dtype=np.float64)

@@ -380,6 +380,8 @@ static void synchrotron(double Ne, double Theta_e, double B, double pitch, doubl
 }
 
 /* images.py:87-118 for one sample: invariant j, alpha from the 5 fluid scalars */
+static double g_sigma_cut = 100.;     /* images.py:116; orc_set_sigma_cut() exists for what-if checks of fixtures */
+
 static void sample_coefficients(const double sc[5], double fluid_gamma, double r_high, double Ne_unit,
                                 double B_unit, double nu_obs, double *em, double *ab)
 {
@@ -395,7 +397,28 @@ static void sample_coefficients(const double sc[5], double fluid_gamma, double r
     double Theta_e = t_e / (ME * CL * CL);
     double Ne = Ne_unit * dens, Bg = B_unit * b, local_nu = -kdotu * nu_obs;
     synchrotron(Ne, Theta_e, Bg, pitch, local_nu, 1, 1. / nu_obs, em, ab);
-    if (sigma > 100.) { *em = 0; *ab = 0; }      /* images.py:116-118 (NaN > 100 is false) */
+    if (sigma > g_sigma_cut) { *em = 0; *ab = 0; }      /* images.py:116-118 (NaN > 100 is false) */
+}
+
+void orc_set_sigma_cut(double cut) { g_sigma_cut = cut; }
+
+/* exported: images.py:87-118 + athenak.py:760-794 on arbitrary (state, primitives) pairs -- the IEEE chain the
+   fused kernel's fast path is held to.  S (n, 8); prims (n, 8) in file order dens, velx, vely, velz, eint, bcc1..3;
+   em, ab (nfreq, n) invariant emissivity / absorptivity; sigma (n) optional */
+int orc_emission(long n, const double *S, const double *prims, double a, double fluid_gamma, double r_high,
+                 double Ne_unit, double B_unit, int nfreq, const double *nu_obs, double *em, double *ab,
+                 double *sigma)
+{
+#pragma omp parallel for schedule(static)
+    for (long p = 0; p < n; p++) {
+        double sc[5];
+        fluid_scalars(S + p * 8, prims + p * 8, a, M_PI / 3., sc);
+        for (int fq = 0; fq < nfreq; fq++)
+            sample_coefficients(sc, fluid_gamma, r_high, Ne_unit, B_unit, nu_obs[fq], em + (size_t)fq * n + p,
+                                ab + (size_t)fq * n + p);
+        if (sigma) sigma[p] = (sc[4] * sc[4]) / sc[0];
+    }
+    return 0;
 }
 
 /* exported: S (nrows, npx, 8) -> scalars (5, nrows, npx) [dens,u,pitch,kdotu,b] or prims (8, nrows, npx) */

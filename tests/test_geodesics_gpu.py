@@ -369,6 +369,53 @@ def test_user_registered_metrics(ma):
         geo.set_metric("kerr_schild")
 
 
+def test_camera_rays_are_null_in_the_registered_spacetime(ma):
+    """initialize_geodesics_at_camera / select_photons_integrator with a user-registered spacetime selected: the
+    wavevectors must be null in THAT metric (the reference's initial_condition uses the module-level metric,
+    geodesics.py:225-230).  Schwarzschild of mass M = 3 in Kerr-Schild coordinates is far enough from the built-in
+    Kerr metric that rays nullified with the wrong one miss g(k, k) = 0 by 4e-3; and its shadow radius for M = 1.5,
+    sqrt(27) M, comes out of find_shadow_bisection_angles at any inclination."""
+    from mahakala_b200 import geodesics as geo
+    from test_host_cpu import SCHWARZSCHILD_KS
+    geo.register_metric("schw_m3", SCHWARZSCHILD_KS, params=[3.0])
+    geo.register_metric("schw_m15", SCHWARZSCHILD_KS, params=[1.5])
+
+    def nullness(s0):
+        s0 = np.asarray(s0)
+        g = np.asarray(geo.metric(s0[:, :4], 0.9))            # the ACTIVE (plugin) metric
+        return np.abs(np.einsum('ai,aij,aj->a', s0[:, 4:], g, s0[:, 4:])).max()
+
+    try:
+        wrong = np.asarray(ma.initialize_geodesics_at_camera(0.9, 60, 1000, -10, 10, 8))      # built-in Kerr, a = 0.9
+        geo.set_metric("schw_m3")
+        assert nullness(wrong) > 1e-3                         # the check discriminates
+        s0 = ma.initialize_geodesics_at_camera(0.9, 60, 1000, -10, 10, 8)
+        assert np.asarray(s0).shape == (64, 8) and nullness(s0) < 1e-13
+        assert np.array_equal(np.asarray(s0)[:, :5], wrong[:, :5])          # same positions, same k^t = 1
+        pts = geo._camera_pixels_state(60, 1000, np.array([4.0, 6.0, 9.0]), np.array([0.3, 2.0, 4.0]), 0.9)
+        assert nullness(pts.cpu()) < 1e-13
+        eq = ma.initialize_geodesics_at_camera(0.9, 60, 1000, -10, 10, 8, camera_type='Equator')
+        assert nullness(eq) < 1e-13
+        geo.set_metric("schw_m15")
+        radii = np.asarray(ma.find_shadow_bisection_angles(0.0, 40, np.linspace(0, 2 * np.pi, 9)[:-1]))
+        assert np.allclose(radii, np.sqrt(27.) * 1.5, rtol=3e-3), radii
+    finally:
+        geo.set_metric("kerr_schild")
+    # zero iterations: outputs of the reference's shapes, per-ray results defined (ADVICE r1)
+    s0 = ma.initialize_geodesics_at_camera(0.9, 60, 1000, -10, 10, 4)
+    S, dt = ma.geodesic_integrator(0, s0, 40, 1e-4, 0.9)
+    assert np.asarray(S).shape == (0, 16, 8) and np.asarray(dt).shape == (0, 16)
+    f, n, rl = geo.integrate_final(0, s0, 40, 1e-4, 0.9)
+    assert np.array_equal(np.asarray(f.cpu()), np.asarray(s0)) and not np.asarray(n.cpu()).any()
+    assert np.allclose(np.asarray(rl.cpu()), np.asarray(ma.radius_cal(s0, 0.9)), rtol=1e-14)
+    # a reused TrajectoryStore starts from an empty pool on every call (ADVICE r1)
+    st = geo.TrajectoryStore.allocate(16, 2000)
+    geo.integrate_paged(2000, s0, 40, 1e-2, 0.9, store=st)
+    used, total = st.pages_used, int(st.total_steps.item())
+    geo.integrate_paged(2000, s0, 40, 1e-2, 0.9, store=st)
+    assert st.pages_used == used and int(st.total_steps.item()) == total and not st.overflowed
+
+
 def test_classification_sweep_spins_and_inclinations(ma):
     """Shadow classification (captured vs escaped) is bit-exact against the oracle across spins, inclinations,
     fields of view and both tolerance settings used by the reference (1e-2 shadow finder, 1e-4 imaging)."""

@@ -425,3 +425,78 @@ def test_image12_by_the_reference_package(oracles):
     err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * ref.max())
     assert ref.max() > 1e-4 and (ref > 0).sum() > 100 and err.max() < 1e-12
     assert abs(img.sum() - ref.sum()) / ref.sum() < 1e-13
+
+
+def _funnel_case(onp, c_oracle):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_funnel_golden.npz"))
+    om = oracle_model(snapshot_arrays(ncells=32, block=16, extent=16.0, funnel={}), 0.94)
+    s0 = onp.initialize_geodesics_at_camera(0.94, 60, 1000, -10, 10, 10)
+    return z, om, s0
+
+
+def test_funnel_image_by_the_reference_package(oracles):
+    """The sigma > 100 cut of images.py:116-118 FIRES here: a 10x10 image by the reference's own make_image on the 32^3
+    fixture snapshot with a magnetised polar funnel (tests/golden/make_reference_funnel_golden.py).  By the reference's
+    own geodesic_integrator + get_fluid_scalars_from_geodesics 2557 of its 21721 in-domain samples have sigma > 100
+    (the smooth torus of the other fixtures peaks at 0.72).  The oracle reproduces the image to 1e-12 and both counts
+    exactly; with the cut disabled its image changes by up to 14x on 42 pixels, so agreement pins the cut."""
+    onp, c_oracle = oracles
+    z, om, s0 = _funnel_case(onp, c_oracle)
+    ref = z["image_res10"]
+    assert int(z["sigma_gt_100"]) == 2557 and int(z["in_domain"]) == 21721 and float(z["sigma_max"]) > 600
+    units = om.get_units(M_BH, MASS_SCALE)
+    img = c_oracle.render(om, s0, units, [230e9])[0][0].reshape(10, 10)
+    err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-6 * ref.max())
+    assert err.max() < 1e-12 and abs(img.sum() - ref.sum()) / ref.sum() < 1e-13
+    S, dt = c_oracle.geodesic_integrator(10000, s0, 40, 1e-4, 0.94)
+    fs = c_oracle.sample(om, S)
+    moving = np.zeros(dt.shape, dtype=bool)
+    moving[1:] = dt[:-1] != 0
+    m = moving & (fs["dens"] > 0)
+    with np.errstate(all='ignore'):
+        sigma = fs["b"]**2 / fs["dens"]
+    assert int(m.sum()) == int(z["in_domain"]) and int((sigma[m] > 100.).sum()) == int(z["sigma_gt_100"])
+    try:
+        c_oracle.set_sigma_cut(1e300)
+        nocut = c_oracle.render(om, s0, units, [230e9])[0][0].reshape(10, 10)
+    finally:
+        c_oracle.set_sigma_cut(100.)
+    changed = np.abs(nocut - ref) / np.maximum(np.abs(ref), 1e-6 * ref.max())
+    assert (changed > 1e-3).sum() >= 30 and changed.max() > 5
+
+
+def test_c_oracle_emission_matches_numpy_chain(oracles):
+    """orc_emission (the checker of the GPU emission probe, tests/test_emission_gpu.py) against the NumPy restatement
+    of athenak.py:760-794 + images.py:87-118 + transfer.py:56-86 on funnel trajectories: zero pattern exact (cut, cold,
+    out-of-domain samples), values within the conditioning of exp(-X^(1/3)) and sin(arccos c)."""
+    onp, c_oracle = oracles
+    z, om, s0 = _funnel_case(onp, c_oracle)
+    S, dt = c_oracle.geodesic_integrator(10000, s0, 40, 1e-4, 0.94)
+    pts = S[::3].reshape(-1, 8)
+    pr = c_oracle.sample(om, pts, mode="prims")
+    p_ref = np.stack([pr[k] for k in ("dens", "U1", "U2", "U3", "u", "B1", "B2", "B3")], axis=1)
+    units = om.get_units(M_BH, MASS_SCALE)
+    em_c, ab_c, sigma_c = c_oracle.emission(pts, p_ref, 0.94, om.fluid_gamma, 40., units, [230e9, 690e9])
+    sc = onp.fluid_frame_scalars(pts, p_ref, 0.94)
+    with np.errstate(all='ignore'):
+        bsq = sc[:, 4]**2
+        sigma = bsq / sc[:, 0]
+        th = onp.rlow_rhigh_model(sc[:, 0], sc[:, 1], sc[:, 1] * (om.fluid_gamma - 1.) / bsq / 0.5, r_high=40.)
+        for f, nu in enumerate((230e9, 690e9)):
+            em, ab = onp.synchrotron_coefficients(units["Ne_unit"] * sc[:, 0], th, units["B_unit"] * sc[:, 4], sc[:, 2],
+                                                  -sc[:, 3] * nu, invariant=True, rescale_nu=1. / nu)
+            em = np.where(sigma > 100., 0.0, em)
+            ab = np.where(sigma > 100., 0.0, ab)
+            assert np.array_equal(em == 0, em_c[f] == 0) and np.array_equal(ab == 0, ab_c[f] == 0)
+            nz = em != 0
+            assert nz.sum() > 1000 and (sigma[pr["dens"] > 0] > 100).sum() > 100
+            # condition number of j w.r.t. rounding of its inputs: exp(-X^(1/3)) and sin(arccos c), c -> +-1
+            from mahakala_b200 import constants as K
+            nus = (2. / 9.) * K.EE * units["B_unit"] * sc[:, 4] / (2 * np.pi * K.ME * K.CL) * th**2 * np.sin(sc[:, 2])
+            kappa = ((1 + np.cbrt(-sc[:, 3] * nu / nus) / 3) / np.sin(sc[:, 2])**2)[nz]
+            e_em, e_ab = np.abs(em_c[f][nz] / em[nz] - 1), np.abs(ab_c[f][nz] / ab[nz] - 1)
+            assert (e_em < 2e-14 * kappa).all() and (e_ab < 2e-14 * kappa + 2e-13).all()
+            assert e_em[kappa < 50].max() < 1e-12 and (kappa < 50).sum() > 1000
+    ok = pr["dens"] > 0
+    assert np.allclose(sigma_c[ok], sigma[ok], rtol=1e-13)
