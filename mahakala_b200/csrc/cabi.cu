@@ -207,7 +207,7 @@ extern "C" int mk_radius_cal(double bhspin, const double* x, long n, long stride
 {
     if (n <= 0) return 0;
     MK_REQUIRE(x && r, "null pointer");
-    KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 0;
+    KerrSchild g; g.set_spin(bhspin);
     radius_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, x, n, stride, r);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -219,7 +219,7 @@ extern "C" int mk_rhs(int metric_id, double bhspin, const double* state, long n,
     MK_REQUIRE(state && out, "null pointer");
     unsigned blocks = (unsigned)((n + 127) / 128);
     if (metric_id == MK_METRIC_KERR_SCHILD) {
-        KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 0;
+        KerrSchild g; g.set_spin(bhspin);
         rhs_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(g, state, n, out);
     } else if (metric_id == MK_METRIC_KERR_SCHILD_DUAL) {
         DualMetric<KerrSchildFn> g; g.fn.a = bhspin; g.rH = 0;
@@ -237,7 +237,7 @@ extern "C" int mk_rhs(int metric_id, double bhspin, const double* state, long n,
 
 #define MK_DISPATCH_METRIC(metric_id, bhspin, CALL)                                                   \
     if (metric_id == MK_METRIC_KERR_SCHILD) {                                                          \
-        KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);  \
+        KerrSchild g; g.set_spin(bhspin);  \
         CALL;                                                                                          \
     } else if (metric_id == MK_METRIC_KERR_SCHILD_DUAL) {                                              \
         DualMetric<KerrSchildFn> g; g.fn.a = bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);         \

@@ -49,7 +49,7 @@ __global__ void initial_condition_kernel(KerrSchild g, const double* s0_x, const
 
 static KerrSchild make_ks(double a)
 {
-    KerrSchild g; g.a = a; g.aa = a * a; g.rH = 1.0 + sqrt(1.0 - a * a);
+    KerrSchild g; g.set_spin(a);
     return g;
 }
 

@@ -11,27 +11,95 @@
 #include <cuda_runtime.h>
 #endif
 
+// Every arithmetic helper of the ray kernels is __host__ __device__: the product only ever calls them on the device,
+// but tests/host_harness compiles the SAME source for the host so that the CPU test suite (no GPU in the build
+// container) can hold the kernels' arithmetic -- closed-form acceleration, RK4 step, step rule, emission chain -- to
+// the CPU restatement of the reference.  On the host the MUFU seeds are replaced by library values truncated to 22 mantissa bits (the hardware's
+// seeds are good to 2^-22..2^-23), so the Newton steps are exercised rather than bypassed.
+#define MK_HD __host__ __device__ __forceinline__
+
+#ifndef __CUDA_ARCH__
+#ifndef __CUDACC_RTC__
+#include <cmath>
+#include <cstring>
+#endif
+#endif
+
 namespace mk {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
-__device__ __forceinline__ double rcp_seed(double x)
+#ifndef __CUDA_ARCH__
+static inline double host_truncate_seed(double y)
 {
+    unsigned long long b;
+    std::memcpy(&b, &y, 8);
+    b &= ~((1ULL << 30) - 1ULL);          // keep 22 mantissa bits
+    std::memcpy(&y, &b, 8);
+    return y;
+}
+#endif
+
+MK_HD double rcp_seed(double x)
+{
+#ifdef __CUDA_ARCH__
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
+#else
+    return host_truncate_seed(1.0 / x);
+#endif
 }
 
-__device__ __forceinline__ double rsqrt_seed(double x)
+MK_HD double rsqrt_seed(double x)
 {
+#ifdef __CUDA_ARCH__
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     return y;
+#else
+    return host_truncate_seed(1.0 / std::sqrt(x));
+#endif
+}
+
+// bit-level helpers with host twins (the device intrinsics do not exist on the host)
+MK_HD int hi_word(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32);
+#endif
+}
+MK_HD int lo_word(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    long long b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffffLL);
+#endif
+}
+MK_HD int floor_to_int(double x)         // round towards minus infinity; NaN -> 0 (cvt.rmi.s32.f64)
+{
+#ifdef __CUDA_ARCH__
+    return __double2int_rd(x);
+#else
+    return (x != x) ? 0 : (int)std::floor(x);
+#endif
+}
+MK_HD double from_words(int hi, int lo)
+{
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, lo);
+#else
+    unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+    double x; std::memcpy(&x, &b, 8); return x;
+#endif
 }
 
 // 1/x to ~1 ulp: MUFU seed (relative error e0 <= ~2^-20) + one cubically convergent step
 //   y1 = y0 (1 + e + e^2),  e = 1 - x y0      ->  error e0^3 <= 2^-60          (3 DFMA)
-__device__ __forceinline__ double fast_rcp(double x)
+MK_HD double fast_rcp(double x)
 {
     double y = rcp_seed(x);
     double e = fma(-x, y, 1.0);
@@ -41,7 +109,7 @@ __device__ __forceinline__ double fast_rcp(double x)
 // sqrt(x) and 1/sqrt(x) together: MUFU seed + one cubically convergent step for the reciprocal root
 //   y1 = y0 (1 + e/2 + 3 e^2/8),  e = 1 - x y0^2                                  (5 FP64 ops)
 // then s = x y1 with one residual correction s += (x - s^2) y1/2                   (4 FP64 ops)
-__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs)
+MK_HD void fast_sqrt_rsqrt(double x, double& s, double& rs)
 {
     double y = rsqrt_seed(x);
     double e = fma(-(x * y), y, 1.0);
@@ -53,7 +121,7 @@ __device__ __forceinline__ void fast_sqrt_rsqrt(double x, double& s, double& rs)
     rs = y;
 }
 
-__device__ __forceinline__ double fast_sqrt(double x)
+MK_HD double fast_sqrt(double x)
 {
     double s, rs;
     fast_sqrt_rsqrt(x, s, rs);
@@ -62,7 +130,7 @@ __device__ __forceinline__ double fast_sqrt(double x)
 
 // The same without the final residual correction: sqrt(x) = x * rsqrt(x) to <= ~3 ulp in 6 FP64 ops.  Used
 // inside the geodesic right-hand side, whose inputs already carry the rounding of the previous stage.
-__device__ __forceinline__ void quick_sqrt_rsqrt(double x, double& s, double& rs)
+MK_HD void quick_sqrt_rsqrt(double x, double& s, double& rs)
 {
     double y = rsqrt_seed(x);
     double e = fma(-(x * y), y, 1.0);
@@ -72,15 +140,38 @@ __device__ __forceinline__ void quick_sqrt_rsqrt(double x, double& s, double& rs
     rs = y;
 }
 
-__device__ __forceinline__ double quick_sqrt(double x)
+MK_HD double quick_sqrt(double x)
 {
     double s, rs;
     quick_sqrt_rsqrt(x, s, rs);
     return s;
 }
 
+// Same accuracy class with the correction applied to both results independently:
+//   g = x y0,  c = (1/2 + 3 e / 8) e,  sqrt = g + g c,  rsqrt = y0 + y0 c
+// 6 FP64 operations for the pair, 5 for the square root alone, and the square root does not wait for the refined
+// reciprocal root (one dependent operation less on the critical path of the geodesic right-hand side).
+MK_HD void pair_sqrt_rsqrt(double x, double& s, double& rs)
+{
+    double y = rsqrt_seed(x);
+    double g = x * y;
+    double e = fma(-g, y, 1.0);
+    double c = fma(0.375, e, 0.5) * e;
+    s = fma(g, c, g);
+    rs = fma(y, c, y);
+}
+
+MK_HD double sqrt_only(double x)
+{
+    double y = rsqrt_seed(x);
+    double g = x * y;
+    double e = fma(-g, y, 1.0);
+    double c = fma(0.375, e, 0.5) * e;
+    return fma(g, c, g);
+}
+
 // a / b with b's reciprocal refined and one residual correction (≈ correctly rounded).
-__device__ __forceinline__ double fast_div(double a, double b)
+MK_HD double fast_div(double a, double b)
 {
     double y = fast_rcp(b);
     double q = a * y;
@@ -92,11 +183,11 @@ __device__ __forceinline__ double fast_div(double a, double b)
 // trick, r = -t - k ln 2 in two FMAs (|r| <= 0.347), degree-13 Taylor polynomial (truncation 4e-18), 2^k by an
 // integer add to the exponent field: 17 FP64 + 4 integer instructions against ~53 for exp().  <= ~1 ulp for
 // t <= 707; beyond (result < 9e-308, where exp() would return subnormals) the result is flushed to 0.  NaN -> NaN.
-__device__ __forceinline__ double fast_exp_neg(double t)
+MK_HD double fast_exp_neg(double t)
 {
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52
     double kd = fma(-t, 1.4426950408889634, MAGIC);
-    int k = __double2loint(kd);
+    int k = lo_word(kd);
     double kf = kd - MAGIC;
     double r = fma(-kf, 6.93147180369123816490e-01, -t);     // ln2 split hi / lo (fdlibm)
     r = fma(-kf, 1.90821492927058770002e-10, r);
@@ -114,7 +205,7 @@ __device__ __forceinline__ double fast_exp_neg(double t)
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double y = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    double y = from_words(hi_word(p) + (k << 20), lo_word(p));
     return (t > 707.0) ? 0.0 : y;
 }
 
@@ -122,11 +213,16 @@ __device__ __forceinline__ double fast_exp_neg(double t)
 // MUFU pair lg2 / ex2 (relative error <~ 5e-6 over 1e-30 < x < 1e30), one quartically convergent FMA-only step
 //   r1 = r0 (1 + e/3 + 2 e^2/9 + 14 e^3/81),  e = 1 - x r0^3      (truncation 35 e^4 / 243 < 1e-19)
 // and cbrt(x) = x r1^2: ~15 instructions against ~40 for cbrt(); <= ~4 ulp.  Returns x^(1/3); rinv = x^(-1/3).
-__device__ __forceinline__ double fast_cbrt_pos(double x, double& rinv)
+MK_HD double fast_cbrt_pos(double x, double& rinv)
 {
     float xf = (float)x, lg, r0f;
+#ifdef __CUDA_ARCH__
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r0f) : "f"(lg * -0.33333334f));
+#else
+    lg = std::log2(xf);
+    r0f = std::exp2(lg * -0.33333334f);
+#endif
     double r0 = (double)r0f;
     double r2 = r0 * r0;
     double e = fma(-x * r0, r2, 1.0);

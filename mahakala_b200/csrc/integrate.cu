@@ -63,7 +63,7 @@ static int launch_zero_steps(double bhspin, const double* s0, long npx, double* 
                              double* r_last, cudaStream_t stream)
 {
     if (npx == 0 || (!final_state && !nsteps && !r_last)) return 0;
-    KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
+    KerrSchild g; g.set_spin(bhspin);
     long blocks = (npx + 127) / 128, cap = (long)sm_count() * 16;
     zero_steps_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, stream>>>(g, s0, npx, final_state, nsteps, r_last);
     MK_CUDA_CHECK(cudaGetLastError());
@@ -126,7 +126,7 @@ static int dispatch_integrate(int metric_id, double bhspin, IntegrateArgs& A, cu
 {
     int rc;
     if (metric_id == MK_METRIC_KERR_SCHILD) {
-        KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
+        KerrSchild g; g.set_spin(bhspin);
         A.rule.rH = g.rH;
         rc = launch_integrate(g, A, stream);
     } else if (metric_id == MK_METRIC_KERR_SCHILD_DUAL) {

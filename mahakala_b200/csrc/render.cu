@@ -80,7 +80,7 @@ struct RenderArgs {
 #else
 #define MK_RENDER_BOUNDS __launch_bounds__(MK_RENDER_THREADS, (NF >= MK_RENDER_SPLIT) ? MK_RENDER_HI : MK_RENDER_LO)
 #endif
-template <int NF>
+template <int NF, int KIND>
 __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -157,7 +157,7 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
                     const double dt_used = dt;
                     double prims[8];
                     double dtn;
-                    if (pending && interp_prims(A.sn, s, prims)) {
+                    if (pending && interp_prims_kind<KIND>(A.sn, s, prims)) {
                         my_samples++;
                         double f, l[4], em[NF], ab[NF];
                         l[0] = 1.0;
@@ -202,7 +202,7 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
                             active = false;         // row N is not part of the reference's scan output
                         } else {
                             double prims[8];
-                            if (interp_prims(A.sn, s, prims)) {
+                            if (interp_prims_kind<KIND>(A.sn, s, prims)) {
                                 my_samples++;
                                 double f, l[4];
                                 l[0] = 1.0;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(128, 3) render_refill_kernel(const RenderArgs 
         }
         if (ray < 0) continue;
         double cand[8], prims[8], dtn;
-        if (pending && interp_prims(A.sn, s, prims)) {
+        if (pending && interp_prims_kind<KIND>(A.sn, s, prims)) {
             double f, l[4], em[1], ab[1];
             l[0] = 1.0;
             A.g.fl(s, cache, f, l[1], l[2], l[3]);
@@ -326,8 +326,21 @@ __global__ void __launch_bounds__(128, 3) render_refill_kernel(const RenderArgs 
 
 #endif  // MK_EXPERIMENTS
 
+template <int NF, int KIND>
+static int launch_render_kind(const RenderArgs& A, long npatches, cudaStream_t stream);
+
 template <int NF>
 static int launch_render(const RenderArgs& A, long npatches, cudaStream_t stream)
+{
+    switch (snapshot_kind(A.sn)) {
+        case SNAP_F64_GRID_POW2: return launch_render_kind<NF, SNAP_F64_GRID_POW2>(A, npatches, stream);
+        case SNAP_F32_GRID_POW2: return launch_render_kind<NF, SNAP_F32_GRID_POW2>(A, npatches, stream);
+        default: return launch_render_kind<NF, SNAP_GENERIC>(A, npatches, stream);
+    }
+}
+
+template <int NF, int KIND>
+static int launch_render_kind(const RenderArgs& A, long npatches, cudaStream_t stream)
 {
 #ifdef MK_EXPERIMENTS
     if (NF == 1 && !A.s0) {
@@ -342,14 +355,14 @@ static int launch_render(const RenderArgs& A, long npatches, cudaStream_t stream
     }
 #endif
     int per_sm = 0;
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF>, MK_RENDER_THREADS, 0));
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF, KIND>, MK_RENDER_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
     long blocks = (long)sm_count() * per_sm;
     const long warps = MK_RENDER_THREADS / 32;
     long need = (npatches + warps - 1) / warps;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    render_kernel<NF><<<(unsigned)blocks, MK_RENDER_THREADS, 0, stream>>>(A);
+    render_kernel<NF, KIND><<<(unsigned)blocks, MK_RENDER_THREADS, 0, stream>>>(A);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -379,7 +392,7 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
     if (!s0) { MK_REQUIRE(res >= 0 && npx == res * res, "npx must equal res*res for the grid camera"); }
     if (npx == 0) return 0;
     RenderArgs A;
-    A.g.a = bhspin; A.g.aa = bhspin * bhspin; A.g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
+    A.g.set_spin(bhspin);
     A.cam.ci = cos_i; A.cam.si = sin_i; A.cam.d = distance;
     A.fov_lo = fov_lower;
     A.step = res > 0 ? (fov_upper - fov_lower) / (double)(2 * res) : 0.0;

@@ -216,6 +216,27 @@ __global__ void sample_prims_kernel(SnapshotView sn, const double* __restrict__ 
     }
 }
 
+// caller's (nmb, 12) geometry records -> internal (nmb, 16) records with 1/dx; *not_pow2 is raised when some cell
+// size is not a power of two (then 1/dx is inexact and cell_index keeps the corrected division)
+__global__ void geom_expand_kernel(const double* __restrict__ g12, double* __restrict__ g16, long nmb, int* not_pow2)
+{
+    long mb = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (mb >= nmb) return;
+    const double* s = g12 + mb * 12;
+    double* d = g16 + mb * GEOM_DOUBLES;
+    for (int i = 0; i < 12; i++) d[i] = s[i];
+    bool bad = false;
+    for (int a = 0; a < 3; a++) {
+        double dx = s[9 + a];
+        d[12 + a] = 1.0 / dx;
+        unsigned long long bits = (unsigned long long)__double_as_longlong(dx);
+        unsigned expo = (unsigned)((bits >> 52) & 0x7ffu);
+        bad |= !(dx > 0.0) || (bits & ((1ULL << 52) - 1ULL)) != 0 || expo < 64 || expo > 1983;
+    }
+    d[15] = 0.0;
+    if (bad) atomicOr(not_pow2, 1);
+}
+
 static unsigned grid_for(long n, int threads)
 {
     long blocks = (n + threads - 1) / threads;
@@ -241,7 +262,7 @@ static int snapshot_alloc(long nmb, long nk, long nj, long ni, const double* geo
     cudaGetDevice(&s->device);
     long cpb = (nk + 2) * (nj + 2) * (ni + 2);
     s->cell_bytes = nmb * cpb * 8 * (store_f32 ? 4 : 8);
-    long geom_bytes = 12 * nmb * (long)sizeof(double);
+    long geom_bytes = GEOM_DOUBLES * nmb * (long)sizeof(double);
     long grid_bytes = grid ? (long)gn[0] * gn[1] * gn[2] * (long)sizeof(int) : 0;
     s->total_bytes = s->cell_bytes + geom_bytes + grid_bytes;
     cudaError_t e = cudaMalloc(&s->cells, s->cell_bytes);
@@ -252,9 +273,20 @@ static int snapshot_alloc(long nmb, long nk, long nj, long ni, const double* geo
         mk_snapshot_destroy(s);
         return 1;
     }
-    cudaMemcpyAsync(s->geom, geom, geom_bytes, cudaMemcpyDeviceToDevice, stream);
+    int* flag = (int*)queue_counter(stream, 2);       // zeroed device word
+    if (!flag) { mk_snapshot_destroy(s); return 1; }
+    geom_expand_kernel<<<(unsigned)((nmb + 127) / 128), 128, 0, stream>>>(geom, s->geom, nmb, flag);
+    int not_pow2 = 1;
+    e = cudaMemcpyAsync(&not_pow2, flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error("snapshot geometry set-up failed: %s", cudaGetErrorString(e));
+        mk_snapshot_destroy(s);
+        return 1;
+    }
     if (grid) cudaMemcpyAsync(s->grid, grid, grid_bytes, cudaMemcpyDeviceToDevice, stream);
     SnapshotView& v = s->view;
+    v.dx_pow2 = not_pow2 ? 0 : 1;
     v.source = 0;
     v.cells = s->cells; v.is_f32 = store_f32 ? 1 : 0;
     v.nmb = (int)nmb; v.nk = (int)nk; v.nj = (int)nj; v.ni = (int)ni;
@@ -467,7 +499,7 @@ extern "C" int mk_sample_scalars(const mk_snapshot* snap, double bhspin, const d
 {
     if (n <= 0) return 0;
     MK_REQUIRE(snap && S && out, "null pointer");
-    KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 0;
+    KerrSchild g; g.set_spin(bhspin);
     sample_scalars_kernel<<<grid_for(n, 128), 128, 0, (cudaStream_t)stream>>>(snap->view, g, S, n, cos(fallback_pitch_angle), out);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;

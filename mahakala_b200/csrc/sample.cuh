@@ -33,9 +33,12 @@ struct SnapshotView {
     int is_f32;
     int nmb, nk, nj, ni;      // interior cells per block
     long sj, sk, sb;          // element strides of the padded cell array: next j row, next k plane, next block
-    // per-block geometry (nmb, 12): lo[3], hi[3] face extents, v0[3] first cell centre, dx[3] cell size;
-    // one 96 B record per block so that a lookup costs one round of 256-bit loads instead of 12 dependent ones
+    // per-block geometry (nmb, 16): lo[3], hi[3] face extents, v0[3] first cell centre, dx[3] cell size, 1/dx[3],
+    // pad; one 128 B record per block so that a lookup costs one round of 256-bit loads instead of dependent ones
     const double* geom;
+    // every cell size of the mesh is a power of two (AthenaK meshes on power-of-two domains): 1/dx is exact, so
+    // xi * (1/dx) IS xi / dx and the floor division of athenak.py:718-733 needs neither a division nor a fix-up
+    int dx_pow2;
     // block lookup grid over the bounding box (regular meshes); grid == nullptr -> linear scan
     const int* grid;
     int gn[3];
@@ -43,34 +46,125 @@ struct SnapshotView {
     double bbox_lo[3], bbox_hi[3];
 };
 
+constexpr int GEOM_DOUBLES = 16;
+
 struct BlockGeom {
     double lo[3], hi[3], v0[3], dx[3];
 };
 
-__device__ __forceinline__ BlockGeom load_geom(const SnapshotView& sn, int mb)
+MK_HD BlockGeom load_geom(const SnapshotView& sn, int mb)
 {
-    const double* p = sn.geom + (long)mb * 12;
+    const double* p = sn.geom + (long)mb * GEOM_DOUBLES;
     double v[12];
+#ifdef __CUDA_ARCH__
 #pragma unroll
     for (int i = 0; i < 3; i++)
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
             : "=d"(v[4 * i]), "=d"(v[4 * i + 1]), "=d"(v[4 * i + 2]), "=d"(v[4 * i + 3]) : "l"(p + 4 * i));
+#else
+    for (int i = 0; i < 12; i++) v[i] = p[i];
+#endif
     BlockGeom g;
 #pragma unroll
     for (int d = 0; d < 3; d++) { g.lo[d] = v[d]; g.hi[d] = v[3 + d]; g.v0[d] = v[6 + d]; g.dx[d] = v[9 + d]; }
     return g;
 }
 
+// 1/dx of the block: the last 32 B of its 128 B record (same line as load_geom just touched), fetched where it is
+// needed so that it does not lengthen the live range of the record
+MK_HD void load_inv_dx(const SnapshotView& sn, int mb, double inv[3])
+{
+    const double* p = sn.geom + (long)mb * GEOM_DOUBLES + 12;
+#ifdef __CUDA_ARCH__
+    double pad;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(inv[0]), "=d"(inv[1]), "=d"(inv[2]), "=d"(pad) : "l"(p));
+#else
+    for (int i = 0; i < 3; i++) inv[i] = p[i];
+#endif
+}
+
 // left-open / right-closed membership (athenak.py:666-668), branch-free
-__device__ __forceinline__ bool in_block(const BlockGeom& g, const double x[4])
+MK_HD bool in_block(const BlockGeom& g, const double x[4])
 {
     return (g.lo[0] < x[1]) & (x[1] <= g.hi[0]) & (g.lo[1] < x[2]) & (x[2] <= g.hi[1]) & (g.lo[2] < x[3]) &
            (x[3] <= g.hi[2]);
 }
 
+// Rare continuation of the grid lookup, kept OUT OF LINE so that the fused kernel's hot loop does not carry its code:
+// a point within rounding distance of a face may land in the neighbouring grid cell -> fix up with the exact extents
+// (x <= lo -> step down, x > hi -> step up), at most one step per axis; then, as a last resort (holes in the mesh,
+// degenerate geometry), the exhaustive 3x3x3 neighbourhood.
+// (All arguments by value: taking the address of the kernel-parameter SnapshotView would force a stack copy of it.)
+#ifdef __CUDA_ARCH__
+static __device__ __noinline__
+#else
+static inline
+#endif
+int locate_block_slow(const int* grid, const double* geom, int gn0, int gn1, int gn2, double x1, double x2, double x3,
+                      int c0, int c1, int c2, int mb)
+{
+    if (!((x1 == x1) & (x2 == x2) & (x3 == x3))) return -1;          // NaN position: outside
+    SnapshotView sn;
+    sn.geom = geom;
+    const double x[4] = {0.0, x1, x2, x3};
+    const int c[3] = {c0, c1, c2}, gn[3] = {gn0, gn1, gn2};
+    int c2v[3];
+    BlockGeom geo;
+    if (mb >= 0) geo = load_geom(sn, mb);
+    for (int d = 0; d < 3; d++) {
+        int s = 0;
+        if (mb >= 0) s = (x[d + 1] <= geo.lo[d]) ? -1 : ((x[d + 1] > geo.hi[d]) ? 1 : 0);
+        c2v[d] = min(max(c[d] + s, 0), gn[d] - 1);
+    }
+    int mb2 = grid[(c2v[2] * gn1 + c2v[1]) * gn0 + c2v[0]];
+    if (mb2 >= 0) {
+        geo = load_geom(sn, mb2);
+        if (in_block(geo, x)) return mb2;
+    }
+    for (int dk = -1; dk <= 1; dk++)
+        for (int dj = -1; dj <= 1; dj++)
+            for (int di = -1; di <= 1; di++) {
+                int a = c0 + di, b = c1 + dj, e = c2 + dk;
+                if (a < 0 || b < 0 || e < 0 || a >= gn0 || b >= gn1 || e >= gn2) continue;
+                int m = grid[(e * gn1 + b) * gn0 + a];
+                if (m < 0) continue;
+                geo = load_geom(sn, m);
+                if (in_block(geo, x)) return m;
+            }
+    return -1;
+}
+
+// Grid lookup (regular meshes): O(1) replacement of the reference's mask loop over meshblocks, athenak.py:663-670.
+// Grid cell of the point.  The range test on the integer cell index doubles as the bounding-box rejection:
+// x below the lower domain face gives a negative quotient (x - g0 is negative exactly when x < g0), x above
+// the upper face gives q >= gn.  q == gn is the one ambiguous value (x on the upper face, which is inside --
+// right-closed extents -- or just beyond it), so only there the exact face is consulted.  NaN converts to 0
+// and fails the exact membership test below.  Whatever passes is decided by in_block() on the stored faces.
+MK_HD int locate_block_grid(const SnapshotView& sn, const double x[4], BlockGeom& geo)
+{
+    int c[3];
+    bool maybe = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        int q = floor_to_int((x[d + 1] - sn.g0[d]) * sn.ginv[d]);
+        if (q == sn.gn[d]) q = (x[d + 1] <= sn.bbox_hi[d]) ? q - 1 : q;
+        maybe &= ((unsigned)q < (unsigned)sn.gn[d]);
+        c[d] = q;
+    }
+    if (!maybe) return -1;
+    int mb = sn.grid[(c[2] * sn.gn[1] + c[1]) * sn.gn[0] + c[0]];
+    if (mb >= 0) {
+        geo = load_geom(sn, mb);
+        if (in_block(geo, x)) return mb;
+    }
+    mb = locate_block_slow(sn.grid, sn.geom, sn.gn[0], sn.gn[1], sn.gn[2], x[1], x[2], x[3], c[0], c[1], c[2], mb);
+    if (mb >= 0) geo = load_geom(sn, mb);
+    return mb;
+}
+
 // athenak.py:663-670.  Blocks tile the domain without overlap, so "last match wins" == "the match".
 // Returns the block index (or -1) and its geometry record.
-__device__ __forceinline__ int locate_block(const SnapshotView& sn, const double x[4], BlockGeom& geo)
+MK_HD int locate_block(const SnapshotView& sn, const double x[4], BlockGeom& geo)
 {
     if (sn.grid == nullptr) {
         // NaN-safe bounding-box rejection (comparisons with NaN are false -> outside), then the reference's scan
@@ -84,59 +178,22 @@ __device__ __forceinline__ int locate_block(const SnapshotView& sn, const double
         }
         return found;
     }
-    // Grid cell of the point.  The range test on the integer cell index doubles as the bounding-box rejection:
-    // x below the lower domain face gives a negative quotient (x - g0 is negative exactly when x < g0), x above
-    // the upper face gives q >= gn.  q == gn is the one ambiguous value (x on the upper face, which is inside --
-    // right-closed extents -- or just beyond it), so only there the exact face is consulted.  NaN converts to 0
-    // and fails the exact membership test below.  Whatever passes is decided by in_block() on the stored faces.
-    int c[3];
-    bool maybe = true;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        int q = __double2int_rd((x[d + 1] - sn.g0[d]) * sn.ginv[d]);
-        if (q == sn.gn[d]) q = (x[d + 1] <= sn.bbox_hi[d]) ? q - 1 : q;
-        maybe &= ((unsigned)q < (unsigned)sn.gn[d]);
-        c[d] = q;
-    }
-    if (!maybe) return -1;
-    int mb = sn.grid[(c[2] * sn.gn[1] + c[1]) * sn.gn[0] + c[0]];
-    if (mb >= 0) {
-        geo = load_geom(sn, mb);
-        if (in_block(geo, x)) return mb;
-    }
-    if (!((x[1] == x[1]) & (x[2] == x[2]) & (x[3] == x[3]))) return -1;          // NaN position: outside
-    // a point within rounding distance of a face may land in the neighbouring grid cell: fix up with the
-    // exact extents (x <= lo -> step down, x > hi -> step up), at most one step per axis
-    int c2[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        int s = 0;
-        if (mb >= 0) s = (x[d + 1] <= geo.lo[d]) ? -1 : ((x[d + 1] > geo.hi[d]) ? 1 : 0);
-        c2[d] = min(max(c[d] + s, 0), sn.gn[d] - 1);
-    }
-    int mb2 = sn.grid[(c2[2] * sn.gn[1] + c2[1]) * sn.gn[0] + c2[0]];
-    if (mb2 >= 0) {
-        geo = load_geom(sn, mb2);
-        if (in_block(geo, x)) return mb2;
-    }
-    // last resort (holes in the mesh, degenerate geometry): exhaustive neighbourhood
-    for (int dk = -1; dk <= 1; dk++)
-        for (int dj = -1; dj <= 1; dj++)
-            for (int di = -1; di <= 1; di++) {
-                int a = c[0] + di, b = c[1] + dj, e = c[2] + dk;
-                if (a < 0 || b < 0 || e < 0 || a >= sn.gn[0] || b >= sn.gn[1] || e >= sn.gn[2]) continue;
-                int m = sn.grid[(e * sn.gn[1] + b) * sn.gn[0] + a];
-                if (m < 0) continue;
-                geo = load_geom(sn, m);
-                if (in_block(geo, x)) return m;
-            }
-    return -1;
+    return locate_block_grid(sn, x, geo);
 }
 
 // athenak.py:718-733: xi = x - x_v[0] + dx ; idx = xi // dx ; delta = (xi / dx) % 1.
-__device__ __forceinline__ void cell_index(double x, double v0, double dx, int& idx, double& delta)
+// pow2 (warp-uniform): dx is a power of two, so xi * (1/dx) is the exact quotient; its floor and fractional part are
+// what the reference's floor division and "% 1" return, with no rounding to repair.
+MK_HD void cell_index(double x, double v0, double dx, double inv_dx, bool pow2, int& idx, double& delta)
 {
     double xi = x - v0 + dx;
+    if (pow2) {
+        double qd = xi * inv_dx;
+        double q = floor(qd);
+        delta = qd - q;
+        idx = (int)q;
+        return;
+    }
     double qd = fast_div(xi, dx);         // dx is a positive normal number
     double q = floor(qd);
     delta = qd - q;                       // python float % 1. for qd >= 0
@@ -146,28 +203,36 @@ __device__ __forceinline__ void cell_index(double x, double v0, double dx, int& 
     if (rem >= dx) idx += 1;
 }
 
-__device__ __forceinline__ void load_cell_pair(const double* p, double a[8], double b[8])
+MK_HD void load_cell_pair(const double* p, double a[8], double b[8])
 {
     // two x-adjacent cells = 128 contiguous bytes, read as four 256-bit read-only loads
     double4 v[4];
+#ifdef __CUDA_ARCH__
 #pragma unroll
     for (int i = 0; i < 4; i++)
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
             : "=d"(v[i].x), "=d"(v[i].y), "=d"(v[i].z), "=d"(v[i].w) : "l"(p + 4 * i));
+#else
+    for (int i = 0; i < 4; i++) v[i] = reinterpret_cast<const double4*>(p)[i];
+#endif
     a[0] = v[0].x; a[1] = v[0].y; a[2] = v[0].z; a[3] = v[0].w; a[4] = v[1].x; a[5] = v[1].y; a[6] = v[1].z; a[7] = v[1].w;
     b[0] = v[2].x; b[1] = v[2].y; b[2] = v[2].z; b[3] = v[2].w; b[4] = v[3].x; b[5] = v[3].y; b[6] = v[3].z; b[7] = v[3].w;
 }
 
-__device__ __forceinline__ void load_cell_pair(const float* p, double a[8], double b[8])
+MK_HD void load_cell_pair(const float* p, double a[8], double b[8])
 {
     // two x-adjacent f32 cells = 64 contiguous bytes, two 256-bit read-only loads
     float v[16];
+#ifdef __CUDA_ARCH__
 #pragma unroll
     for (int i = 0; i < 2; i++)
         asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
             : "=f"(v[8 * i]), "=f"(v[8 * i + 1]), "=f"(v[8 * i + 2]), "=f"(v[8 * i + 3]), "=f"(v[8 * i + 4]),
               "=f"(v[8 * i + 5]), "=f"(v[8 * i + 6]), "=f"(v[8 * i + 7])
             : "l"(p + 8 * i));
+#else
+    for (int i = 0; i < 16; i++) v[i] = p[i];
+#endif
 #pragma unroll
     for (int q = 0; q < 8; q++) { a[q] = (double)v[q]; b[q] = (double)v[8 + q]; }
 }
@@ -176,15 +241,18 @@ __device__ __forceinline__ void load_cell_pair(const float* p, double a[8], doub
 // same trilinear interpolant is accumulated as sum_c w_c v_c with the 8 corner weights (identical in exact
 // arithmetic, ~1 ulp apart in floating point): 64 FMAs instead of 112 operations, and each x-pair of cells is
 // consumed as soon as it is loaded, which keeps the register footprint of the fused kernel small.
-template <class CellT>
-__device__ __forceinline__ void trilinear(const SnapshotView& sn, int mb, const BlockGeom& geo, const double x[4],
+template <class CellT, int POW2 = -1>
+MK_HD void trilinear(const SnapshotView& sn, int mb, const BlockGeom& geo, const double x[4],
                                           double prims[8])
 {
     int i1, i2, i3;
     double d1, d2, d3;
-    cell_index(x[1], geo.v0[0], geo.dx[0], i1, d1);
-    cell_index(x[2], geo.v0[1], geo.dx[1], i2, d2);
-    cell_index(x[3], geo.v0[2], geo.dx[2], i3, d3);
+    const bool pow2 = (POW2 < 0) ? (sn.dx_pow2 != 0) : (POW2 != 0);
+    double inv[3] = {0.0, 0.0, 0.0};
+    if (pow2) load_inv_dx(sn, mb, inv);
+    cell_index(x[1], geo.v0[0], geo.dx[0], inv[0], pow2, i1, d1);
+    cell_index(x[2], geo.v0[1], geo.dx[1], inv[1], pow2, i2, d2);
+    cell_index(x[3], geo.v0[2], geo.dx[2], inv[2], pow2, i3, d3);
     // in-block points have indices in [0, n]; clamp defensively so that no load can leave the block
     i1 = min(max(i1, 0), sn.ni); i2 = min(max(i2, 0), sn.nj); i3 = min(max(i3, 0), sn.nk);
     const long sj = sn.sj, sk = sn.sk;
@@ -206,7 +274,7 @@ __device__ __forceinline__ void trilinear(const SnapshotView& sn, int mb, const 
 // Analytic torus primitives in canonical order; zero outside r <= r_out (the model's "domain").  Same formulas as
 // mahakala_b200/synthetic.py::torus_fields (no waves); divisions, square roots and the two Gaussians use the
 // MUFU-seeded FP64 helpers (<= few ulp; the exponentials flush results below 1e-307 to zero).
-__device__ __forceinline__ bool torus_prims(const TorusParams& t, const double x[4], double prims[8])
+MK_HD bool torus_prims(const TorusParams& t, const double x[4], double prims[8])
 {
     double R2 = fma(x[1], x[1], x[2] * x[2]);
     double R = fast_sqrt(R2) + 1e-12, r = fast_sqrt(fma(x[3], x[3], R2)) + 1e-12;
@@ -242,8 +310,21 @@ __device__ __forceinline__ bool torus_prims(const TorusParams& t, const double x
     return true;
 }
 
+// Snapshot kinds the fused render kernel is specialised for (its hot loop then carries only that kind's code: the
+// kernel is sensitive to instruction-cache footprint and register pressure).  GENERIC handles everything at run time.
+enum { SNAP_GENERIC = 0, SNAP_F64_GRID_POW2 = 1, SNAP_F32_GRID_POW2 = 2 };
+
+MK_HD int snapshot_kind(const SnapshotView& sn)
+{
+    if (sn.source == 0 && sn.grid != nullptr && sn.dx_pow2) return sn.is_f32 ? SNAP_F32_GRID_POW2 : SNAP_F64_GRID_POW2;
+    return SNAP_GENERIC;
+}
+
+template <int KIND>
+MK_HD bool interp_prims_kind(const SnapshotView& sn, const double x[4], double prims[8]);
+
 // prims in canonical order dens, eint, U1..3, B1..3; returns false (and zeros) outside the domain
-__device__ __forceinline__ bool interp_prims(const SnapshotView& sn, const double x[4], double prims[8])
+MK_HD bool interp_prims(const SnapshotView& sn, const double x[4], double prims[8])
 {
     if (sn.source == 1) return torus_prims(sn.torus, x, prims);
     BlockGeom geo;
@@ -258,12 +339,28 @@ __device__ __forceinline__ bool interp_prims(const SnapshotView& sn, const doubl
     return true;
 }
 
+template <int KIND>
+MK_HD bool interp_prims_kind(const SnapshotView& sn, const double x[4], double prims[8])
+{
+    if (KIND == SNAP_GENERIC) return interp_prims(sn, x, prims);
+    BlockGeom geo;
+    int mb = locate_block_grid(sn, x, geo);
+    if (mb < 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) prims[q] = 0.0;
+        return false;
+    }
+    if (KIND == SNAP_F32_GRID_POW2) trilinear<float, 1>(sn, mb, geo, x, prims);
+    else trilinear<double, 1>(sn, mb, geo, x, prims);
+    return true;
+}
+
 struct FluidScalars {
     double dens, u, cos_pitch, kdotu, b;     // cos_pitch: clamped cosine; pitch_angle = acos(cos_pitch)
 };
 
 // athenak.py:760-792 with g = eta + f l l, g^-1 = eta - f l^m l^n in closed form (Kerr-Schild family).
-__device__ __forceinline__ FluidScalars fluid_frame(double f, const double l[4], const double s[8],
+MK_HD FluidScalars fluid_frame(double f, const double l[4], const double s[8],
                                                     const double prims[8], double cos_fallback)
 {
     const double* U = prims + 2;
@@ -314,7 +411,7 @@ struct EmissionParams {
 };
 
 // transfer.py:56-86.  sin_pitch = sin(pitch_angle).  Returns (emissivity, absorptivity).
-__device__ __forceinline__ void synchrotron(const EmissionParams& P, double Ne, double Theta_e, double B,
+MK_HD void synchrotron(const EmissionParams& P, double Ne, double Theta_e, double B,
                                             double sin_pitch, double nu, int invariant, double rescale_nu,
                                             double& em_out, double& ab_out)
 {
@@ -344,7 +441,7 @@ __device__ __forceinline__ void synchrotron(const EmissionParams& P, double Ne, 
 }
 
 // images.py:87-102 + electrons.py:46-50: everything between the fluid scalars and (Ne, Theta_e, B)
-__device__ __forceinline__ void plasma_state(const EmissionParams& P, const FluidScalars& fs, double& Ne,
+MK_HD void plasma_state(const EmissionParams& P, const FluidScalars& fs, double& Ne,
                                              double& Theta_e, double& Bg, double& sigma)
 {
     double bsq = fs.b * fs.b;
@@ -382,7 +479,7 @@ struct EmissionConsts {      // derived once per launch on the host from Emissio
     // by one multiplication, so cbrt / sqrt / reciprocal are evaluated once per sample, not once per frequency
     double nu0;              // nu_obs[0]
     double ratio[8];         // nu_f / nu_0
-    double iratio[8];        // nu_0 / nu_f
+    double iratio3[8];       // (nu_0 / nu_f)^3
     double c13[8];           // cbrt(nu_f / nu_0)
     double c16[8];           // (nu_f / nu_0)^(1/6)
 };
@@ -404,7 +501,7 @@ __host__ __device__ inline EmissionConsts make_emission_consts(const EmissionPar
     for (int f = 0; f < 8; f++) {
         double r = (nu_obs && f < nfreq) ? nu_obs[f] / c.nu0 : 1.0;
         c.ratio[f] = r;
-        c.iratio[f] = 1.0 / r;
+        c.iratio3[f] = 1.0 / (r * r * r);
         c.c13[f] = cbrt(r);
         c.c16[f] = sqrt(c.c13[f]);
     }
@@ -414,7 +511,7 @@ __host__ __device__ inline EmissionConsts make_emission_consts(const EmissionPar
 // `sink(fq, em, ab)` receives the invariant emissivity and absorptivity of frequency fq as soon as they are known, so
 // that a multi-frequency caller can fold them into its accumulators without holding 2 NF values in registers.
 template <int NF, class Sink>
-__device__ __forceinline__ bool emission_fast(const EmissionParams& P, const EmissionConsts& C, double f,
+MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, double f,
                                               const double l[4], const double s[8], const double prims[8],
                                               const double* nu_obs, const double* inv_nu_obs, Sink&& sink)
 {
@@ -500,8 +597,9 @@ __device__ __forceinline__ bool emission_fast(const EmissionParams& P, const Emi
         double e = pref * (term * term) * fast_exp_neg(x13);
         double bx = bx0 * C.ratio[fq];
         double den = (bx < 2.e-3) ? bx * (1. / 24.) * fma(bx, fma(bx, 4. + bx, 12.), 24.) : exp(bx) - 1.0;
-        double ir = C.iratio[fq];
-        double a = e * den * kab0 * (ir * ir * ir);
+        // (k_ab / nu_0^3) (nu_0 / nu_f)^3 first: with frequencies decades apart the product e den k_ab / nu_0^3
+        // would underflow before the ratio brings it back
+        double a = (e * den) * (kab0 * C.iratio3[fq]);
         e = e * irn2;
         a = a * rn;
         bool ok = valid & (X <= 1.e12) & (e == e) & (a == a);

@@ -196,7 +196,7 @@ extern "C" int mk_emission_from_states(const mk_snapshot* snap, const mk_emissio
     MK_REQUIRE(snap && params && S && em && ab, "null pointer");
     EmissionParams P;
     memcpy(&P, params, sizeof P);
-    KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 0;
+    KerrSchild g; g.set_spin(bhspin);
     emission_from_states_kernel<<<grid1d(n, 128), 128, 0, (cudaStream_t)stream>>>(snap->view, P, g, S, n, nu_obs, em, ab);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -222,7 +222,7 @@ extern "C" int mk_emission_probe(const mk_emission_params* params, double bhspin
     EmissionParams P;
     memcpy(&P, params, sizeof P);
     EmissionConsts C = make_emission_consts(P, nu_obs, nfreq);
-    KerrSchild g; g.a = bhspin; g.aa = bhspin * bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
+    KerrSchild g; g.set_spin(bhspin);
     ProbeFreq F;
     for (int f = 0; f < 8; f++) { F.nu[f] = nu_obs[f < nfreq ? f : nfreq - 1]; F.inv_nu[f] = 1.0 / F.nu[f]; }
     switch (nfreq) {

@@ -1,0 +1,115 @@
+// TEST INFRASTRUCTURE: the arithmetic of the ray kernels compiled FOR THE HOST from the product's own headers
+// (mahakala_b200/csrc/*.cuh are __host__ __device__), so that the CPU test suite can hold the closed-form
+// acceleration, the RK4 step, the step rule and the fused emission chain to the oracle without a GPU.  Nothing in
+// the product loads this library; the product path stays CUDA-only.  Built by tests/host_harness/build.py.
+#include <cmath>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../../mahakala_b200/csrc/integrate.cuh"
+#include "../../mahakala_b200/csrc/ks_metric.cuh"
+#include "../../mahakala_b200/csrc/sample.cuh"
+
+using namespace mk;
+
+static KerrSchild make_ks(double a)
+{
+    KerrSchild g;
+    g.set_spin(a);
+    return g;
+}
+
+extern "C" void hk_rhs(long n, const double* s, double a, double* out)
+{
+    KerrSchild g = make_ks(a);
+    for (long i = 0; i < n; i++) {
+        double acc[4];
+        g.accel(s + 8 * i, s + 8 * i + 4, acc);
+        for (int m = 0; m < 4; m++) { out[8 * i + m] = s[8 * i + 4 + m]; out[8 * i + 4 + m] = acc[m]; }
+    }
+}
+
+extern "C" void hk_rk4(long n, const double* s, const double* dt, double a, double* out)
+{
+    KerrSchild g = make_ks(a);
+    for (long i = 0; i < n; i++) rk4_step(g, s + 8 * i, dt[i], out + 8 * i);
+}
+
+// the per-ray loop of integrate_kernel.cuh (final-state mode) without the warp machinery
+extern "C" void hk_integrate(long n, const double* s0, int N, double div, double tol, double a, double* final_state,
+                             int* nsteps, double* r_last)
+{
+    KerrSchild g = make_ks(a);
+    StepRule rule;
+    rule.div = div; rule.inv_div = 1.0 / div; rule.tol = tol; rule.rH = g.rH;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long p = 0; p < n; p++) {
+        double s[8], sn[8];
+        std::memcpy(s, s0 + 8 * p, sizeof s);
+        KerrSchild::Cache c, cn;
+        double r_cur = g.radius(s, c), r_prev = r_cur, best_dt = -1e300, r_before_best = r_cur;
+        double dt = rule(r_cur);
+        int it = 0, best_idx = -1;
+        bool capped = false;
+        for (;;) {
+            double r_new = 0, dtn = 0;
+            if (dt != 0.0) {
+                rk4_step(g, s, dt, sn, &c);
+                r_new = g.radius(sn, cn);
+                dtn = rule(r_new);
+            }
+            if (dt == 0.0 || dtn == 0.0) break;
+            if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
+            r_prev = r_cur; r_cur = r_new; dt = dtn; it++;
+            std::memcpy(s, sn, sizeof s); c = cn;
+            if (it == N) { capped = true; break; }
+        }
+        std::memcpy(final_state + 8 * p, s, sizeof s);
+        nsteps[p] = it;
+        double rl;
+        if (capped) rl = (best_idx >= 1) ? r_before_best : r_prev;
+        else rl = (best_dt > 0.0) ? ((best_idx >= 1) ? r_before_best : r_cur) : ((it >= 1) ? r_prev : r_cur);
+        r_last[p] = rl;
+    }
+}
+
+struct hk_params { double v[15]; };
+
+extern "C" void hk_emission_fast(long n, const double* S, const double* prims, const double* params15, double a,
+                                 int nfreq, const double* nu_obs, double* em, double* ab)
+{
+    KerrSchild g = make_ks(a);
+    EmissionParams P;
+    std::memcpy(&P, params15, sizeof P);
+    EmissionConsts C = make_emission_consts(P, nu_obs, nfreq);
+    double nu[8], inu[8];
+    for (int f = 0; f < 8; f++) { nu[f] = nu_obs[f < nfreq ? f : nfreq - 1]; inu[f] = 1.0 / nu[f]; }
+    for (long p = 0; p < n; p++) {
+        const double* s = S + 8 * p;
+        KerrSchild::Cache c;
+        g.radius(s, c);
+        double f, l[4];
+        l[0] = 1.0;
+        g.fl(s, c, f, l[1], l[2], l[3]);
+        auto sink = [&](int fq, double e, double b) { em[(long)fq * n + p] = e; ab[(long)fq * n + p] = b; };
+        switch (nfreq) {
+            case 1: emission_fast<1>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            case 2: emission_fast<2>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            case 3: emission_fast<3>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            case 4: emission_fast<4>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            case 5: emission_fast<5>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            case 6: emission_fast<6>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            case 7: emission_fast<7>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+            default: emission_fast<8>(P, C, f, l, s, prims + 8 * p, nu, inu, sink); break;
+        }
+    }
+}
+
+extern "C" void hk_rhs_v1(long n, const double* s, double a, double* out)
+{
+    KerrSchild g = make_ks(a);
+    for (long i = 0; i < n; i++) {
+        double acc[4];
+        g.accel_v1(s + 8 * i, s + 8 * i + 4, acc);
+        for (int m = 0; m < 4; m++) { out[8 * i + m] = s[8 * i + 4 + m]; out[8 * i + 4 + m] = acc[m]; }
+    }
+}

@@ -1,0 +1,114 @@
+"""The ARITHMETIC of the ray kernels, compiled for the host from the product's own headers (tests/host_harness), held to
+the oracle in the CPU suite: closed-form Kerr-Schild acceleration (ks_metric.cuh), RK4 step and step rule
+(integrate.cuh), the per-ray loop of integrate_kernel.cuh, and the fused emission chain (sample.cuh::emission_fast).
+
+The build container has no GPU, so without this the kernels' numerics would only ever be checked at round end.  The
+device differs from this build in one place only: the MUFU seeds of 1/x and 1/sqrt(x) (emulated here by library values
+truncated to 22 bits); everything downstream is the same FMA sequence.  The -m gpu tests remain the parity tests
+proper; nothing in the product loads this library (test_product_package_never_imports_the_oracle covers tests/ too).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+A = 0.94
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+@pytest.fixture(scope="module")
+def hk(built):
+    from host_harness import build
+    return build.lib()
+
+
+def _rhs(hk, P, which="hk_rhs"):
+    out = np.empty_like(P)
+    getattr(hk, which)(ctypes.c_long(P.shape[0]), _d(P), ctypes.c_double(A), _d(out))
+    return out
+
+
+def test_closed_form_acceleration_matches_the_oracle(hk):
+    """KerrSchild::accel (expansion + twist form of grad l, 87 FP64 operations) and the round-1 component-wise form
+    against the oracle's jets + 4x4 inverse (geodesics.py:294-309): 1e-12 at generic points, 1e-9 along trajectories
+    that graze the horizon (where the oracle's own inverse loses digits)."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    rng = np.random.default_rng(0)
+    rnd = np.concatenate([np.zeros((6000, 1)), rng.normal(0, 6, (6000, 3)), rng.normal(0, 1, (6000, 4))], axis=1)
+    rnd = np.ascontiguousarray(rnd[onp.radius_cal(rnd, A) > 1.4])
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 16))
+    S, dt = c_oracle.geodesic_integrator(10000, s0, 40, 1e-4, A)
+    traj = S[::5].reshape(-1, 8)
+    traj = np.ascontiguousarray(traj[onp.radius_cal(traj, A) > 1.36])
+    for P, tol in ((rnd, 1e-12), (traj, 1e-9)):
+        ref = c_oracle.rhs(P, A)
+        scale = np.abs(ref[:, 4:]).max(axis=1, keepdims=True)
+        new, old = _rhs(hk, P), _rhs(hk, P, "hk_rhs_v1")
+        assert np.array_equal(new[:, :4], P[:, 4:])
+        assert (np.abs(new[:, 4:] - ref[:, 4:]) / scale).max() < tol
+        assert (np.abs(old[:, 4:] - ref[:, 4:]) / scale).max() < tol
+        assert (np.abs(new[:, 4:] - old[:, 4:]) / scale).max() < tol
+
+
+def test_rk4_step_matches_the_oracle(hk):
+    from oracle import mahakala_oracle as onp
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 12))
+    rng = np.random.default_rng(1)
+    pts = s0.copy()
+    pts[:, 1:4] *= rng.uniform(0.004, 0.05, (pts.shape[0], 1))          # r from 4 to 50 along the camera rays
+    dt = -(onp.radius_cal(pts, A) - onp.radius_EH(A)) / 40.
+    out = np.empty_like(pts)
+    hk.hk_rk4(ctypes.c_long(pts.shape[0]), _d(pts), _d(np.ascontiguousarray(dt)), ctypes.c_double(A), _d(out))
+    ref = onp.RK4_gen(pts, dt, A)
+    assert (np.abs(out - ref) / np.abs(ref).max(axis=1, keepdims=True)).max() < 1e-13
+
+
+@pytest.mark.parametrize("res,N,tol,sub", [(64, 2000, 1e-2, 1), (1024, 10000, 1e-4, 16)])
+def test_ray_loop_matches_the_oracle(hk, res, N, tol, sub):
+    """BASELINE config 1 (full 64x64 grid) and the every-16th-pixel sub-lattice of config 2 through the per-ray loop of
+    the integrate kernel: classification bit-exact, step counts identical on escaped rays, end states 1e-9."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, res))
+    if sub > 1:
+        idx = (np.arange(0, res, sub)[:, None] * res + np.arange(0, res, sub)[None, :]).reshape(-1)
+        s0 = np.ascontiguousarray(s0[idx])
+    n = s0.shape[0]
+    fin, ns, rl = np.empty((n, 8)), np.empty(n, dtype=np.int32), np.empty(n)
+    hk.hk_integrate(ctypes.c_long(n), _d(s0), ctypes.c_int(N), ctypes.c_double(40.), ctypes.c_double(tol),
+                    ctypes.c_double(A), _d(fin), ns.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _d(rl))
+    ref = c_oracle.integrate(N, s0, 40, tol, A)
+    cap = ref["r_last"] < 100
+    assert np.array_equal(rl < 100, cap) and cap.sum() in (792, 799)
+    esc = ~cap
+    assert np.array_equal(ns[esc], ref["nsteps"][esc])
+    assert abs(int(ns.sum()) - int(ref["nsteps"].sum())) <= 4 * cap.sum()
+    err = np.abs(fin[esc] - ref["final"][esc]).max(axis=1) / np.abs(ref["final"][esc]).max(axis=1)
+    assert err.max() < 1e-9
+    assert np.allclose(rl[esc], ref["r_last"][esc], rtol=1e-9)
+
+
+def test_fused_emission_chain_on_adversarial_inputs(hk, monkeypatch):
+    """The adversarial cases of tests/test_emission_gpu.py (sigma cut, Theta_e floor, X range, Planck switch, aligned /
+    reversed / null wavevectors, degenerate primitives, exp underflow) run through the HOST build of emission_fast."""
+    import test_emission_gpu as T
+    from mahakala_b200 import transfer
+
+    def host_probe(S, pc, a, P, nus, fast=True):
+        S, pc = np.ascontiguousarray(S), np.ascontiguousarray(np.asarray(pc))
+        nus = np.ascontiguousarray(np.atleast_1d(nus), dtype=np.float64)
+        n = S.shape[0]
+        em, ab = np.empty((nus.size, n)), np.empty((nus.size, n))
+        pv = np.array([getattr(P, k) for k, _ in P._fields_])
+        hk.hk_emission_fast(ctypes.c_long(n), _d(S), _d(pc), _d(pv), ctypes.c_double(a), ctypes.c_int(nus.size),
+                            _d(nus), _d(em), _d(ab))
+        return em, ab
+
+    monkeypatch.setattr(transfer, "emission_probe", host_probe)
+    for name in ("test_sigma_cut_both_sides", "test_theta_floor_both_sides", "test_x_range_and_cube_root_fallback",
+                 "test_planck_series_switch", "test_field_aligned_reversed_and_null_wavevectors",
+                 "test_degenerate_primitives", "test_exp_underflow_band"):
+        getattr(T, name)(True)
