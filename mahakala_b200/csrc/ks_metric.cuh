@@ -103,7 +103,14 @@ struct KerrSchild {
     // force either (grad f = alpha grad r + beta e_z).  87 FP64 operations per call (71 with the point cache)
     // against 103 for the component-wise form of round 1; identical to it up to rounding
     // (tests/test_host_harness_cpu.py holds both to the literal jets + 4x4 inverse of the CPU restatement).
-    MK_HD void accel(const double x[4], const double v[4], double acc[4], const Cache* cache = nullptr) const
+    // The metric functions at the point of an acceleration call, for callers that need them as well (the fused
+    // render kernel's fluid-frame algebra at the state it is about to step from).
+    struct MetricFunctions {
+        double f, l1, l2, l3;
+    };
+
+    MK_HD void accel(const double x[4], const double v[4], double acc[4], const Cache* cache = nullptr,
+                     MetricFunctions* mf = nullptr) const
     {
         const double X = x[1], Y = x[2], Z = x[3];
         const double v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3];
@@ -126,6 +133,7 @@ struct KerrSchild {
         double l1 = fma(r, X, a * Y) * iq;
         double l2 = fma(r, Y, -(a * X)) * iq;
         double l3 = Z * ri;
+        if (mf) { mf->f = t + t; mf->l1 = l1; mf->l2 = l2; mf->l3 = l3; }
         double zr = Z * rid;
         double raz = aa * zr;                               // grad r = (t x, t y, t z + raz)
         double om4 = a4 * zr;                               // 4 omega

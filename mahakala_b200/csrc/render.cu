@@ -134,52 +134,43 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const RenderArgs A)
         if (active) dt = A.rule(A.g.radius(s, cache));
         if (dt == 0.0) active = false;          // never moves: n = 0, no row pair contributes
 
-        // Two loop shapes (compile-time, MK_RENDER_PIPE_MAX = largest NF that uses the first): a software-pipelined
-        // form that samples the state accepted in the previous iteration next to the RK4 step that leaves it, and
-        // the plain form "step, then sample the new state".  Measured on B200 (scripts/dev/render_variants.py, cfg4,
-        // same-box A/B): while the loop still copied the candidate state the pipelined form was ~2 % ahead for one
-        // or two frequencies; with the in-place RK4 update the plain form wins everywhere (1 / 2 / 8 frequencies:
-        // 25.6 / 27.5 / 37.3 ms against 25.8 / 27.9 ms pipelined, and 33.5 / 40.5 ms when 4 / 8 frequencies are
-        // pipelined: its extra live registers spill), with one RK4 copy less in the instruction stream.
+        // Two loop shapes (compile-time, MK_RENDER_PIPE_MAX = largest NF that uses the first):
+        //  * stage-1-first: the first RK4 stage of the step that LEAVES state s is evaluated before s is sampled, and
+        //    its metric functions (f, l) feed the fluid-frame algebra of the sample, so the sample needs no metric
+        //    evaluation of its own (17 FP64 operations and the dependency on the point cache);
+        //  * plain: "step, then sample the new state" with f, l from the point cache.
         // (The ping-pong register scheme of integrate_kernel.cuh, which removes the s = cand copies, was tried here
-        // too: it duplicates the whole sample + emission + RK4 body, and the kernel got 25 % SLOWER -- 34.2 vs
+        // too in round 1: it duplicates the whole sample + emission + RK4 body, and the kernel got 25 % SLOWER -- 34.2 vs
         // 27.4 ms on cfg4 -- at any register budget: the doubled code no longer fits the instruction cache.)
         if constexpr (NF <= MK_RENDER_PIPE_MAX) {
-            // Software-pipelined loop: the sample of state s (accepted in the previous iteration, weight wdt) and
-            // the RK4 step that leaves s are independent, so they sit in ONE straight-line block and the scheduler
-            // can fill the latency of the gathers and of the emission chain with RK4 arithmetic.
             double wdt = 0.0;
             bool pending = false;
             while (__any_sync(FULL_MASK, active)) {
                 if (active) {
-                    // The RK4 step updates s IN PLACE: when the step is rejected the ray retires and its old state
-                    // is not needed any more (it was sampled above), so no candidate copy has to be kept.
-                    const double dt_used = dt;
-                    double prims[8];
-                    double dtn;
-                    if (pending && interp_prims_kind<KIND>(A.sn, s, prims)) {
-                        my_samples++;
-                        double f, l[4], em[NF], ab[NF];
-                        l[0] = 1.0;
-                        A.g.fl(s, cache, f, l[1], l[2], l[3]);
-                        emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
-                                          [&](int fq, double e, double a) { em[fq] = e; ab[fq] = a; });
-                        rk4_step(A.g, s, dt, s, &cache);
-                        dtn = A.rule(A.g.radius(s, cache));
-    #pragma unroll
-                        for (int fq = 0; fq < NF; fq++) {      // em = ab = 0 leaves (I, T) unchanged
-                            const double Tf = T(fq);
-                            I(fq) = fma(Tf, wdt * em[fq], I(fq));
-                            T(fq) = Tf * fma(-wdt, ab[fq], 1.0);
+                    double a1[4];
+                    KerrSchild::MetricFunctions mf;
+                    A.g.accel(s, s + 4, a1, &cache, &mf);
+                    if (pending) {
+                        double prims[8];
+                        if (interp_prims_kind<KIND>(A.sn, s, prims)) {
+                            my_samples++;
+                            const double l[4] = {1.0, mf.l1, mf.l2, mf.l3};
+                            emission_fast<NF>(A.P, A.C, mf.f, l, s, prims, A.nu_obs, A.inv_nu_obs,
+                                              [&](int fq, double e, double a) {
+                                                  const double Tf = T(fq);
+                                                  I(fq) = fma(Tf, wdt * e, I(fq));
+                                                  T(fq) = Tf * fma(-wdt, a, 1.0);
+                                              });
                         }
-                    } else {
-                        rk4_step(A.g, s, dt, s, &cache);
-                        dtn = A.rule(A.g.radius(s, cache));
                     }
+                    // in place: when the step is rejected the ray retires and its old state (sampled above) is not
+                    // needed any more
+                    rk4_rest(A.g, s, a1, dt, s);
+                    const double dtn = A.rule(A.g.radius(s, cache));
                     if (dtn == 0.0) {
-                        active = false;             // step rejected; the ray was frozen at the state sampled above
+                        active = false;             // step rejected; ray frozen (geodesics.py:264-267)
                     } else {
-                        wdt = -dt_used * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
+                        wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
                         dt = dtn;
                         it++;
                         pending = true;

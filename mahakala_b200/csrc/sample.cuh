@@ -477,7 +477,7 @@ struct EmissionConsts {      // derived once per launch on the host from Emissio
     double k_ab;             // CL^2 / (2 HPL)
     // frequency ratios relative to nu_obs[0]: X, bx and 1/nu of frequency f follow from those of frequency 0
     // by one multiplication, so cbrt / sqrt / reciprocal are evaluated once per sample, not once per frequency
-    double nu0;              // nu_obs[0]
+    double nu0, inv_nu0;     // nu_obs[0] and its reciprocal
     double ratio[8];         // nu_f / nu_0
     double iratio3[8];       // (nu_0 / nu_f)^3
     double c13[8];           // cbrt(nu_f / nu_0)
@@ -498,6 +498,7 @@ __host__ __device__ inline EmissionConsts make_emission_consts(const EmissionPar
     c.k_bx = P.HPL / (P.ME * P.CL * P.CL);
     c.k_ab = (P.CL * P.CL) / (2.0 * P.HPL);
     c.nu0 = (nu_obs && nfreq > 0) ? nu_obs[0] : 1.0;
+    c.inv_nu0 = 1.0 / c.nu0;
     for (int f = 0; f < 8; f++) {
         double r = (nu_obs && f < nfreq) ? nu_obs[f] / c.nu0 : 1.0;
         c.ratio[f] = r;
@@ -582,12 +583,12 @@ MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, doubl
     if (valid && !((X0 > 1e-30) & (X0 < 1e30))) x13_0 = cbrt(X0);     // outside the float-seeded range (rare)
     double x16_0 = quick_sqrt(x13_0);
     double bx0 = C.k_bx * nu0 * ith;
-    double inu0 = fast_rcp(nu0);
-    double kab0 = C.k_ab * (inu0 * inu0 * inu0);
     // invariant rescaling (transfer.py:77-80): nu * rescale_nu = (-k.u nu_f) / nu_f = -k.u for every frequency
     double rn = -kdotu;
     double irn = fast_rcp(rn);
     double irn2 = irn * irn;
+    double inu0 = irn * C.inv_nu0;                               // 1 / (-k.u nu_0)
+    double kab0 = C.k_ab * (inu0 * inu0 * inu0);
 #pragma unroll
     for (int fq = 0; fq < NF; fq++) {
         double X = X0 * C.ratio[fq];

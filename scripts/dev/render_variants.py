@@ -23,6 +23,13 @@ print("%%-8s 1f %%.2f  1f-f64cells %%.2f  2f %%.2f  4f %%.2f  8f %%.2f ms" %% (s
       timeit(lambda: images.render(m64, resolution=1024)), timeit(lambda: images.render(m, resolution=1024, observing_frequencies=F8[2:4])),
       timeit(lambda: images.render(m, resolution=1024, observing_frequencies=F8[2:6])),
       timeit(lambda: images.render(m, resolution=1024, observing_frequencies=F8))), flush=True)
+m.release(); m64.release()
+import mahakala_b200 as ma
+from mahakala_b200 import geodesics as geo
+s0 = ma.initialize_geodesics_at_camera(0.94, 60, 1000, -10, 10, 1024)
+store = geo.TrajectoryStore.allocate(s0.shape[0], 10000, mem_fraction=0.5)
+print("%%-8s integrate final %%.2f  paged dump %%.2f ms" %% (sys.argv[1], timeit(lambda: geo.integrate_final(10000, s0, 40, 1e-4, 0.94)),
+      timeit(lambda: geo.integrate_paged(10000, s0, 40, 1e-4, 0.94, store=store))), flush=True)
 ''' % root
 libs = [("default", None)] + [(os.path.basename(p)[3:-3], p) for p in sorted(glob.glob(os.path.join(root, "mahakala_b200/variants/lib*.so")))]
 for name, path in libs:

@@ -113,3 +113,29 @@ extern "C" void hk_rhs_v1(long n, const double* s, double a, double* out)
         for (int m = 0; m < 4; m++) { out[8 * i + m] = s[8 * i + 4 + m]; out[8 * i + 4 + m] = acc[m]; }
     }
 }
+
+// Sampling path (block lookup, cell index, trilinear gather) on HOST arrays laid out like the device snapshot:
+// cells [mb][k][j][i][8] (canonical primitive order, ghost padded), geom (nmb, 16), int32 block grid.
+extern "C" void hk_sample_prims(int kind, const void* cells, int is_f32, int nmb, int nk, int nj, int ni,
+                                const double* geom16, const int* grid, const int* gn, const double* g0,
+                                const double* ginv, const double* bbox_lo, const double* bbox_hi, int dx_pow2,
+                                long n, const double* S, double* out)
+{
+    SnapshotView v;
+    std::memset(&v, 0, sizeof v);
+    v.source = 0; v.cells = cells; v.is_f32 = is_f32;
+    v.nmb = nmb; v.nk = nk; v.nj = nj; v.ni = ni;
+    v.sj = (long)(ni + 2) * 8; v.sk = v.sj * (nj + 2); v.sb = v.sk * (nk + 2);
+    v.geom = geom16; v.grid = grid; v.dx_pow2 = dx_pow2;
+    for (int d = 0; d < 3; d++) {
+        v.gn[d] = grid ? gn[d] : 0; v.g0[d] = grid ? g0[d] : 0; v.ginv[d] = grid ? ginv[d] : 0;
+        v.bbox_lo[d] = bbox_lo[d]; v.bbox_hi[d] = bbox_hi[d];
+    }
+    for (long p = 0; p < n; p++) {
+        double prims[8];
+        if (kind == SNAP_F64_GRID_POW2) interp_prims_kind<SNAP_F64_GRID_POW2>(v, S + 8 * p, prims);
+        else if (kind == SNAP_F32_GRID_POW2) interp_prims_kind<SNAP_F32_GRID_POW2>(v, S + 8 * p, prims);
+        else interp_prims(v, S + 8 * p, prims);
+        for (int q = 0; q < 8; q++) out[(long)q * n + p] = prims[q];
+    }
+}

@@ -407,7 +407,7 @@ def test_camera_rays_are_null_in_the_registered_spacetime(ma):
     assert np.asarray(S).shape == (0, 16, 8) and np.asarray(dt).shape == (0, 16)
     f, n, rl = geo.integrate_final(0, s0, 40, 1e-4, 0.9)
     assert np.array_equal(np.asarray(f.cpu()), np.asarray(s0)) and not np.asarray(n.cpu()).any()
-    assert np.allclose(np.asarray(rl.cpu()), np.asarray(ma.radius_cal(s0, 0.9)), rtol=1e-14)
+    assert np.allclose(np.asarray(rl.cpu()), np.asarray(geo.radius_cal(s0, 0.9)), rtol=1e-14)
     # a reused TrajectoryStore starts from an empty pool on every call
     st = geo.TrajectoryStore.allocate(16, 2000)
     geo.integrate_paged(2000, s0, 40, 1e-2, 0.9, store=st)

@@ -112,3 +112,81 @@ def test_fused_emission_chain_on_adversarial_inputs(hk, monkeypatch):
                  "test_planck_series_switch", "test_field_aligned_reversed_and_null_wavevectors",
                  "test_degenerate_primitives", "test_exp_underflow_band"):
         getattr(T, name)(True)
+
+
+def _host_snapshot(om, storage=np.float64):
+    """Host arrays in the device snapshot's layout from an oracle model (reference layout all_meshblocks)."""
+    from mahakala_b200.grmhd.athenak import build_block_grid
+    amb = om.all_meshblocks                                   # (nmb, 8, nk+2, nj+2, ni+2), file order
+    canon = [0, 4, 1, 2, 3, 5, 6, 7]                          # dens, eint, U1..3, B1..3
+    cells = np.ascontiguousarray(amb[:, canon].transpose(0, 2, 3, 4, 1)).astype(storage)
+    nmb = amb.shape[0]
+    dx = [np.asarray(v)[:, 1] - np.asarray(v)[:, 0] for v in (om.x1v, om.x2v, om.x3v)]
+    geom = np.zeros((nmb, 16))
+    geom[:, 0:3] = np.stack([om.x1f[:, 0], om.x2f[:, 0], om.x3f[:, 0]], axis=1)
+    geom[:, 3:6] = np.stack([om.x1f[:, -1], om.x2f[:, -1], om.x3f[:, -1]], axis=1)
+    geom[:, 6:9] = np.stack([om.x1v[:, 0], om.x2v[:, 0], om.x3v[:, 0]], axis=1)
+    geom[:, 9:12] = np.stack(dx, axis=1)
+    geom[:, 12:15] = 1.0 / geom[:, 9:12]
+    pow2 = bool(np.all(np.frexp(geom[:, 9:12])[0] == 0.5))
+    grid, gn, g0, ginv = build_block_grid(om.x1f, om.x2f, om.x3f)
+    lo, hi = geom[:, 0:3].min(axis=0), geom[:, 3:6].max(axis=0)
+    return dict(cells=cells, geom=geom, grid=np.ascontiguousarray(grid), gn=gn, g0=g0, ginv=ginv, lo=lo, hi=hi,
+                pow2=pow2, shape=amb.shape)
+
+
+def _host_sample(hk, snap, S, kind):
+    S = np.ascontiguousarray(S.reshape(-1, 8))
+    out = np.empty((8, S.shape[0]))
+    nmb, _, nk2, nj2, ni2 = snap["shape"]
+    ip = ctypes.POINTER(ctypes.c_int)
+    hk.hk_sample_prims(ctypes.c_int(kind), snap["cells"].ctypes.data_as(ctypes.c_void_p),
+                       ctypes.c_int(1 if snap["cells"].dtype == np.float32 else 0), ctypes.c_int(nmb),
+                       ctypes.c_int(nk2 - 2), ctypes.c_int(nj2 - 2), ctypes.c_int(ni2 - 2), _d(snap["geom"]),
+                       snap["grid"].ctypes.data_as(ip), snap["gn"].ctypes.data_as(ip), _d(snap["g0"]), _d(snap["ginv"]),
+                       _d(snap["lo"]), _d(snap["hi"]), ctypes.c_int(1 if snap["pow2"] else 0),
+                       ctypes.c_long(S.shape[0]), _d(S), _d(out))
+    return out
+
+
+def test_sampling_path_matches_the_oracle(hk):
+    """Block lookup + cell index + trilinear gather of sample.cuh (generic path and the two specialisations of the
+    fused kernel, whose cell index multiplies by the exact 1/dx of power-of-two meshes) against the oracle's literal
+    athenak.py:663-757 on trajectories, on points exactly on faces / corners, outside, and NaN."""
+    from helpers import oracle_model, snapshot_arrays
+    from oracle import c_oracle, mahakala_oracle as onp
+    om = oracle_model(snapshot_arrays(ncells=32, block=16, extent=16.0, funnel={}), A)
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 10))
+    S, dt = c_oracle.geodesic_integrator(10000, s0, 40, 1e-4, A)
+    f = om.x1f[0]
+    edge = [[0.0, x, y, z, 1.0, 0.3, -0.2, 0.1]
+            for x in (f[0], f[1], f[-1], -16.0, 16.0, 0.0, 15.999999999999998, 16.000000000000004, -15.75, 1e300, np.nan)
+            for y in (0.0, -16.0, 16.0, 2.0) for z in (0.5, 0.0, 16.0, -16.0)]
+    pts = np.concatenate([S.reshape(-1, 8), np.array(edge)])
+    ref = c_oracle.sample(om, pts, mode="prims")
+    ref = np.stack([ref[k] for k in ("dens", "u", "U1", "U2", "U3", "B1", "B2", "B3")])
+    assert (ref[0] > 0).sum() > 5000 and (ref[0] == 0).sum() > 5000
+    snap64, snap32 = _host_snapshot(om), _host_snapshot(om, np.float32)
+    assert snap64["pow2"]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    results = {}
+    for name, snap, kind in (("generic", snap64, 0), ("f64 pow2", snap64, 1), ("f32 pow2", snap32, 2),
+                             ("generic f32", snap32, 0)):
+        got = _host_sample(hk, snap, pts, kind)
+        assert np.array_equal(got == 0, ref == 0), name
+        assert (np.abs(got - ref) / scale).max() < 1e-14, name
+        results[name] = got
+    # the specialisations return the very same numbers as the generic path (values are float32-representable)
+    for name in ("f64 pow2", "f32 pow2", "generic f32"):
+        assert np.array_equal(results[name], results["generic"]), name
+    # a mesh whose cell size is NOT a power of two keeps the corrected division: still the oracle's numbers
+    arr = snapshot_arrays(ncells=24, block=12, extent=15.0)
+    om2 = oracle_model(arr, A)
+    snap = _host_snapshot(om2)
+    assert not snap["pow2"]
+    pts2 = np.ascontiguousarray(S[150:400].reshape(-1, 8))
+    ref2 = c_oracle.sample(om2, pts2, mode="prims")
+    ref2 = np.stack([ref2[k] for k in ("dens", "u", "U1", "U2", "U3", "B1", "B2", "B3")])
+    got2 = _host_sample(hk, snap, pts2, 0)
+    assert (ref2[0] > 0).sum() > 2000 and np.array_equal(got2 == 0, ref2 == 0)
+    assert (np.abs(got2 - ref2) / np.abs(ref2).max(axis=1, keepdims=True)).max() < 1e-14
