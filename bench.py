@@ -182,7 +182,11 @@ def workload_config(args, mode):
                         f"i=60 deg, fov 20 M, div=40, tol=1e-4, N=10000",
             "mode": mode, "rays": args.res * args.res,
             "l2_policy": "256 MiB scratch write between timed iterations (L2 flush); the dump itself is >> L2",
-            "multi_gpu": "one full frame per rank at its own inclination (weak scaling, no data-path collective)"}
+            "multi_gpu": ("N frames (one per GPU, inclinations " + ", ".join(f"{i:g}" for i in WEAK_INCLINATIONS) +
+                          " deg in rank order) integrated by ALL GPUs together: one dynamic ray queue in rank 0's "
+                          "memory shared over NVLink (system-scope atomics, chunked + prefetched), longest rays first, "
+                          "per-ray results stored by the kernels straight into rank 0's memory (in-kernel gather), "
+                          "trajectories paged where they are computed; weak scaling, no data-path collective")}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -224,18 +228,38 @@ def run_b200(args):
     _cabi.call("mk_measure_fp64_peak", 20000, tf, ms)
     fp64_peak = tf.value
 
-    store = geo.TrajectoryStore.allocate(npx, CFG2["N"])
     mode = "trajectory dump (paged warp logs, single pass)"
     launches = [0]
+    shared = None
+    if world > 1:
+        # BASELINE north_star split: ONE job of `world` frames, every GPU holds all bundles, rays come from one queue
+        from mahakala_b200 import multigpu
+        frames = [WEAK_INCLINATIONS[f % len(WEAK_INCLINATIONS)] for f in range(world)]
+        s0_all = torch.cat([ma.initialize_geodesics_at_camera(a, frames[f], CFG2["distance"], -CFG2["fov"] / 2,
+                                                              CFG2["fov"] / 2, res) for f in range(world)])
+        order = torch.from_numpy(multigpu.longest_first_ray_order(res, world)).to(dev)
+        shared = multigpu.SharedRays(world * npx)
+        job_store = geo.TrajectoryStore.allocate(world * npx, CFG2["N"], mem_fraction=0.45)
+    store = geo.TrajectoryStore.allocate(npx, CFG2["N"], mem_fraction=0.55 if world > 1 else 0.6)
 
     def step_device():
-        if store is not None:
-            out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)   # resets the store
+        """-> device tensor with the ray-steps this rank integrated in the step"""
+        if world > 1:
+            geo.integrate_paged(CFG2["N"], s0_all, CFG2["div"], CFG2["tol"], a, store=job_store,
+                                queue=shared.queue_ptr, ray_order=order, results=shared.results(),
+                                page_id_offset=rank * job_store.max_pages)
             launches[0] += 1
-            return out.total_steps
-        final, nsteps, r_last, total = geo.integrate_final(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, want_total=True)
+            return job_store.total_steps
+        out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)   # resets the store
         launches[0] += 1
-        return total
+        return out.total_steps
+
+    def fence_queue():
+        """between two jobs on the shared queue: everybody is done, rank 0 zeroes the counter, everybody sees it"""
+        if world > 1:
+            barrier()
+            shared.reset()
+            barrier()
 
     host_out = {"final": torch.empty((npx, 8), dtype=torch.float64, pin_memory=True),
                 "nsteps": torch.empty((npx,), dtype=torch.int32, pin_memory=True),
@@ -267,6 +291,7 @@ def run_b200(args):
 
     # ---- warm-up ----
     for _ in range(args.warmup):
+        fence_queue()
         total = step_device()
         flush.fill_(1)
     barrier()
@@ -284,14 +309,61 @@ def run_b200(args):
     totals = []
     for k in range(args.steps):
         flush.fill_(k)                      # L2 flush, outside the event pair
+        fence_queue()                       # N > 1: queue reset between two barriers, outside the event pair
         ev[k][0].record()
         totals.append(step_device())
         ev[k][1].record()
     barrier()
     t_wall1 = time.time()
     dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    steps_per_pass = int(totals[-1].item())
+    steps_per_pass = int(totals[-1].item())     # ray-steps THIS rank integrated in the last step
     n_launch = launches[0]
+
+    # ---- N > 1: the gathered results of the split job against rank 0 integrating every frame alone ----
+    split = None
+    if world > 1:
+        pages_job = job_store.pages_used
+        overflow = torch.tensor([1.0 if job_store.overflowed else 0.0, float(steps_per_pass)], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros_like(overflow) for _ in range(world)]
+        dist.all_gather(per_rank, overflow)
+        if rank == 0:
+            views = shared.local_views()
+            same, worst = True, 0.0
+            for f in range(world):
+                alone = geo.integrate_paged(CFG2["N"], s0_all[f * npx:(f + 1) * npx], CFG2["div"], CFG2["tol"], a, store=store)
+                sl = slice(f * npx, (f + 1) * npx)
+                ok = (torch.equal(views["final"][sl], alone.final) and torch.equal(views["nsteps"][sl], alone.nsteps)
+                      and torch.equal(views["r_last"][sl], alone.r_last))
+                same = same and ok
+                worst = max(worst, float((views["final"][sl] - alone.final).abs().max()))
+            owner = views["page_first"][:, 0] // job_store.max_pages
+            split = {"split_identical": bool(same), "max_abs_diff_final_state": worst,
+                     "check": "final states, step counts and classifier radii of all frames gathered in rank 0's memory "
+                              "by the shared-queue job, torch.equal against rank 0 integrating each frame alone",
+                     "rays_per_rank": [int((owner == r).sum()) for r in range(world)],
+                     "ray_steps_per_rank": [int(t[1]) for t in per_rank],
+                     "page_pool_overflowed": bool(any(float(t[0]) for t in per_rank))}
+        del job_store
+        torch.cuda.empty_cache()
+        # for the record: the trivially parallel alternative, every rank integrating its own frame with no sharing
+        barrier()
+        iv = []
+        for k in range(3):
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record()
+            own = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)
+            i1.record()
+            torch.cuda.synchronize()
+            iv.append(i0.elapsed_time(i1))
+        ind = torch.tensor([float(np.mean(iv[1:])), float(own.total_steps.item())], dtype=torch.float64, device=dev)
+        ind_t, ind_w = ind[0:1].clone(), ind[1:2].clone()
+        dist.all_reduce(ind_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ind_w, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            split["independent_frames"] = {"value": float(ind_w) / (float(ind_t) * 1e-3), "unit": "ray-steps/s",
+                                           "ms_per_step": float(ind_t),
+                                           "note": "one frame per rank, private queues, nothing shared: the slowest "
+                                                   "inclination sets the time"}
 
     # ---- timed: end to end through the public API with host buffers ----
     step_e2e()
@@ -325,7 +397,7 @@ def run_b200(args):
     e2e_value = e2e_work * args.steps / e2e_s_max
 
     render = None
-    pages_used = store.pages_used if store is not None else 0
+    pages_used = store.pages_used if world == 1 else pages_job
     store = None
     torch.cuda.empty_cache()
     if not args.no_render:
@@ -334,7 +406,8 @@ def run_b200(args):
     if rank == 0:
         kernel_ms = dev_ms / args.steps
         achieved = steps_per_pass * FLOP_PER_RAY_STEP / (kernel_ms * 1e-3) / 1e12
-        dump_bytes = 72 * (steps_per_pass + npx) if pages_used else 0
+        rays_here = split["rays_per_rank"][0] if split is not None else npx
+        dump_bytes = 72 * (steps_per_pass + rays_here) if pages_used else 0
         line = {
             "metric": "ray_steps_per_sec_fp64", "value": value, "unit": "ray-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
@@ -361,16 +434,29 @@ def run_b200(args):
                                  "achieved_GBps": dump_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "peak_GBps": hbm_peak()}},
         }
+        if split is not None:
+            line["split"] = split
         if render is not None:
             line["render"] = render
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             v, info = time_cpu_oracle(args.res, args.cpu_sample)
             line["cpu_baseline"] = {"value": v, "unit": "ray-steps/s", "cores": info["cores"], "kind": "port",
                                     "sample": info["sample"] + "; C/OpenMP restatement of the reference's JAX path"}
         print(json.dumps(line))
+        failed = (split is not None and not split["split_identical"]) or \
+                 (render is not None and render.get("strong_image_identical") is False) or \
+                 (render is not None and render.get("strong_scaling_large_image", {}).get("identical") is False)
+    else:
+        failed = False
     if world > 1:
+        if shared is not None:
+            dist.barrier()
+            shared.close()
         dist.barrier()
         dist.destroy_process_group()
+    if failed:
+        sys.stdout.flush()
+        sys.exit(3)         # a split result that differs from the single-GPU one is a failure, not a number
 
 
 def measured_traffic(paged, res):
@@ -409,20 +495,24 @@ def render_leg(args, rank, world, dev):
     nc = args.snapshot_cells
     model = None
     if rank == 0:       # the other ranks get a geometry-only replica and the cells by one NCCL broadcast
-        arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0)
+        # float32 interior arrays, which is what an AthenaK dump holds (and what a loader hands over)
+        arr = make_synthetic_snapshot(ncells=nc, block=32 if nc % 32 == 0 else 16, extent=32.0, seed=0, dtype=np.float32)
         model = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"],
                                               arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"],
                                               CFG2["bhspin"], fluid_gamma=arr["fluid_gamma"], storage=RENDER_STORAGE)
         del arr
-    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nccl_init_ms = multigpu.warm_communicator()      # communicator start-up, reported on its own
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t_setup = time.perf_counter()
-    b0.record()
     model = multigpu.replicate_snapshot(model)       # rank 0: upload of the interior arrays + ghost fill / repack kernel
-    b1.record()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t_setup = 1e3 * (time.perf_counter() - t_setup)
-    bcast_ms = b0.elapsed_time(b1)
+    rep = model.replication_timing
+    bcast_ms = rep["broadcast"]
     incl = WEAK_INCLINATIONS[rank % len(WEAK_INCLINATIONS)]
     res = args.res
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -467,13 +557,22 @@ def render_leg(args, rank, world, dev):
                 dist.barrier()
             if it >= 1:
                 st.append(e0.elapsed_time(e1))
+        same, worst = None, None
         if world > 1:
-            fl = float(shared.local_view()[1].sum()) if rank == 0 else 0.0
+            fl = 0.0
+            if rank == 0:       # the split image against the same frame rendered by rank 0 alone, pixel for pixel
+                got = shared.local_view()[1]
+                alone = images.render(model, camera_inclination=CFG2["inclination"], resolution=sres,
+                                      observing_frequencies=(230e9,))
+                same = bool(torch.equal(got, alone))
+                worst = float((got - alone).abs().max())
+                fl = float(got.sum())
+                del alone
             dist.barrier()
             shared.close()
         else:
             fl = float(out.sum())
-        return float(np.mean(st)), fl
+        return float(np.mean(st)), fl, same, worst
 
     # The only timing the reference publishes for this path (demos/grmhd_detailed.ipynb cells 10-11, hardware not
     # stated): get_fluid_scalars_from_geodesics on the trajectories of a 160x160 image, 456 meshblocks: 31.8 s for
@@ -531,8 +630,8 @@ def render_leg(args, rank, world, dev):
         torch.cuda.synchronize()
         other["cfg3_torus_512"] = {"call": "fused render of the analytic thin torus, 512x512 at 230 GHz", "ms": e0.elapsed_time(e1),
                                    "image_sum": float(timg.sum())}
-    strong, flux = strong_leg(res, 3) if world > 1 else (0.0, 0.0)
-    strong_big, flux_big = strong_leg(args.strong_res, 2) if args.strong_res > 0 else (0.0, 0.0)
+    strong, flux, same, worst = strong_leg(res, 3) if world > 1 else (0.0, 0.0, None, None)
+    strong_big, flux_big, same_big, worst_big = strong_leg(args.strong_res, 2) if args.strong_res > 0 else (0.0, 0.0, None, None)
     t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong, bcast_ms, strong_big], dtype=torch.float64, device=dev)
     w = torch.tensor([float(counters[0]), float(counters[1])], dtype=torch.float64, device=dev)
     if world > 1:
@@ -546,6 +645,7 @@ def render_leg(args, rank, world, dev):
            "ray_steps_per_s": steps / (ms * 1e-3),
            "sampling_algorithmic_GBps": samples * (256 if model.storage == "f32" else 512) / (ms * 1e-3) / 1e9,
            "snapshot_bytes": model.snapshot_bytes(), "snapshot_setup_ms": t_setup,
+           "snapshot_setup_phases_ms": {k: rep[k] for k in ("host_prep", "upload", "ghost_fill")},
            "snapshot_setup_note": "host interior arrays -> device snapshot (upload + fused ghost-fill/repack kernel"
                                   + (" + NCCL broadcast" if world > 1 else "") + "), outside the render time",
            "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
@@ -556,13 +656,26 @@ def render_leg(args, rank, world, dev):
     if args.strong_res > 0:
         out["strong_scaling_large_image"] = {"resolution": args.strong_res, "ms": float(t[4]), "image_sum": flux_big,
                                              "note": "ONE cfg5-sized frame rendered by all ranks together"}
+        if same_big is not None:
+            out["strong_scaling_large_image"].update(identical=same_big, max_abs_diff=worst_big)
     if world > 1:
         out["strong_scaling_single_image_ms"] = float(t[2])
         out["strong_scaling_note"] = ("one i=60 deg image split over all ranks: shared atomic tile queue + in-kernel "
                                       "gather into rank 0 over NVLink (CUDA IPC), device-timed, max over ranks; at 1024^2 "
                                       "the floor is the serial latency of the longest photon-ring ray (~8 ms)")
         out["strong_image_sum"] = flux
-        out["snapshot_upload_repack_broadcast_ms"] = float(t[3])      # incl. rank 0 upload + repack and NCCL start-up
+        if same is not None:
+            out["strong_image_identical"] = same
+            out["strong_image_max_abs_diff"] = worst
+        out["snapshot_replication"] = {
+            "total_ms": t_setup, "host_prep_ms": rep["host_prep"], "upload_ms": rep["upload"],
+            "ghost_fill_ms": rep["ghost_fill"], "meta_ms": rep["meta"], "broadcast_ms": float(t[3]),
+            "wire_format": rep.get("wire_format"), "wire_bytes": rep["wire_bytes"],
+            "broadcast_GBps": rep["wire_bytes"] / (float(t[3]) * 1e-3) / 1e9 if float(t[3]) > 0 else None,
+            "nccl_init_ms": nccl_init_ms,
+            "note": "total = wall time on rank 0 from host arrays to a usable snapshot on every rank (max over ranks for "
+                    "broadcast_ms); the communicator was created beforehand by one tiny all-reduce + broadcast "
+                    "(nccl_init_ms, NOT part of total_ms)"}
     return out
 
 

@@ -29,6 +29,7 @@ SIGNATURES = {
     "mk_integrate": "idllpddpppppl" "pp",
     "mk_fill_frozen_rows": "ppppllp",
     "mk_integrate_paged": "idllpdd" "ppp" "pppp" "l" "pp" "p",
+    "mk_integrate_shared": "idllpdd" "ppp" "pppp" "l" "pp" "pp" "l" "p",
     "mk_paged_gather": "ppppp" "lll" "ppp",
     "mk_radius_cal": "dpllpp",
     "mk_rhs": "idplpp",
@@ -36,6 +37,7 @@ SIGNATURES = {
     "mk_metric": "idplppp",
     "mk_snapshot_create": "llllpppppppppipp",
     "mk_snapshot_create_from_interiors": "llll" "pipii" "ppp" "ppppppp" "i" "ppp",
+    "mk_upload_pageable": "pplip",
     "mk_snapshot_unpack": "pppp",
     "mk_snapshot_create_torus": "pp",
     "mk_snapshot_destroy": "p",

@@ -116,6 +116,7 @@ extern "C" int mk_integrate(int metric_id, double bhspin, long N, long npx, cons
     A.S = S; A.dt = dt; A.nrows = S ? nrows : 0;
     A.queue = queue_counter(stream, 0);
     if (!A.queue) return 1;
+    A.ray_order = nullptr; A.page_id_offset = 0;
     A.total_steps = total_steps;
     A.pages = nullptr; A.page_next = nullptr; A.page_first = nullptr; A.page_counter = nullptr;
     A.max_pages = 0; A.overflow = nullptr;
@@ -166,31 +167,60 @@ extern "C" int mk_fill_frozen_rows(double* S, double* dt, const double* final_st
 // ---- paged (single-pass, ragged) trajectory dump ------------------------------------------------------
 extern "C" int mk_page_rows(void) { return PAGE_SLOTS; }
 
+static int integrate_paged_impl(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
+                                double tol, double* final_state, int32_t* nsteps, double* r_last, double* pages,
+                                int32_t* page_next, int32_t* page_first, unsigned int* page_counter, long max_pages,
+                                int32_t* overflow, unsigned long long* total_steps, unsigned int* queue,
+                                const int32_t* ray_order, long page_id_offset, cudaStream_t stream)
+{
+    MK_REQUIRE(npx >= 0 && N >= 0 && N < (1L << 31) - 2, "npx / N out of range");
+    MK_REQUIRE(npx < (1L << 31) - 64, "more than 2^31 rays per launch");
+    MK_REQUIRE(pages && page_next && page_first && page_counter && overflow, "null page-store pointer");
+    MK_REQUIRE(max_pages > 0 && max_pages < (1L << 31), "max_pages out of range");
+    MK_REQUIRE(page_id_offset >= 0 && page_id_offset + max_pages < (1L << 31), "page_id_offset out of range");
+    MK_REQUIRE(npx == 0 || s0 != nullptr, "s0 is null");
+    MK_REQUIRE(div != 0.0, "div must be non-zero");
+    if (npx == 0) return 0;
+    if (N == 0) {                                          // no rows, no pages
+        MK_REQUIRE(!queue && !ray_order, "N == 0 is not supported with a shared queue");
+        return launch_zero_steps(bhspin, s0, npx, final_state, nsteps, r_last, stream);
+    }
+    IntegrateArgs A;
+    A.s0 = s0; A.npx = npx; A.N = (int)N;
+    A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol;
+    A.final_state = final_state; A.nsteps = nsteps; A.r_last = r_last;
+    A.S = nullptr; A.dt = nullptr; A.nrows = 0;
+    A.queue = queue ? queue : queue_counter(stream, 0);
+    if (!A.queue) return 1;
+    A.ray_order = ray_order; A.page_id_offset = (int)page_id_offset;
+    A.total_steps = total_steps;
+    A.pages = pages; A.page_next = page_next; A.page_first = page_first; A.page_counter = page_counter;
+    A.max_pages = (unsigned)max_pages; A.overflow = overflow;
+    return dispatch_integrate(metric_id, bhspin, A, stream);
+}
+
 extern "C" int mk_integrate_paged(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
                                   double tol, double* final_state, int32_t* nsteps, double* r_last,
                                   double* pages, int32_t* page_next, int32_t* page_first,
                                   unsigned int* page_counter, long max_pages, int32_t* overflow,
                                   unsigned long long* total_steps, void* stream_)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    MK_REQUIRE(npx >= 0 && N >= 0 && N < (1L << 31) - 2, "npx / N out of range");
-    MK_REQUIRE(pages && page_next && page_first && page_counter && overflow, "null page-store pointer");
-    MK_REQUIRE(max_pages > 0 && max_pages < (1L << 31), "max_pages out of range");
-    MK_REQUIRE(npx == 0 || s0 != nullptr, "s0 is null");
-    MK_REQUIRE(div != 0.0, "div must be non-zero");
-    if (npx == 0) return 0;
-    if (N == 0) return launch_zero_steps(bhspin, s0, npx, final_state, nsteps, r_last, stream);   // no rows, no pages
-    IntegrateArgs A;
-    A.s0 = s0; A.npx = npx; A.N = (int)N;
-    A.rule.div = div; A.rule.inv_div = 1.0 / div; A.rule.tol = tol;
-    A.final_state = final_state; A.nsteps = nsteps; A.r_last = r_last;
-    A.S = nullptr; A.dt = nullptr; A.nrows = 0;
-    A.queue = queue_counter(stream, 0);
-    if (!A.queue) return 1;
-    A.total_steps = total_steps;
-    A.pages = pages; A.page_next = page_next; A.page_first = page_first; A.page_counter = page_counter;
-    A.max_pages = (unsigned)max_pages; A.overflow = overflow;
-    return dispatch_integrate(metric_id, bhspin, A, stream);
+    return integrate_paged_impl(metric_id, bhspin, N, npx, s0, div, tol, final_state, nsteps, r_last, pages, page_next,
+                                page_first, page_counter, max_pages, overflow, total_steps, nullptr, nullptr, 0,
+                                (cudaStream_t)stream_);
+}
+
+extern "C" int mk_integrate_shared(int metric_id, double bhspin, long N, long npx, const double* s0, double div,
+                                   double tol, double* final_state, int32_t* nsteps, double* r_last,
+                                   double* pages, int32_t* page_next, int32_t* page_first,
+                                   unsigned int* page_counter, long max_pages, int32_t* overflow,
+                                   unsigned long long* total_steps, unsigned int* queue, const int32_t* ray_order,
+                                   long page_id_offset, void* stream_)
+{
+    MK_REQUIRE(queue != nullptr, "queue is null (use mk_integrate_paged for a private queue)");
+    return integrate_paged_impl(metric_id, bhspin, N, npx, s0, div, tol, final_state, nsteps, r_last, pages, page_next,
+                                page_first, page_counter, max_pages, overflow, total_steps, queue, ray_order,
+                                page_id_offset, (cudaStream_t)stream_);
 }
 
 namespace mk {

@@ -32,7 +32,9 @@ struct IntegrateArgs {
     double* S;             // dump: (nrows, npx, 8) or null
     double* dt;            // dump: (nrows, npx)
     long nrows;
-    unsigned int* queue;   // zero-initialised ray counter
+    unsigned int* queue;   // zero-initialised ray counter; may live in a peer GPU's memory (one queue for all GPUs)
+    const int* ray_order;  // optional: queue position q -> ray index (scheduling order; results stay indexed by ray)
+    int page_id_offset;    // added to the page numbers stored in page_first (rank * pool size in a multi-GPU job)
     unsigned long long* total_steps;  // optional global sum of accepted steps
     // paged dump (single pass, ragged).  Each WARP appends to its own log: in every loop iteration the active
     // lanes write their row into the same slot, so one slot is 32 x 64 B = 2 KB of contiguous state (fully
@@ -49,6 +51,10 @@ struct IntegrateArgs {
 };
 
 constexpr int PAGE_SLOTS = 16;
+// Rays are taken from the queue in chunks of QUEUE_CHUNK positions per warp, and the NEXT chunk is requested while the
+// current one is being consumed: the atomic's round trip (a few microseconds when the counter sits in a peer GPU's
+// memory across NVLink) overlaps the RK4 steps in between instead of stalling the warp at every refill.
+constexpr int QUEUE_CHUNK = 16;
 constexpr int PAGE_DOUBLES = PAGE_SLOTS * 32 * 9;
 enum { MODE_FINAL = 0, MODE_PADDED = 1, MODE_PAGED = 2 };
 
@@ -67,9 +73,17 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
     int wpage = -1, wslot = 0, my_slot = 0;    // warp-uniform log position (MODE_PAGED)
     const unsigned lane = threadIdx.x & 31u;
     bool drained = false;           // queue exhausted (warp-uniform)
+    long cur = 0, cur_end = 0;      // the warp's private range of queue positions (warp-uniform)
+    unsigned nxt = 0;               // base of the prefetched chunk (meaningful in lane 0 while have_next)
+    bool have_next = false;
     LaneRay L;
     L.ray = -1; L.dt = 0.0; L.r_cur = 0.0; L.r_prev = 0.0; L.best_dt = 0.0; L.r_before_best = 0.0; L.it = 0; L.best_idx = -1;
     unsigned long long my_steps = 0;
+
+    auto request_chunk = [&]() {
+        if (lane == 0) nxt = atomicAdd_system(A.queue, (unsigned)QUEUE_CHUNK);
+        have_next = true;
+    };
 
     // One loop iteration of the reference's scan for every lane of the warp: refill idle lanes into (s, cache),
     // take one step of the active lanes from (s, cache) into (sn, cn).  Returns false when the warp is done.
@@ -77,31 +91,39 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
     // the 8-vector and its cache (the loop-carried moves were ~8 % of the issued instructions).
     auto iteration = [&](double (&s)[8], typename Metric::Cache& cache, double (&sn)[8],
                          typename Metric::Cache& cn) -> bool {
-        // ---- refill idle lanes from the queue ----
+        // ---- refill idle lanes from the warp's private range, topping it up from the queue ----
         unsigned idle = __ballot_sync(FULL_MASK, L.ray < 0);
         if (idle) {
-            if (!drained) {
-                int cnt = __popc(idle);
-                unsigned base = 0;
-                int leader = __ffs(idle) - 1;
-                if ((int)lane == leader) base = atomicAdd(A.queue, (unsigned)cnt);
-                base = __shfl_sync(FULL_MASK, base, leader);
-                if ((long)base + cnt >= A.npx) drained = true;
-                if (L.ray < 0) {
-                    long idx = (long)base + __popc(idle & ((1u << lane) - 1u));
-                    if (idx < A.npx) {
-                        L.ray = idx;
-                        const double4* p = reinterpret_cast<const double4*>(A.s0 + idx * 8);
-                        double4 lo = p[0], hi = p[1];
-                        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
-                        s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
-                        L.r_cur = g.radius(s, cache);
-                        L.dt = A.rule(L.r_cur);
-                        L.r_prev = L.r_cur;
-                        L.it = 0; L.best_idx = -1; L.best_dt = -1.0e300; L.r_before_best = L.r_cur;
-                    }
+            int need = __popc(idle);
+            const int my_rank = __popc(idle & ((1u << lane) - 1u));     // position among the idle lanes
+            int given = 0;
+            while (need > 0 && !drained) {
+                if (cur == cur_end) {
+                    if (!have_next) request_chunk();
+                    const unsigned b = __shfl_sync(FULL_MASK, nxt, 0);   // waits for the atomic only if still in flight
+                    have_next = false;
+                    if ((long)b >= A.npx) { drained = true; break; }
+                    cur = (long)b;
+                    cur_end = ((long)b + QUEUE_CHUNK < A.npx) ? (long)b + QUEUE_CHUNK : A.npx;
                 }
+                const int avail = (int)(cur_end - cur);
+                const int take = need < avail ? need : avail;
+                if (L.ray < 0 && my_rank >= given && my_rank < given + take) {
+                    const long q = cur + (my_rank - given);
+                    const long idx = A.ray_order ? (long)A.ray_order[q] : q;
+                    L.ray = idx;
+                    const double4* p = reinterpret_cast<const double4*>(A.s0 + idx * 8);
+                    double4 lo = p[0], hi = p[1];
+                    s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+                    s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+                    L.r_cur = g.radius(s, cache);
+                    L.dt = A.rule(L.r_cur);
+                    L.r_prev = L.r_cur;
+                    L.it = 0; L.best_idx = -1; L.best_dt = -1.0e300; L.r_before_best = L.r_cur;
+                }
+                cur += take; given += take; need -= take;
             }
+            if (!have_next && !drained && cur_end - cur <= QUEUE_CHUNK / 2) request_chunk();
             if (__ballot_sync(FULL_MASK, L.ray >= 0) == 0) return false;
         }
         const bool act = L.ray >= 0;
@@ -126,7 +148,7 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
             my_slot = wslot;
             wslot = (wslot + 1) & (PAGE_SLOTS - 1);
             if (act && L.it == 0) {
-                A.page_first[2 * L.ray] = wpage;
+                A.page_first[2 * L.ray] = wpage < 0 ? -1 : wpage + A.page_id_offset;
                 A.page_first[2 * L.ray + 1] = my_slot * 32 + (int)lane;
             }
         }

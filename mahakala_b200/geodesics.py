@@ -364,8 +364,13 @@ class TrajectoryStore:
         return DeviceArray.wrap(S), DeviceArray.wrap(dt)
 
 
-def integrate_paged(N, s0, div, tol, bhspin, store=None):
-    """Single-pass trajectory dump of a whole bundle into a ``TrajectoryStore`` (see there)."""
+def integrate_paged(N, s0, div, tol, bhspin, store=None, queue=None, ray_order=None, results=None, page_id_offset=0):
+    """Single-pass trajectory dump of a whole bundle into a ``TrajectoryStore`` (see there).
+
+    ``queue`` (a device pointer, possibly in a peer GPU's memory) makes this launch one participant of a multi-GPU
+    job that shares ONE dynamic ray queue (``mahakala_b200.multigpu.integrate_distributed``): ``ray_order`` (int32
+    tensor) is the order in which rays are handed out, ``results`` = (final, nsteps, r_last, page_first) pointers in
+    the gathering GPU's memory, ``page_id_offset`` tags the page numbers with their owner."""
     s = as_device(s0)
     npx = s.shape[0]
     if store is None:
@@ -373,6 +378,13 @@ def integrate_paged(N, s0, div, tol, bhspin, store=None):
     if store.npx != npx or store.N != int(N):
         raise ValueError("TrajectoryStore was allocated for a different bundle")
     store.reset()                 # a reused store starts from an empty page pool (page counter, overflow flag, total)
+    if queue is not None:
+        final, nsteps, r_last, page_first = results if results is not None else (store.final, store.nsteps,
+                                                                                 store.r_last, store.page_first)
+        _cabi.call("mk_integrate_shared", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
+                   final, nsteps, r_last, store.pages, store.page_next, page_first, store.ctrl[0:1], store.max_pages,
+                   store.ctrl[1:2], store.total_steps, queue, ray_order, int(page_id_offset), stream_ptr())
+        return store
     _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
                store.final, store.nsteps, store.r_last, store.pages, store.page_next, store.page_first,
                store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps, stream_ptr())

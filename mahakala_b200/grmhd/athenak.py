@@ -420,6 +420,9 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         dev = require_gpu()
         if self._snap is not None and self._snap_device == dev:
             return self._snap
+        import time
+        torch = __import__('torch')
+        t_start = time.perf_counter()
         nmb, _, nk2, nj2, ni2 = self._block_shape
         if self._uov is None and fill:
             raise ValueError("a replica model has no host data: fill it with multigpu.replicate_snapshot")
@@ -453,14 +456,16 @@ class AthenakFluidModel(DeviceSampledFluidModel):
             c_gi = (ctypes.c_double * 3)(*[float(q) for q in ginv])
         else:
             d_grid, c_gn, c_g0, c_gi = None, None, None, None
+        t_prep = t_up = time.perf_counter()
         if on_device:
-            torch = __import__('torch')
             src_f32 = self._uov.dtype == np.float32 and self._B.dtype == np.float32
             dt = torch.float32 if src_f32 else torch.float64
             d_uov, d_B = self._upload_meshblocks(self._uov, dtype=dt), self._upload_meshblocks(self._B, dtype=dt)
             loc = np.ascontiguousarray(self.LogicalLocations, dtype=np.int32)
             lev = np.ascontiguousarray(self.Levels, dtype=np.int32)
             stored = ctypes.c_int(0)
+            torch.cuda.current_stream().synchronize()
+            t_up = time.perf_counter()
             _cabi.call("mk_snapshot_create_from_interiors", nmb, nk2 - 2, nj2 - 2, ni2 - 2, d_uov,
                        int(self._uov.shape[0]), d_B, int(self._B.shape[0]), 1 if src_f32 else 0, pidx,
                        loc.ctypes.data, lev.ctypes.data, d_geom, d_grid, c_gn, c_g0, c_gi, bbox_lo, bbox_hi,
@@ -475,6 +480,12 @@ class AthenakFluidModel(DeviceSampledFluidModel):
             _cabi.call("mk_snapshot_create", nmb, nk2 - 2, nj2 - 2, ni2 - 2, d_mb, pidx, d_geom, d_grid, c_gn, c_g0,
                        c_gi, bbox_lo, bbox_hi, 1 if storage == 'f32' else 0, ctypes.byref(handle), stream_ptr())
             del d_mb
+        torch.cuda.current_stream().synchronize()
+        t_end = time.perf_counter()
+        # phases of the set-up in ms: host-side geometry / lookup tables, upload of the cell arrays, kernel
+        # (ghost fill + repack; includes the padded-array upload when ghost_fill='host')
+        self.setup_timing = dict(host_prep=1e3 * (t_prep - t_start), upload=1e3 * (t_up - t_prep),
+                                 ghost_fill=1e3 * (t_end - t_up))
         self._snap = handle
         self._snap_device = dev
         self.storage = storage
@@ -483,9 +494,9 @@ class AthenakFluidModel(DeviceSampledFluidModel):
 
     @staticmethod
     def _upload_meshblocks(amb, chunk_bytes=256 << 20, dtype=None):
-        """Host -> device copy of a large block array.  Large arrays are copied slice by slice from pageable
-        memory (the driver pipelines them through its own staging buffers): pinning a multi-GB NumPy array first
-        costs more than the copy itself."""
+        """Host -> device copy of a large block array from pageable memory (``mk_upload_pageable``): pinning a
+        multi-GB NumPy array first costs more than the copy itself, and the driver's own staging of a pageable
+        cudaMemcpy runs on one thread."""
         torch = __import__('torch')
         dtype = dtype or torch.float64
         if amb.nbytes <= (16 << 20):
@@ -493,10 +504,8 @@ class AthenakFluidModel(DeviceSampledFluidModel):
         np_dtype = {torch.float64: np.float64, torch.float32: np.float32}[dtype]
         h = np.ascontiguousarray(amb, dtype=np_dtype).reshape(-1)
         d = empty(amb.shape, dtype=dtype)
-        flat = d.reshape(-1)
-        per = max(1, chunk_bytes // h.itemsize)
-        for b0 in range(0, h.size, per):
-            flat[b0:b0 + per].copy_(torch.from_numpy(h[b0:b0 + per]), non_blocking=True)
+        # native pipelined uploader: host threads fill one pinned staging buffer while the DMA engine empties the other
+        _cabi.call("mk_upload_pageable", d, h.ctypes.data, int(h.nbytes), 0, stream_ptr())
         return d
 
     def snapshot_bytes(self):

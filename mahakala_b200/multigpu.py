@@ -52,7 +52,10 @@ def static_assignment(npatches, rank, world):
 def combine_static(local_image, dst=0, group=None):
     """Sum the disjoint per-rank images onto ``dst`` (in place).  Works on CUDA (NCCL) and CPU (gloo)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.reduce(local_image, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        if local_image.is_cuda and dist.get_backend(group) == "gloo":
+            dist.all_reduce(local_image, op=dist.ReduceOp.SUM, group=group)     # gloo has no CUDA reduce
+        else:
+            dist.reduce(local_image, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return local_image
 
 
@@ -76,14 +79,18 @@ def tensor_from_pointer(ptr, nbytes, device):
     return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
 
 
-class SharedImage:
-    """Rank-``owner`` buffer [256 B queue counter | image (nfreq, npx) f64] mapped by every rank."""
+HEADER_BYTES = 512          # queue counters, 128 B apart (0: patch / ray queue, 128: photon-ring patch queue)
 
-    def __init__(self, nfreq, npx, owner=0):
+
+class SharedBuffer:
+    """``nbytes`` of rank-``owner`` device memory (zero-filled) mapped into every rank with CUDA IPC.  The first
+    ``HEADER_BYTES`` hold the queue counters that the persistent kernels of all GPUs advance with system-scope
+    atomics over NVLink; the payload behind them receives the results (the gather is fused into the kernels)."""
+
+    def __init__(self, payload_bytes, owner=0):
         rank, _ = world()
         self.owner, self.rank = owner, rank
-        self.nfreq, self.npx = nfreq, npx
-        self.nbytes = 256 + 8 * nfreq * npx
+        self.nbytes = HEADER_BYTES + int(payload_bytes)
         handle = (ctypes.c_ubyte * 64)()
         ptr = ctypes.c_void_p()
         box = [None]
@@ -97,19 +104,18 @@ class SharedImage:
             _cabi.call("mk_ipc_open", handle, ctypes.byref(ptr))
         self.ptr = ptr.value
         self.queue_ptr = self.ptr
-        self.image_ptr = self.ptr + 256
+        self.ring_queue_ptr = self.ptr + 128
+        self.payload_ptr = self.ptr + HEADER_BYTES
 
-    def local_view(self):
-        """(counter tensor, image tensor) on the owner rank."""
+    def _raw(self):
         assert self.rank == self.owner
-        dev = torch.device("cuda", torch.cuda.current_device())
-        raw = tensor_from_pointer(self.ptr, self.nbytes, dev)
-        return raw[:4].view(torch.int32), raw[256:].view(torch.float64).view(self.nfreq, self.npx)
+        return tensor_from_pointer(self.ptr, self.nbytes, torch.device("cuda", torch.cuda.current_device()))
 
     def reset(self):
+        """Zero the queue counters (owner rank; call between jobs, followed by a barrier)."""
         if self.rank == self.owner:
-            q, _ = self.local_view()
-            q.zero_()
+            self._raw()[:HEADER_BYTES].zero_()
+            torch.cuda.synchronize()        # a host-side (gloo) barrier after this must imply "counters are zero"
 
     def close(self):
         if self.ptr:
@@ -117,40 +123,174 @@ class SharedImage:
             self.ptr = 0
 
 
+class SharedImage(SharedBuffer):
+    """[queue counters | image (nfreq, npx) f64] in rank ``owner``'s memory, mapped by every rank."""
+
+    def __init__(self, nfreq, npx, owner=0):
+        self.nfreq, self.npx = nfreq, npx
+        super().__init__(8 * nfreq * npx, owner)
+        self.image_ptr = self.payload_ptr
+
+    def local_view(self):
+        """(counter tensor, image tensor) on the owner rank."""
+        raw = self._raw()
+        return raw[:4].view(torch.int32), raw[HEADER_BYTES:].view(torch.float64).view(self.nfreq, self.npx)
+
+
+class SharedRays(SharedBuffer):
+    """[queue counters | final (n, 8) f64 | r_last (n) f64 | nsteps (n) i32 | page_first (n, 2) i32]: the per-ray
+    results of a bundle integrated by all ranks together, gathered in rank ``owner``'s memory by the kernels."""
+
+    def __init__(self, n, owner=0):
+        self.n = int(n)
+        super().__init__(self.n * (64 + 8 + 4 + 8), owner)
+        self.final_ptr = self.payload_ptr
+        self.r_last_ptr = self.final_ptr + 64 * self.n
+        self.nsteps_ptr = self.r_last_ptr + 8 * self.n
+        self.page_first_ptr = self.nsteps_ptr + 4 * self.n
+
+    def results(self):
+        return self.final_ptr, self.nsteps_ptr, self.r_last_ptr, self.page_first_ptr
+
+    def local_views(self):
+        """dict of tensors (final, r_last, nsteps, page_first) on the owner rank."""
+        raw, n, o = self._raw(), self.n, HEADER_BYTES
+        return {"final": raw[o:o + 64 * n].view(torch.float64).view(n, 8),
+                "r_last": raw[o + 64 * n:o + 72 * n].view(torch.float64),
+                "nsteps": raw[o + 72 * n:o + 76 * n].view(torch.int32),
+                "page_first": raw[o + 76 * n:o + 84 * n].view(torch.int32).view(n, 2)}
+
+
+def longest_first_ray_order(res, frames=1):
+    """Queue order for ``frames`` bundles of res x res grid-camera rays stored back to back: pixels by distance from
+    the image centre (the long photon-ring rays sit a few M from it for any spin and inclination), frames interleaved,
+    so that every long ray of every frame starts early and the short outer rays fill the tail of the queue.  Returns an
+    int32 NumPy array: queue position -> frame * res^2 + ix * res + iy."""
+    c = (np.arange(res) + 0.5) - res / 2.0
+    rho = np.hypot(c[:, None], c[None, :]).reshape(-1)
+    pix = np.argsort(rho, kind="stable").astype(np.int64)
+    order = (np.arange(frames, dtype=np.int64)[None, :] * (res * res) + pix[:, None]).reshape(-1)
+    return order.astype(np.int32)
+
+
+def integrate_distributed(N, s0, div, tol, bhspin, store, shared, ray_order=None):
+    """Integrate ONE bundle ``s0`` (n, 8), resident on every rank, with all ranks together (trajectory-dump mode).
+
+    All GPUs pull rays from the one queue in ``shared`` (a ``SharedRays``) and store each ray's final state, step
+    count, classifier radius and page locator straight into the owner's memory over NVLink; trajectories are logged
+    in each rank's own ``store`` (``page_first[:, 0] // store.max_pages`` names the rank that holds a ray).  No
+    collective on the data path; the two barriers only fence the queue reset.  Returns the owner's result views
+    (``SharedRays.local_views()``) on the owner rank, None elsewhere."""
+    from . import geodesics as geo
+    rank, nranks = world()
+    shared.reset()
+    if nranks > 1:
+        dist.barrier()
+    geo.integrate_paged(N, s0, div, tol, bhspin, store=store, queue=shared.queue_ptr, ray_order=ray_order,
+                        results=shared.results(), page_id_offset=rank * store.max_pages)
+    torch.cuda.synchronize()
+    if nranks > 1:
+        dist.barrier()
+    return shared.local_views() if rank == shared.owner else None
+
+
 # ---------------------------------------------------------------------------------------------------
 # snapshot replication
 # ---------------------------------------------------------------------------------------------------
-def replicate_snapshot(model=None, src=0):
-    """Give every rank the device snapshot held by rank ``src``.
-
-    Rank ``src`` passes its ``AthenakFluidModel``; the other ranks may pass ``None`` (they receive the mesh
-    geometry with ``broadcast_object_list`` and build a geometry-only replica) or a model of the same shape.
-    Rank ``src`` repacks its host arrays once; the cell array then travels to all other ranks with ONE NCCL
-    broadcast over NVLink.  Returns the (replica) model on every rank.
-    """
-    from .grmhd.athenak import AthenakFluidModel
+def warm_communicator():
+    """Create the communicator and its channels (first-collective cost of NCCL: a few hundred ms) with one tiny
+    all-reduce and one tiny broadcast, so that later timings measure the collectives and not NCCL start-up.
+    Returns the milliseconds it took."""
+    import time
     rank, nranks = world()
     if nranks == 1:
-        model.snapshot()
-        return model
-    meta = [None]
-    if rank == src:
-        model.snapshot()
-        meta = [model.replica_meta()]
-    dist.broadcast_object_list(meta, src=src)
-    if rank != src:
-        if model is None:
-            model = AthenakFluidModel.replica(**meta[0])
-        else:
-            model._storage = meta[0]["storage"]
-        model.snapshot(fill=False)
+        return 0.0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t0 = time.perf_counter()
+    x = torch.ones(1024, dtype=torch.float32, device=dev)
+    dist.all_reduce(x)
+    dist.broadcast(x, src=0)
+    torch.cuda.synchronize()
+    return 1e3 * (time.perf_counter() - t0)
+
+
+def _cells_tensor(model):
     cells = ctypes.c_void_p()
     nbytes = ctypes.c_long()
     _cabi.call("mk_snapshot_cells", model.snapshot(), ctypes.byref(cells), ctypes.byref(nbytes))
     dev = torch.device("cuda", torch.cuda.current_device())
-    t = tensor_from_pointer(cells.value, nbytes.value, dev)
-    dist.broadcast(t, src=src)
+    return tensor_from_pointer(cells.value, nbytes.value, dev)
+
+
+def replicate_snapshot(model=None, src=0, wire="auto"):
+    """Give every rank the device snapshot held by rank ``src``.
+
+    Rank ``src`` passes its ``AthenakFluidModel``; the other ranks may pass ``None`` (they receive the mesh
+    geometry with ``broadcast_object_list`` and build a geometry-only replica) or a model of the same shape.
+    Rank ``src`` uploads its interior arrays and runs the ghost-fill / repack kernel once; the cell array then travels
+    to all other ranks with ONE NCCL broadcast over NVLink.  ``wire``: 'f64' sends float64 cells as they are, 'f32'
+    / 'auto' send them as float32 when that is lossless (AthenaK writes float32, and so are its ghost-zone averages
+    checked on the device) -- half the bytes on the wire, expanded again by the receivers; float32 snapshots always
+    travel as stored.  Returns the (replica) model on every rank; ``model.replication_timing`` holds the phases in
+    ms: host_prep / upload / ghost_fill (rank ``src``; zero elsewhere), meta (geometry exchange), broadcast (device
+    time of the collective, incl. the wire conversion), wire_bytes, effective broadcast GB/s.
+    """
+    import time
+    from .grmhd.athenak import AthenakFluidModel
+    rank, nranks = world()
+    if nranks == 1:
+        model.snapshot()
+        model.replication_timing = dict(getattr(model, "setup_timing", {}), meta=0.0, broadcast=0.0, wire_bytes=0)
+        return model
+    dev = torch.device("cuda", torch.cuda.current_device())
+    meta = [None]
+    t64 = None
+    if rank == src:
+        model.snapshot()
+        m = model.replica_meta()
+        m["wire"] = model.storage
+        if model.storage == "f64" and wire in ("auto", "f32"):
+            t64 = _cells_tensor(model).view(torch.float64)
+            lossless = bool(torch.equal(t64.to(torch.float32).to(torch.float64), t64))
+            if lossless:
+                m["wire"] = "f32"
+            elif wire == "f32":
+                raise ValueError("float32 wire format requested but the cells are not float32-representable")
+        meta = [m]
+    t0 = time.perf_counter()
+    dist.broadcast_object_list(meta, src=src)
+    if rank != src:
+        if model is None:
+            kw = dict(meta[0])
+            kw.pop("wire")
+            model = AthenakFluidModel.replica(**kw)
+        else:
+            model._storage = meta[0]["storage"]
+        model.snapshot(fill=False)
     torch.cuda.synchronize()
+    t_meta = 1e3 * (time.perf_counter() - t0)
+    t = _cells_tensor(model)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if meta[0]["wire"] == "f32" and meta[0]["storage"] == "f64":
+        t64 = t.view(torch.float64)
+        w = t64.to(torch.float32) if rank == src else torch.empty(t64.shape, dtype=torch.float32, device=dev)
+        dist.broadcast(w, src=src)
+        if rank != src:
+            t64.copy_(w)                      # float32 -> float64 is exact
+        wire_bytes = w.numel() * 4
+        del w
+    else:
+        dist.broadcast(t, src=src)
+        wire_bytes = t.numel()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    base = getattr(model, "setup_timing", {}) if rank == src else {}
+    model.replication_timing = dict(host_prep=base.get("host_prep", 0.0), upload=base.get("upload", 0.0),
+                                    ghost_fill=base.get("ghost_fill", 0.0), meta=t_meta, broadcast=ms,
+                                    wire_bytes=int(wire_bytes), wire_format=meta[0]["wire"],
+                                    broadcast_GBps=wire_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0)
     return model
 
 

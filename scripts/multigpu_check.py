@@ -1,22 +1,34 @@
 """torchrun --nproc-per-node N scripts/multigpu_check.py [res] [ncells]
-Checks that the distributed render (shared NVLink tile queue, and static + NCCL reduce) reproduces the
-single-GPU image bit for bit, and prints timings."""
+
+Checks that the multi-GPU paths reproduce the single-GPU results bit for bit and prints timings:
+  * the distributed render: shared NVLink tile queue with in-kernel gather, and static sharding + reduce;
+  * the distributed integration: one ray queue for all ranks, per-ray results gathered in rank 0's memory by the
+    kernels, trajectories paged where they are computed and found again through the rank-tagged page locator.
+MK_SAME_GPU=1 runs every rank on GPU 0 (gloo instead of NCCL, which refuses two ranks on one device): the queue
+counter and the result buffers are then CUDA-IPC mappings of the same device, i.e. exactly the code path of the
+multi-GPU run, and a single-GPU box can execute the test."""
 import os
 import sys
 import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
+import numpy as np
 import torch
 import torch.distributed as dist
-from mahakala_b200 import images, multigpu
+import mahakala_b200 as ma
+from mahakala_b200 import geodesics as geo, images, multigpu
 from mahakala_b200.grmhd import AthenakFluidModel
 from mahakala_b200.synthetic import make_synthetic_snapshot
 
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 nc = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-local = int(os.environ.get("LOCAL_RANK", "0"))
+same_gpu = os.environ.get("MK_SAME_GPU", "0") == "1"
+local = 0 if same_gpu else int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if same_gpu:
+    dist.init_process_group("gloo")
+else:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 m = None
 if rank == 0:
@@ -25,7 +37,7 @@ if rank == 0:
                                       arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.94,
                                       fluid_gamma=arr["fluid_gamma"], storage="f32")
 t0 = time.time()
-m = multigpu.replicate_snapshot(m)      # geometry-only replicas on the other ranks + one NCCL broadcast of the cells
+m = multigpu.replicate_snapshot(m)      # geometry-only replicas on the other ranks + one broadcast of the cells
 t_bcast = time.time() - t0
 kw = dict(resolution=res, observing_frequencies=(230e9, 345e9))
 ref = images.render(m, **kw) if rank == 0 else None
@@ -40,11 +52,48 @@ for mode in ("queue", "static"):
         out[mode] = 1e3 * (time.perf_counter() - t0)
     if rank == 0:
         same = bool(torch.equal(img, ref))
-        print(f"[{world} GPUs] mode={mode}: identical to single-GPU image: {same}; {out[mode]:.2f} ms (wall, incl. barriers)")
+        print(f"[{world} ranks] mode={mode}: identical to single-GPU image: {same}; {out[mode]:.2f} ms (wall, incl. barriers)")
         assert same
 if rank == 0:
     torch.cuda.synchronize(); t0 = time.perf_counter(); images.render(m, **kw); torch.cuda.synchronize()
     print(f"single GPU: {1e3 * (time.perf_counter() - t0):.2f} ms; snapshot broadcast {t_bcast * 1e3:.1f} ms; flux {float(ref.sum()):.6e}")
 dist.barrier()
 shared.close()
+
+# ---- distributed integration: `world` frames in one job ----
+a, N, tol = 0.94, 10000, 1e-4
+incl = [60.0, 17.0, 30.0, 80.0, 45.0, 70.0, 25.0, 52.0]
+npx = res * res
+s0_all = torch.cat([ma.initialize_geodesics_at_camera(a, incl[f % 8], 1000, -10, 10, res) for f in range(world)])
+order = torch.from_numpy(multigpu.longest_first_ray_order(res, world)).cuda()
+rays = multigpu.SharedRays(world * npx)
+store = geo.TrajectoryStore.allocate(world * npx, N, mem_fraction=0.2)
+for rep in range(2):
+    views = multigpu.integrate_distributed(N, s0_all, 40, tol, a, store, rays, ray_order=order)
+mine = torch.tensor([float(store.total_steps.item())], dtype=torch.float64, device="cpu" if same_gpu else "cuda")
+per_rank = [torch.zeros_like(mine) for _ in range(world)]
+dist.all_gather(per_rank, mine)
+if rank == 0:
+    alone = geo.TrajectoryStore.allocate(world * npx, N, mem_fraction=0.2)
+    geo.integrate_paged(N, s0_all, 40, tol, a, store=alone)
+    same = (torch.equal(views["final"], alone.final) and torch.equal(views["nsteps"], alone.nsteps)
+            and torch.equal(views["r_last"], alone.r_last))
+    owner = views["page_first"][:, 0] // store.max_pages
+    steps = [int(t.item()) for t in per_rank]
+    print(f"[{world} ranks] shared ray queue: identical to single-GPU integration: {same}; rays per rank "
+          f"{[int((owner == r).sum()) for r in range(world)]}, ray-steps per rank {steps}, total {sum(steps)} "
+          f"(single GPU: {int(alone.total_steps.item())})")
+    assert same and sum(steps) == int(alone.total_steps.item()) and int(owner.min()) >= 0 and int(owner.max()) < world
+    # trajectories of rank 0's own rays through the rank-tagged page locator: same rows as the single-GPU dump
+    mine_idx = torch.nonzero(owner == 0).flatten()[:64]
+    if mine_idx.numel():
+        store.page_first[mine_idx] = views["page_first"][mine_idx]          # page numbers of rank 0 carry offset 0
+        store.nsteps.copy_(views["nsteps"])
+        S, dt = store.padded(mine_idx.cpu().numpy())
+        Sa, dta = alone.padded(mine_idx.cpu().numpy())
+        traj_same = bool(torch.equal(S, Sa) and torch.equal(dt, dta))
+        print(f"[{world} ranks] trajectories of {mine_idx.numel()} rays held by rank 0: identical to the single-GPU dump: {traj_same}")
+        assert traj_same
+dist.barrier()
+rays.close()
 dist.destroy_process_group()
