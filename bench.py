@@ -231,9 +231,13 @@ def run_b200(args):
     mode = "trajectory dump (paged warp logs, single pass)"
     launches = [0]
     shared = None
+    from mahakala_b200 import multigpu
+    if world == 1:
+        # the same launch as the N > 1 job with N = 1: rays handed out longest first from a (here local) queue
+        order = torch.from_numpy(multigpu.longest_first_ray_order(res, 1)).to(dev)
+        local_queue = torch.zeros(64, dtype=torch.int32, device=dev)
     if world > 1:
         # BASELINE north_star split: ONE job of `world` frames, every GPU holds all bundles, rays come from one queue
-        from mahakala_b200 import multigpu
         frames = [WEAK_INCLINATIONS[f % len(WEAK_INCLINATIONS)] for f in range(world)]
         s0_all = torch.cat([ma.initialize_geodesics_at_camera(a, frames[f], CFG2["distance"], -CFG2["fov"] / 2,
                                                               CFG2["fov"] / 2, res) for f in range(world)])
@@ -247,10 +251,11 @@ def run_b200(args):
         if world > 1:
             geo.integrate_paged(CFG2["N"], s0_all, CFG2["div"], CFG2["tol"], a, store=job_store,
                                 queue=shared.queue_ptr, ray_order=order, results=shared.results(),
-                                page_id_offset=rank * job_store.max_pages)
+                                page_id_offset=rank << multigpu.PAGE_RANK_SHIFT, participants=world)
             launches[0] += 1
             return job_store.total_steps
-        out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)   # resets the store
+        out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store, queue=local_queue,
+                                  ray_order=order)                                        # resets the store
         launches[0] += 1
         return out.total_steps
 
@@ -260,10 +265,14 @@ def run_b200(args):
             barrier()
             shared.reset()
             barrier()
+        else:
+            local_queue.zero_()
 
     host_out = {"final": torch.empty((npx, 8), dtype=torch.float64, pin_memory=True),
                 "nsteps": torch.empty((npx,), dtype=torch.int32, pin_memory=True),
                 "r_last": torch.empty((npx,), dtype=torch.float64, pin_memory=True)}
+
+    e2e_order = torch.from_numpy(multigpu.longest_first_ray_order(res, 1)).to(dev)
 
     def step_e2e(chunks=None):
         chunks = E2E_CHUNKS if chunks is None else chunks
@@ -274,7 +283,8 @@ def run_b200(args):
             if chunks > 0:
                 geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=chunks)
             else:
-                geo.integrate_paged_host(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out)
+                geo.integrate_paged_host(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out,
+                                         ray_order=e2e_order)
             return int(host_out["nsteps"].sum())
         d = s0_host.to(dev, non_blocking=True)
         if store is not None:
@@ -336,7 +346,7 @@ def run_b200(args):
                       and torch.equal(views["r_last"][sl], alone.r_last))
                 same = same and ok
                 worst = max(worst, float((views["final"][sl] - alone.final).abs().max()))
-            owner = views["page_first"][:, 0] // job_store.max_pages
+            owner = views["page_first"][:, 0] >> multigpu.PAGE_RANK_SHIFT
             split = {"split_identical": bool(same), "max_abs_diff_final_state": worst,
                      "check": "final states, step counts and classifier radii of all frames gathered in rank 0's memory "
                               "by the shared-queue job, torch.equal against rank 0 integrating each frame alone",

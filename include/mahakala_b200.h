@@ -120,8 +120,9 @@ int mk_integrate_paged(int metric_id, double bhspin, long N, long npx, const dou
  * The same launch as one PARTICIPANT of a multi-GPU job (BASELINE north_star: "tiles handed out across the GPUs from
  * a dynamic queue ... gathered at the end").  Every GPU of the node runs this call on the same (npx, 8) bundle:
  *   queue        one zero-initialised u32 in the memory of ONE GPU, mapped by all others (mk_ipc_alloc / mk_ipc_open);
- *                warps take chunks of 16 queue positions with system-scope atomics over NVLink and request the next
- *                chunk while the current one is being integrated, so the round trip is never waited for;
+ *                warps take chunks of up to 32 queue positions with system-scope atomics over NVLink and request
+ *                the next chunk while the current one is being integrated, so the round trip is never waited for;
+ *                chunks shrink to single rays as the queue empties (participants = number of GPUs on the queue);
  *   ray_order    (npx,) int32 or NULL: queue position -> ray index.  Handing out the long rays (photon ring) first
  *                keeps the tail of the queue short; results stay indexed by ray;
  *   final_state, nsteps, r_last, page_first
@@ -136,7 +137,7 @@ int mk_integrate_shared(int metric_id, double bhspin, long N, long npx, const do
                         double* final_state, int32_t* nsteps, double* r_last, double* pages, int32_t* page_next,
                         int32_t* page_first, unsigned int* page_counter, long max_pages, int32_t* overflow,
                         unsigned long long* total_steps, unsigned int* queue, const int32_t* ray_order,
-                        long page_id_offset, void* stream);
+                        long page_id_offset, int participants, void* stream);
 int mk_paged_gather(const double* pages, const int32_t* page_next, const int32_t* page_first,
                     const int32_t* nsteps, const long* ray_idx, long nsel, long nrows, long N, double* S,
                     double* dt, void* stream);
@@ -193,7 +194,9 @@ int mk_snapshot_create_from_interiors(long nmb, long nk, long nj, long ni, const
                                       const double* bbox_lo, const double* bbox_hi, int store_mode,
                                       int* stored_f32, mk_snapshot** out, void* stream);
 /* Host -> device copy of a large PAGEABLE host array (the interior arrays a loader returns) through two pinned
-   staging buffers: host_threads (0 = up to 8) threads fill one buffer while the DMA engine empties the other.
+   staging buffers: host_threads (0 = up to 8) threads fill one buffer while the DMA engine empties the other;
+   host_threads < 0 pins the caller's pages in place instead (cudaHostRegister) and lets the DMA engine read them
+   directly -- no host-side copy -- falling back to staging when they cannot be pinned.
    Synchronous with respect to the host on return (the source may be freed); ordered on `stream`. */
 int mk_upload_pageable(void* dst_device, const void* src_host, long bytes, int host_threads, void* stream);
 /* inverse of the repack: cells -> the reference's self.all_meshblocks (nmb, 8, nk+2, nj+2, ni+2) float64

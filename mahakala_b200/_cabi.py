@@ -29,7 +29,7 @@ SIGNATURES = {
     "mk_integrate": "idllpddpppppl" "pp",
     "mk_fill_frozen_rows": "ppppllp",
     "mk_integrate_paged": "idllpdd" "ppp" "pppp" "l" "pp" "p",
-    "mk_integrate_shared": "idllpdd" "ppp" "pppp" "l" "pp" "pp" "l" "p",
+    "mk_integrate_shared": "idllpdd" "ppp" "pppp" "l" "pp" "pp" "li" "p",
     "mk_paged_gather": "ppppp" "lll" "ppp",
     "mk_radius_cal": "dpllpp",
     "mk_rhs": "idplpp",

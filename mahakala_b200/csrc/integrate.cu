@@ -17,10 +17,10 @@ namespace mk {
 #ifndef MK_PAGED_CTAS
 #define MK_PAGED_CTAS 3
 #endif
-template <class Metric, int MODE>
+template <class Metric, int MODE, bool SHARED = false>
 __global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : 4)) integrate_kernel(const Metric g, const IntegrateArgs A)
 {
-    integrate_body<Metric, MODE>(g, A);
+    integrate_body<Metric, MODE, SHARED>(g, A);
 }
 
 // Rows after a ray's frozen row repeat the frozen state with dt = 0 (the reference's scan keeps
@@ -77,7 +77,8 @@ template <class Metric>
 static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_t stream)
 {
     int per_sm = 0;
-    auto kern = A.pages ? integrate_kernel<Metric, MODE_PAGED>
+    const bool shared = A.chunk_div > 0;       // set by mk_integrate_shared (number of GPUs on the queue)
+    auto kern = A.pages ? (shared ? integrate_kernel<Metric, MODE_PAGED, true> : integrate_kernel<Metric, MODE_PAGED>)
                         : (A.S ? integrate_kernel<Metric, MODE_PADDED> : integrate_kernel<Metric, MODE_FINAL>);
     MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
     if (per_sm < 1) per_sm = 1;
@@ -86,7 +87,10 @@ static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_
     long need = (warps_needed + 3) / 4;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    kern<<<(unsigned)blocks, 128, 0, stream>>>(g, A);
+    IntegrateArgs B = A;
+    B.chunk_div = (int)(4 * 4 * blocks) * (shared ? A.chunk_div : 1);     // 4 x warps x participating GPUs
+    B.chunk_mul = (unsigned)(0x100000000ULL / (unsigned long long)B.chunk_div);
+    kern<<<(unsigned)blocks, 128, 0, stream>>>(g, B);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -116,7 +120,7 @@ extern "C" int mk_integrate(int metric_id, double bhspin, long N, long npx, cons
     A.S = S; A.dt = dt; A.nrows = S ? nrows : 0;
     A.queue = queue_counter(stream, 0);
     if (!A.queue) return 1;
-    A.ray_order = nullptr; A.page_id_offset = 0;
+    A.ray_order = nullptr; A.page_id_offset = 0; A.chunk_div = 0; A.chunk_mul = 0;
     A.total_steps = total_steps;
     A.pages = nullptr; A.page_next = nullptr; A.page_first = nullptr; A.page_counter = nullptr;
     A.max_pages = 0; A.overflow = nullptr;
@@ -171,7 +175,7 @@ static int integrate_paged_impl(int metric_id, double bhspin, long N, long npx, 
                                 double tol, double* final_state, int32_t* nsteps, double* r_last, double* pages,
                                 int32_t* page_next, int32_t* page_first, unsigned int* page_counter, long max_pages,
                                 int32_t* overflow, unsigned long long* total_steps, unsigned int* queue,
-                                const int32_t* ray_order, long page_id_offset, cudaStream_t stream)
+                                const int32_t* ray_order, long page_id_offset, int participants, cudaStream_t stream)
 {
     MK_REQUIRE(npx >= 0 && N >= 0 && N < (1L << 31) - 2, "npx / N out of range");
     MK_REQUIRE(npx < (1L << 31) - 64, "more than 2^31 rays per launch");
@@ -193,6 +197,9 @@ static int integrate_paged_impl(int metric_id, double bhspin, long N, long npx, 
     A.queue = queue ? queue : queue_counter(stream, 0);
     if (!A.queue) return 1;
     A.ray_order = ray_order; A.page_id_offset = (int)page_id_offset;
+    // > 0 selects the shared-queue kernel variant; launch_integrate multiplies by 4 x its own warps
+    A.chunk_div = queue ? (participants > 0 ? participants : 1) : 0;
+    A.chunk_mul = 0;
     A.total_steps = total_steps;
     A.pages = pages; A.page_next = page_next; A.page_first = page_first; A.page_counter = page_counter;
     A.max_pages = (unsigned)max_pages; A.overflow = overflow;
@@ -206,7 +213,7 @@ extern "C" int mk_integrate_paged(int metric_id, double bhspin, long N, long npx
                                   unsigned long long* total_steps, void* stream_)
 {
     return integrate_paged_impl(metric_id, bhspin, N, npx, s0, div, tol, final_state, nsteps, r_last, pages, page_next,
-                                page_first, page_counter, max_pages, overflow, total_steps, nullptr, nullptr, 0,
+                                page_first, page_counter, max_pages, overflow, total_steps, nullptr, nullptr, 0, 1,
                                 (cudaStream_t)stream_);
 }
 
@@ -215,12 +222,12 @@ extern "C" int mk_integrate_shared(int metric_id, double bhspin, long N, long np
                                    double* pages, int32_t* page_next, int32_t* page_first,
                                    unsigned int* page_counter, long max_pages, int32_t* overflow,
                                    unsigned long long* total_steps, unsigned int* queue, const int32_t* ray_order,
-                                   long page_id_offset, void* stream_)
+                                   long page_id_offset, int participants, void* stream_)
 {
     MK_REQUIRE(queue != nullptr, "queue is null (use mk_integrate_paged for a private queue)");
     return integrate_paged_impl(metric_id, bhspin, N, npx, s0, div, tol, final_state, nsteps, r_last, pages, page_next,
                                 page_first, page_counter, max_pages, overflow, total_steps, queue, ray_order,
-                                page_id_offset, (cudaStream_t)stream_);
+                                page_id_offset, participants, (cudaStream_t)stream_);
 }
 
 namespace mk {

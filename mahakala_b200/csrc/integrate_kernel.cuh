@@ -33,6 +33,8 @@ struct IntegrateArgs {
     double* dt;            // dump: (nrows, npx)
     long nrows;
     unsigned int* queue;   // zero-initialised ray counter; may live in a peer GPU's memory (one queue for all GPUs)
+    int chunk_div;         // guided self-scheduling: a warp asks for (rays left) / chunk_div positions, 1..QUEUE_CHUNK
+    unsigned chunk_mul;    // floor(2^32 / chunk_div): the division above as one multiply-high
     const int* ray_order;  // optional: queue position q -> ray index (scheduling order; results stay indexed by ray)
     int page_id_offset;    // added to the page numbers stored in page_first (rank * pool size in a multi-GPU job)
     unsigned long long* total_steps;  // optional global sum of accepted steps
@@ -51,10 +53,12 @@ struct IntegrateArgs {
 };
 
 constexpr int PAGE_SLOTS = 16;
-// Rays are taken from the queue in chunks of QUEUE_CHUNK positions per warp, and the NEXT chunk is requested while the
-// current one is being consumed: the atomic's round trip (a few microseconds when the counter sits in a peer GPU's
-// memory across NVLink) overlaps the RK4 steps in between instead of stalling the warp at every refill.
-constexpr int QUEUE_CHUNK = 16;
+// Rays are taken from the queue in chunks of up to QUEUE_CHUNK positions per warp, and the NEXT chunk is requested
+// while the current one is being consumed: the atomic's round trip (a few microseconds when the counter sits in a
+// peer GPU's memory across NVLink) overlaps the RK4 steps in between instead of stalling the warp at every refill.
+// Chunks shrink as the queue empties (guided self-scheduling: rays left / (4 x warps of all participants)), down to
+// single rays, so that no warp sits on a private stock of rays while lanes elsewhere run dry.
+constexpr int QUEUE_CHUNK = 32;
 constexpr int PAGE_DOUBLES = PAGE_SLOTS * 32 * 9;
 enum { MODE_FINAL = 0, MODE_PADDED = 1, MODE_PAGED = 2 };
 
@@ -66,7 +70,11 @@ struct LaneRay {
     int it, best_idx;
 };
 
-template <class Metric, int MODE>
+// SHARED = false: the queue is this GPU's own counter -- a lane refill costs one device-scope atomic for exactly the
+// idle lanes (ray-granular, nothing is held back).  SHARED = true: the counter may sit in a peer GPU's memory --
+// chunked, prefetched system-scope atomics with guided chunk sizes and an optional scheduling order (see above).
+// (Measured on B200, cfg2, one GPU: the chunked scheme costs ~1.5 % when the queue is local, hence two variants.)
+template <class Metric, int MODE, bool SHARED = false>
 __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateArgs& A)
 {
     constexpr bool DUMP = (MODE == MODE_PADDED);
@@ -75,13 +83,17 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
     bool drained = false;           // queue exhausted (warp-uniform)
     long cur = 0, cur_end = 0;      // the warp's private range of queue positions (warp-uniform)
     unsigned nxt = 0;               // base of the prefetched chunk (meaningful in lane 0 while have_next)
+    int nxt_len = 0;                // its length (warp-uniform)
+    long last_base = 0;             // base of the latest chunk received: how far the queue has advanced
     bool have_next = false;
     LaneRay L;
     L.ray = -1; L.dt = 0.0; L.r_cur = 0.0; L.r_prev = 0.0; L.best_dt = 0.0; L.r_before_best = 0.0; L.it = 0; L.best_idx = -1;
     unsigned long long my_steps = 0;
 
     auto request_chunk = [&]() {
-        if (lane == 0) nxt = atomicAdd_system(A.queue, (unsigned)QUEUE_CHUNK);
+        unsigned want = __umulhi((unsigned)(A.npx - last_base), A.chunk_mul);     // rays left / chunk_div (npx < 2^31)
+        nxt_len = want < 1u ? 1 : (want > (unsigned)QUEUE_CHUNK ? QUEUE_CHUNK : (int)want);
+        if (lane == 0) nxt = atomicAdd_system(A.queue, (unsigned)nxt_len);
         have_next = true;
     };
 
@@ -91,9 +103,35 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
     // the 8-vector and its cache (the loop-carried moves were ~8 % of the issued instructions).
     auto iteration = [&](double (&s)[8], typename Metric::Cache& cache, double (&sn)[8],
                          typename Metric::Cache& cn) -> bool {
-        // ---- refill idle lanes from the warp's private range, topping it up from the queue ----
         unsigned idle = __ballot_sync(FULL_MASK, L.ray < 0);
-        if (idle) {
+        if (!SHARED && idle) {
+            // ---- refill idle lanes from the local queue ----
+            if (!drained) {
+                int cnt = __popc(idle);
+                unsigned base = 0;
+                int leader = __ffs(idle) - 1;
+                if ((int)lane == leader) base = atomicAdd(A.queue, (unsigned)cnt);
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if ((long)base + cnt >= A.npx) drained = true;
+                if (L.ray < 0) {
+                    long idx = (long)base + __popc(idle & ((1u << lane) - 1u));
+                    if (idx < A.npx) {
+                        L.ray = idx;
+                        const double4* p = reinterpret_cast<const double4*>(A.s0 + idx * 8);
+                        double4 lo = p[0], hi = p[1];
+                        s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+                        s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+                        L.r_cur = g.radius(s, cache);
+                        L.dt = A.rule(L.r_cur);
+                        L.r_prev = L.r_cur;
+                        L.it = 0; L.best_idx = -1; L.best_dt = -1.0e300; L.r_before_best = L.r_cur;
+                    }
+                }
+            }
+            if (__ballot_sync(FULL_MASK, L.ray >= 0) == 0) return false;
+        }
+        if (SHARED && idle) {
+            // ---- refill idle lanes from the warp's private range, topping it up from the shared queue ----
             int need = __popc(idle);
             const int my_rank = __popc(idle & ((1u << lane) - 1u));     // position among the idle lanes
             int given = 0;
@@ -103,8 +141,8 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                     const unsigned b = __shfl_sync(FULL_MASK, nxt, 0);   // waits for the atomic only if still in flight
                     have_next = false;
                     if ((long)b >= A.npx) { drained = true; break; }
-                    cur = (long)b;
-                    cur_end = ((long)b + QUEUE_CHUNK < A.npx) ? (long)b + QUEUE_CHUNK : A.npx;
+                    cur = last_base = (long)b;
+                    cur_end = ((long)b + nxt_len < A.npx) ? (long)b + nxt_len : A.npx;
                 }
                 const int avail = (int)(cur_end - cur);
                 const int take = need < avail ? need : avail;
@@ -123,7 +161,7 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 }
                 cur += take; given += take; need -= take;
             }
-            if (!have_next && !drained && cur_end - cur <= QUEUE_CHUNK / 2) request_chunk();
+            if (!have_next && !drained && cur_end - cur <= 2) request_chunk();
             if (__ballot_sync(FULL_MASK, L.ray >= 0) == 0) return false;
         }
         const bool act = L.ray >= 0;

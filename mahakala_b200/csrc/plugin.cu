@@ -69,6 +69,10 @@ int plugin_integrate(int metric_id, double bhspin, IntegrateArgs& A, cudaStream_
     long need = ((A.npx + 31) / 32 + 3) / 4;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
+    if (A.chunk_div > 0 || A.ray_order) {
+        set_error("run-time registered spacetimes integrate on one GPU's own queue (no shared queue / ray order)");
+        return 2;
+    }
     void* args[] = {&b, &A};
     MK_CUDA_CHECK(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(128), args, 0, stream));
     return 0;

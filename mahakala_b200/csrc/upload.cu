@@ -4,6 +4,7 @@
 // bench hosts); pinning a multi-GB array first costs more than the copy.  Snapshot ingestion is a "next" row of the
 // hot path (the reference re-uploads the ghost-padded array on every call, athenak.py:693).
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -45,12 +46,39 @@ void parallel_copy(char* dst, const char* src, size_t n, int threads)
 }
 }  // namespace
 
+// Strategy "register": pin the caller's pages in place (cudaHostRegister), let the DMA engine read them directly,
+// unpin.  No host-side copy at all -- on hosts whose memcpy bandwidth is a few GB/s (virtualised bench boxes) the
+// staging copy is the bottleneck of the staged strategy.
+static int upload_registered(char* dst, const char* src, size_t total, cudaStream_t stream)
+{
+    const size_t page = 4096;
+    const char* lo = (const char*)((uintptr_t)src & ~(uintptr_t)(page - 1));
+    const char* hi = (const char*)(((uintptr_t)(src + total) + page - 1) & ~(uintptr_t)(page - 1));
+    cudaError_t e = cudaHostRegister((void*)lo, (size_t)(hi - lo), cudaHostRegisterReadOnly);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaHostRegister((void*)lo, (size_t)(hi - lo), cudaHostRegisterDefault);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }          // caller falls back to staging
+    cudaError_t c = cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, stream);
+    if (c == cudaSuccess) c = cudaStreamSynchronize(stream);
+    cudaHostUnregister((void*)lo);
+    if (c != cudaSuccess) { mk::set_error("registered upload failed: %s", cudaGetErrorString(c)); return 1; }
+    return 0;
+}
+
 extern "C" int mk_upload_pageable(void* dst_device, const void* src_host, long bytes, int host_threads, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     MK_REQUIRE(bytes >= 0, "negative size");
     if (bytes == 0) return 0;
     MK_REQUIRE(dst_device && src_host, "null pointer");
+    // host_threads < 0 selects the in-place registration strategy (falls back to staging if the pages cannot be pinned)
+    if (host_threads < 0) {
+        int rc = upload_registered((char*)dst_device, (const char*)src_host, (size_t)bytes, stream);
+        if (rc >= 0) return rc;
+        host_threads = 0;
+    }
     std::lock_guard<std::mutex> lock(g_mtx);
     if (!stage_init()) { mk::set_error("pinned staging buffers could not be allocated"); return 1; }
     int threads = host_threads > 0 ? host_threads : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));

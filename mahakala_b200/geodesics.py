@@ -364,13 +364,15 @@ class TrajectoryStore:
         return DeviceArray.wrap(S), DeviceArray.wrap(dt)
 
 
-def integrate_paged(N, s0, div, tol, bhspin, store=None, queue=None, ray_order=None, results=None, page_id_offset=0):
+def integrate_paged(N, s0, div, tol, bhspin, store=None, queue=None, ray_order=None, results=None, page_id_offset=0,
+                    participants=1):
     """Single-pass trajectory dump of a whole bundle into a ``TrajectoryStore`` (see there).
 
     ``queue`` (a device pointer, possibly in a peer GPU's memory) makes this launch one participant of a multi-GPU
     job that shares ONE dynamic ray queue (``mahakala_b200.multigpu.integrate_distributed``): ``ray_order`` (int32
     tensor) is the order in which rays are handed out, ``results`` = (final, nsteps, r_last, page_first) pointers in
-    the gathering GPU's memory, ``page_id_offset`` tags the page numbers with their owner."""
+    the gathering GPU's memory, ``page_id_offset`` tags the page numbers with their owner, ``participants`` is the
+    number of GPUs pulling from the queue (sizes the chunks warps take from it)."""
     s = as_device(s0)
     npx = s.shape[0]
     if store is None:
@@ -383,7 +385,8 @@ def integrate_paged(N, s0, div, tol, bhspin, store=None, queue=None, ray_order=N
                                                                                  store.r_last, store.page_first)
         _cabi.call("mk_integrate_shared", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
                    final, nsteps, r_last, store.pages, store.page_next, page_first, store.ctrl[0:1], store.max_pages,
-                   store.ctrl[1:2], store.total_steps, queue, ray_order, int(page_id_offset), stream_ptr())
+                   store.ctrl[1:2], store.total_steps, queue, ray_order, int(page_id_offset), int(participants),
+                   stream_ptr())
         return store
     _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s, float(div), float(tol),
                store.final, store.nsteps, store.r_last, store.pages, store.page_next, store.page_first,
@@ -400,8 +403,9 @@ def _side_streams(dev):
     return _stream_pool[dev]
 
 
-def integrate_paged_host(N, s0_host, div, tol, bhspin, store, host_out):
-    """Host-to-host ``integrate_paged`` without staging copies (zero-copy).
+def integrate_paged_host(N, s0_host, div, tol, bhspin, store, host_out, ray_order=None):
+    """Host-to-host ``integrate_paged`` without staging copies (zero-copy).  ``ray_order`` (device int32 tensor):
+    optional order in which the rays are handed out (longest first shortens the tail of the launch).
 
     ``s0_host`` (npx, 8) and ``host_out`` = {``final`` (npx, 8), ``nsteps`` (npx,) int32, ``r_last`` (npx,)} are
     PINNED CPU tensors.  Under unified addressing pinned host memory is mapped into the device address space, so
@@ -424,9 +428,18 @@ def integrate_paged_host(N, s0_host, div, tol, bhspin, store, host_out):
             (torch.float64, torch.float64, torch.int32, torch.float64):
         raise ValueError("s0 / final / r_last must be float64 and nsteps int32")
     store.reset()
-    _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s0_host, float(div), float(tol),
-               host_out["final"], host_out["nsteps"], host_out["r_last"], store.pages, store.page_next,
-               store.page_first, store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps, stream_ptr())
+    if ray_order is not None:
+        if not hasattr(store, "_queue"):
+            store._queue = torch.zeros(64, dtype=torch.int32, device=store.pages.device)
+        store._queue.zero_()
+        _cabi.call("mk_integrate_shared", _active_metric, float(bhspin), int(N), npx, s0_host, float(div), float(tol),
+                   host_out["final"], host_out["nsteps"], host_out["r_last"], store.pages, store.page_next,
+                   store.page_first, store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps,
+                   store._queue, ray_order, 0, 1, stream_ptr())
+    else:
+        _cabi.call("mk_integrate_paged", _active_metric, float(bhspin), int(N), npx, s0_host, float(div), float(tol),
+                   host_out["final"], host_out["nsteps"], host_out["r_last"], store.pages, store.page_next,
+                   store.page_first, store.ctrl[0:1], store.max_pages, store.ctrl[1:2], store.total_steps, stream_ptr())
     torch.cuda.current_stream().synchronize()
     store._host_results = host_out
     return store

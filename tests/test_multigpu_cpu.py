@@ -66,3 +66,22 @@ def test_patch_geometry_matches_library(built):
             seen = np.concatenate([multigpu.patch_pixels(p, res) for p in range(n)])
             assert np.array_equal(np.sort(seen), np.arange(res * res))
     assert multigpu.static_assignment(10, 1, 4) == (1, 10, 4)
+
+
+def test_longest_first_ray_order_is_an_interleaved_permutation(built):
+    """Queue order of a multi-frame integration job: a permutation of all rays, frames interleaved position by
+    position, pixels by distance from the image centre (host logic of multigpu.integrate_distributed)."""
+    from mahakala_b200 import multigpu
+    res, frames = 12, 3
+    order = multigpu.longest_first_ray_order(res, frames)
+    n = res * res
+    assert order.dtype == np.int32 and order.shape == (frames * n,)
+    assert np.array_equal(np.sort(order), np.arange(frames * n))
+    assert np.array_equal(order.reshape(n, frames) // n, np.tile(np.arange(frames), (n, 1)))      # frames interleaved
+    pix = order.reshape(n, frames)[:, 0]
+    ix, iy = pix // res, pix % res
+    rho = np.hypot(ix + 0.5 - res / 2, iy + 0.5 - res / 2)
+    assert np.all(np.diff(rho) >= 0)                                                               # centre first
+    assert np.array_equal(multigpu.longest_first_ray_order(5, 1), multigpu.longest_first_ray_order(5))
+    # SharedRays layout: offsets of the four result arrays (bytes) behind the 512 B of queue counters
+    assert multigpu.HEADER_BYTES == 512
