@@ -272,8 +272,6 @@ def run_b200(args):
                 "nsteps": torch.empty((npx,), dtype=torch.int32, pin_memory=True),
                 "r_last": torch.empty((npx,), dtype=torch.float64, pin_memory=True)}
 
-    e2e_order = torch.from_numpy(multigpu.longest_first_ray_order(res, 1)).to(dev)
-
     def step_e2e(chunks=None):
         chunks = E2E_CHUNKS if chunks is None else chunks
         if store is not None:
@@ -283,8 +281,9 @@ def run_b200(args):
             if chunks > 0:
                 geo.integrate_paged_streamed(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out, chunks=chunks)
             else:
-                geo.integrate_paged_host(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out,
-                                         ray_order=e2e_order)
+                # (pixel order: with the longest-first order the 64 B PCIe reads of s0 become random and the
+                # host-to-host step was measured 19.1 ms instead of 16.3 ms)
+                geo.integrate_paged_host(CFG2["N"], s0_host, CFG2["div"], CFG2["tol"], a, store, host_out)
             return int(host_out["nsteps"].sum())
         d = s0_host.to(dev, non_blocking=True)
         if store is not None:
