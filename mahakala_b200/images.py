@@ -53,14 +53,46 @@ def centre_out_patch_order(res, device):
     return _order_cache[key]
 
 
+_learned_order = {}
+
+
+def _camera_key(bhspin, camera_inclination, camera_distance, fov, resolution, max_nsteps, div, tol, device):
+    return (float(bhspin), float(camera_inclination), float(camera_distance), float(fov), int(resolution),
+            int(max_nsteps), float(div), float(tol), str(device))
+
+
+def learn_patch_order(bhspin, camera_inclination=60, camera_distance=1000, fov=20, resolution=160, max_nsteps=10000,
+                      div=40, tol=1e-4):
+    """Profile-guided scheduling for REPEATED frames of one camera (a movie, a frequency or model sweep): the step
+    count of a ray depends on the camera and the spacetime only, not on the fluid, so one geodesics-only pass
+    (``integrate_final``, ~15 ms for 1024^2 rays) gives the exact length of every 4x8-pixel patch.  Later
+    ``render`` calls with the same camera hand the patches out longest first, the optimal list schedule for the
+    dynamic queue: the patch that contains the longest photon-ring ray (a chain of dependent RK4 steps nothing can
+    shorten) starts at time zero instead of whenever the centre-out heuristic reaches it.  Results are unaffected
+    (scheduling only).  Returns the permutation (device int32 tensor)."""
+    dev = require_gpu()
+    res = int(resolution)
+    s0 = geo.initialize_geodesics_at_camera(bhspin, camera_inclination, camera_distance, -fov / 2., fov / 2., res)
+    _, nsteps, _ = geo.integrate_final(max_nsteps, s0, div, tol, bhspin)
+    px_n, py_n = -(-res // 4), -(-res // 8)
+    img = torch.zeros((px_n * 4, py_n * 8), dtype=torch.int32, device=dev)
+    img[:res, :res] = nsteps.view(res, res)
+    longest = img.view(px_n, 4, py_n, 8).amax(dim=(1, 3)).reshape(-1)          # patch index = px * py_n + py
+    order = torch.argsort(longest, descending=True, stable=True).to(torch.int32)
+    _learned_order[_camera_key(bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)] = order
+    return order
+
+
 def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26, M_bh=6.2e9 * Msun,
            r_high=40, observing_frequencies=(230.e9,), fov=20, resolution=160, max_nsteps=10000, s0=None,
            div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1, 1), want_counters=False,
-           patch_order="centre_out"):
+           patch_order="auto"):
     """Fused multi-frequency render.  Returns ``image (nfreq, npx)`` on the device (plus counters).
 
     ``s0`` (npx, 8) replaces the grid camera by explicit rays.  ``image_out`` / ``queue`` may be tensors
     or raw device pointers (possibly in a peer GPU's memory) — see ``mahakala_b200.multigpu``.
+    ``patch_order``: 'auto' = the order learned for this camera by ``learn_patch_order`` if there is one, else
+    'centre_out'; 'centre_out'; None = row-major; or an int32 device tensor.
     """
     dev = require_gpu()
     snap = fluid_model.snapshot()
@@ -94,13 +126,23 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
         img = torch.zeros((nfreq, npx), dtype=torch.float64, device=dev)    # partial render: others stay 0
     nsteps = None
     counters = torch.zeros(2, dtype=torch.int64, device=dev) if want_counters else None
+    order = None
+    if s0d is None:
+        if isinstance(patch_order, torch.Tensor):
+            order = patch_order
+        elif patch_order == "auto":
+            order = _learned_order.get(_camera_key(fluid_model.bhspin, camera_inclination, camera_distance, fov, res,
+                                                   max_nsteps, div, tol, dev))
+            if order is None:
+                order = centre_out_patch_order(res, dev)
+        elif patch_order == "centre_out":
+            order = centre_out_patch_order(res, dev)
     i = camera_inclination * np.pi / 180
     _cabi.call("mk_render", float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
                -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
                img, nsteps, counters[0:1] if want_counters else None, counters[1:2] if want_counters else None,
                queue, int(patch_range[0]), int(patch_range[1]), int(patch_range[2]) if len(patch_range) > 2 else 1,
-               centre_out_patch_order(res, dev) if (s0d is None and patch_order == "centre_out") else None,
-               stream_ptr())
+               order, stream_ptr())
     if want_counters:
         return img, counters
     return img
