@@ -141,6 +141,14 @@ int mk_integrate_shared(int metric_id, double bhspin, long N, long npx, const do
 int mk_paged_gather(const double* pages, const int32_t* page_next, const int32_t* page_first,
                     const int32_t* nsteps, const long* ray_idx, long nsel, long nrows, long N, double* S,
                     double* dt, void* stream);
+/* geodesics.py:405-435 find_shadow_bisection_angles in one launch (built-in Kerr-Schild spacetime): for each of the n
+   image-plane angles (cos_angle, sin_angle: DEVICE arrays of cos / sin evaluated by the caller) n_iter bisection
+   steps on the bracket [inner0, outer0]: ray through the mid radius (geodesics.py:107-134 + :219-230), integrated
+   for at most N steps with div / tol (:354-378), bracket halved on "classifier radius < limit".  inner_out /
+   outer_out (n,) receive the final brackets; the reference returns inner. */
+int mk_shadow_bisection(double bhspin, double cos_i, double sin_i, double distance, const double* cos_angle,
+                        const double* sin_angle, long n, long N, double div, double tol, int n_iter, double inner0,
+                        double outer0, double limit, double* inner_out, double* outer_out, void* stream);
 /* geodesics.py:284-291 radius_cal for n points of stride `stride` doubles (x at offsets 1..3) */
 int mk_radius_cal(double bhspin, const double* x, long n, long stride, double* r, void* stream);
 /* geodesics.py:294-314 rhs on a bundle: state (n, 8) -> (n, 8); metric_id selects the plugin */

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mk_integrate_paged": "idllpdd" "ppp" "pppp" "l" "pp" "p",
     "mk_integrate_shared": "idllpdd" "ppp" "pppp" "l" "pp" "pp" "li" "p",
     "mk_paged_gather": "ppppp" "lll" "ppp",
+    "mk_shadow_bisection": "dddd" "pp" "ll" "dd" "i" "ddd" "ppp",
     "mk_radius_cal": "dpllpp",
     "mk_rhs": "idplpp",
     "mk_rk4_step": "idpplpp",

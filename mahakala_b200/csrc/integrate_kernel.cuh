@@ -74,6 +74,38 @@ struct LaneRay {
 // idle lanes (ray-granular, nothing is held back).  SHARED = true: the counter may sit in a peer GPU's memory --
 // chunked, prefetched system-scope atomics with guided chunk sizes and an optional scheduling order (see above).
 // (Measured on B200, cfg2, one GPU: the chunked scheme costs ~1.5 % when the queue is local, hence two variants.)
+// One ray from s0 to its end, no queue: the per-lane logic of integrate_body (same calls in the same order, so the
+// same numbers) for callers that iterate on the outcome of single rays (shadow bisection).  Returns the classifier
+// radius radius_cal(S[argmax(dt) - 1]) of geodesics.py:370-378; s0 is overwritten with the final state.
+template <class Metric>
+MK_HD double integrate_one(const Metric& g, const StepRule& rule, double (&s)[8], int N, int& nsteps)
+{
+    typename Metric::Cache c, cn;
+    double sn[8];
+    double r_cur = g.radius(s, c), r_prev = r_cur, best_dt = -1.0e300, r_before_best = r_cur;
+    double dt = rule(r_cur);
+    int it = 0, best_idx = -1;
+    bool capped = false;
+    for (;;) {
+        double r_new = 0.0, dtn = 0.0;
+        if (dt != 0.0) {
+            rk4_step(g, s, dt, sn, &c);
+            r_new = g.radius(sn, cn);
+            dtn = rule(r_new);
+        }
+        if ((dt == 0.0) || (dtn == 0.0)) break;
+        if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
+        r_prev = r_cur; r_cur = r_new; dt = dtn; it++;
+#pragma unroll
+        for (int m = 0; m < 8; m++) s[m] = sn[m];
+        c = cn;
+        if (it == N) { capped = true; break; }
+    }
+    nsteps = it;
+    if (capped) return (best_idx >= 1) ? r_before_best : r_prev;
+    return (best_dt > 0.0) ? ((best_idx >= 1) ? r_before_best : r_cur) : ((it >= 1) ? r_prev : r_cur);
+}
+
 template <class Metric, int MODE, bool SHARED = false>
 __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateArgs& A)
 {

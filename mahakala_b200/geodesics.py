@@ -516,22 +516,54 @@ def find_shadow_bisection(bhspin, inc, num_angles, max_steps=2000, error_allowed
     return angles, radii
 
 
+def _bisection_iterations(lo, hi, error_allowed, max_it):
+    """How many times the reference's loop (geodesics.py:420-434) runs: every angle starts from the same bracket and
+    halves it each time, so ``max(error)`` follows one sequence.  Returns None when a width comes within rounding of
+    ``error_allowed`` (the two halves of a bracket can differ in the last bit; then the host loop decides)."""
+    n = 0
+    width = float(hi) - float(lo)
+    while width > error_allowed and n < max_it:
+        if abs(width - error_allowed) <= 1e-9 * error_allowed:
+            return None
+        width = width / 2
+        n += 1
+    return None if abs(width - error_allowed) <= 1e-9 * error_allowed else n
+
+
 def find_shadow_bisection_angles(bhspin, inc, angles, max_steps=2000, error_allowed=0.001, max_it=40):
-    """geodesics.py:405-435: bisection on the image-plane radius of the shadow edge, per angle."""
+    """geodesics.py:405-435: bisection on the image-plane radius of the shadow edge, per angle.
+
+    With the built-in spacetime the whole bisection runs in ONE kernel launch (``mk_shadow_bisection``: a lane owns an
+    angle and iterates ray -> captured? -> halve); a user-registered spacetime, or a bracket that stalls (NaN
+    classifier radius), goes through the reference's own iteration-by-iteration loop below."""
     require_gpu()
     angles = np.asarray(angles, dtype=np.float64)
-    inner = np.zeros_like(angles) + 0.5
-    outer = np.zeros_like(angles) + 10
-    error = outer - inner
-    bisection_limit = 100
-    counter = 0
-    while np.max(error) > error_allowed and counter < max_it:
-        final_mid = np.asarray(select_photons_integrator(inc, angles, (outer - inner) / 2 + inner, bhspin,
-                                                         max_steps=max_steps))
-        fell = np.where(final_mid < bisection_limit)
-        got_away = np.where(final_mid >= bisection_limit)
-        inner[fell] = (outer[fell] - inner[fell]) / 2 + inner[fell]
-        outer[got_away] = (outer[got_away] - inner[got_away]) / 2 + inner[got_away]
-        error = outer - inner
-        counter += 1
-    return inner
+    n_iter = _bisection_iterations(0.5, 10, error_allowed, max_it)
+    if _active_metric == KERR_SCHILD and n_iter is not None and angles.size:
+        flat = angles.reshape(-1)
+        ci, si = _cos_sin_deg(inc)
+        inner, outer = empty((flat.size,)), empty((flat.size,))
+        _cabi.call("mk_shadow_bisection", float(bhspin), ci, si, 1000.0, as_device(np.cos(flat)), as_device(np.sin(flat)),
+                   flat.size, int(max_steps), 40.0, 1e-2, n_iter, 0.5, 10.0, 100.0, inner, outer, stream_ptr())
+        inner_h, outer_h = inner.cpu().numpy(), outer.cpu().numpy()
+        if not (np.max(outer_h - inner_h) > error_allowed and n_iter < max_it):      # the loop would have stopped here too
+            return inner_h.reshape(angles.shape)
+    return _find_shadow_bisection_angles_host(bhspin, inc, angles, max_steps, error_allowed, max_it)
+
+
+def _find_shadow_bisection_angles_host(bhspin, inc, angles, max_steps=2000, error_allowed=0.001, max_it=40):
+    """The reference's loop, one bundle launch per bisection iteration (geodesics.py:417-435): brackets start at
+    [0.5, 10]; a mid-radius ray whose last-point radius is below 100 fell in (edge further out), at or above 100 it
+    got away; a NaN radius moves neither end."""
+    require_gpu()
+    angles = np.asarray(angles, dtype=np.float64)
+    lo = np.full(angles.shape, 0.5)
+    hi = np.full(angles.shape, 10.0)
+    for _ in range(max_it):
+        if not np.max(hi - lo) > error_allowed:
+            break
+        mid = (hi - lo) / 2 + lo
+        r_end = np.asarray(select_photons_integrator(inc, angles, mid, bhspin, max_steps=max_steps))
+        lo = np.where(r_end < 100, mid, lo)
+        hi = np.where(r_end >= 100, mid, hi)
+    return lo

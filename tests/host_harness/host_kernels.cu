@@ -5,7 +5,7 @@
 #include <cmath>
 #include <cstring>
 #include <cuda_runtime.h>
-#include "../../mahakala_b200/csrc/integrate.cuh"
+#include "../../mahakala_b200/csrc/integrate_kernel.cuh"
 #include "../../mahakala_b200/csrc/ks_metric.cuh"
 #include "../../mahakala_b200/csrc/sample.cuh"
 
@@ -34,7 +34,7 @@ extern "C" void hk_rk4(long n, const double* s, const double* dt, double a, doub
     for (long i = 0; i < n; i++) rk4_step(g, s + 8 * i, dt[i], out + 8 * i);
 }
 
-// the per-ray loop of integrate_kernel.cuh (final-state mode) without the warp machinery
+// the per-ray loop of integrate_kernel.cuh (integrate_one: the lane logic of the kernel without the warp machinery)
 extern "C" void hk_integrate(long n, const double* s0, int N, double div, double tol, double a, double* final_state,
                              int* nsteps, double* r_last)
 {
@@ -43,32 +43,12 @@ extern "C" void hk_integrate(long n, const double* s0, int N, double div, double
     rule.div = div; rule.inv_div = 1.0 / div; rule.tol = tol; rule.rH = g.rH;
 #pragma omp parallel for schedule(dynamic, 16)
     for (long p = 0; p < n; p++) {
-        double s[8], sn[8];
+        double s[8];
         std::memcpy(s, s0 + 8 * p, sizeof s);
-        KerrSchild::Cache c, cn;
-        double r_cur = g.radius(s, c), r_prev = r_cur, best_dt = -1e300, r_before_best = r_cur;
-        double dt = rule(r_cur);
-        int it = 0, best_idx = -1;
-        bool capped = false;
-        for (;;) {
-            double r_new = 0, dtn = 0;
-            if (dt != 0.0) {
-                rk4_step(g, s, dt, sn, &c);
-                r_new = g.radius(sn, cn);
-                dtn = rule(r_new);
-            }
-            if (dt == 0.0 || dtn == 0.0) break;
-            if (dt > best_dt) { best_dt = dt; best_idx = it; r_before_best = r_prev; }
-            r_prev = r_cur; r_cur = r_new; dt = dtn; it++;
-            std::memcpy(s, sn, sizeof s); c = cn;
-            if (it == N) { capped = true; break; }
-        }
+        int it = 0;
+        r_last[p] = integrate_one(g, rule, s, N, it);
         std::memcpy(final_state + 8 * p, s, sizeof s);
         nsteps[p] = it;
-        double rl;
-        if (capped) rl = (best_idx >= 1) ? r_before_best : r_prev;
-        else rl = (best_dt > 0.0) ? ((best_idx >= 1) ? r_before_best : r_cur) : ((it >= 1) ? r_prev : r_cur);
-        r_last[p] = rl;
     }
 }
 

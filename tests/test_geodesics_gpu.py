@@ -273,6 +273,37 @@ def test_golden_shadows_through_dropin_api(ma, golden_shadows):
     assert ang.shape == rad.shape == (13,) and rad[0] == rad[-1]
 
 
+def test_device_side_bisection_equals_the_host_loop(ma, golden_shadows):
+    """find_shadow_bisection_angles runs the whole bisection in one launch (mk_shadow_bisection); the radii must be
+    the ones the reference's iteration-by-iteration loop returns -- bit for bit -- on the four golden cases, and the
+    launch must beat the 56 launches of the host loop."""
+    import time
+    import torch
+    from mahakala_b200 import geodesics as geo
+    for key, c in golden_shadows.items():
+        dev_r = np.asarray(geo.find_shadow_bisection_angles(c["bhspin"], c["inclination"], c["angles"]))
+        host_r = geo._find_shadow_bisection_angles_host(c["bhspin"], c["inclination"], c["angles"])
+        assert np.array_equal(dev_r, host_r), (key, np.abs(dev_r - host_r).max())
+    assert geo._bisection_iterations(0.5, 10, 0.001, 40) == 14 and geo._bisection_iterations(0.5, 10, 0.001, 5) == 5
+    # other tolerances / iteration caps take the same path; a stalled bracket falls back to the host loop
+    c = golden_shadows["test1"]
+    a5 = np.asarray(geo.find_shadow_bisection_angles(c["bhspin"], c["inclination"], c["angles"][:40], max_it=5))
+    h5 = geo._find_shadow_bisection_angles_host(c["bhspin"], c["inclination"], c["angles"][:40], max_it=5)
+    assert np.array_equal(a5, h5) and np.abs(a5 - c["radii"][:40]).max() < 9.5 / 2**5
+    assert np.asarray(geo.find_shadow_bisection_angles(0.9, 60, np.zeros((0,)))).shape == (0,)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for c in golden_shadows.values():
+        geo.find_shadow_bisection_angles(c["bhspin"], c["inclination"], c["angles"])
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for c in golden_shadows.values():
+        geo._find_shadow_bisection_angles_host(c["bhspin"], c["inclination"], c["angles"])
+    t_host = time.perf_counter() - t0
+    print(f"4 golden cases: one-launch bisection {1e3 * t_dev:.1f} ms, host loop {1e3 * t_host:.1f} ms")
+    assert t_dev < t_host
+
+
 KERR_SCHILD_USER = r"""
 // the reference's metric (geodesics.py:95-104) typed by a "user": spin = params[0] (the bhspin argument)
 struct UserMetric {
