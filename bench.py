@@ -41,6 +41,8 @@ E2E_CHUNKS = int(os.environ.get("MK_E2E_CHUNKS", "0"))
 # gather; the kernel is FP64/latency-bound, not traffic-bound) at twice the HBM footprint; images are bit-identical
 RENDER_STORAGE = os.environ.get("MK_RENDER_STORAGE", "f64")
 FLOP_PER_RAY_STEP = 859          # 312 add + 523 mul + 12 div + 12 sqrt
+RENDER_FP64_PER_STEP = 455       # executed FP64-pipe instructions of the fused kernel per ray-step (SASS count) ...
+RENDER_FP64_PER_SAMPLE = 340     # ... and per in-domain sample on top of that
 CFG2 = dict(bhspin=0.94, inclination=60.0, distance=1000.0, fov=20.0, div=40.0, tol=1e-4, N=10000)
 WEAK_INCLINATIONS = [60.0, 17.0, 30.0, 80.0, 45.0, 70.0, 25.0, 52.0]    # one frame per rank (cfg5-style)
 
@@ -58,6 +60,7 @@ def parse():
                     help="side of the large single image used for the strong-scaling render leg (cfg5-sized frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=341, help="side of the pixel sub-lattice timed on the CPU")
+    ap.add_argument("--render-cpu-stride", type=int, default=16, help="pixel stride of the CPU render baseline")
     return ap.parse_args()
 
 
@@ -410,7 +413,7 @@ def run_b200(args):
     store = None
     torch.cuda.empty_cache()
     if not args.no_render:
-        render = render_leg(args, rank, world, dev)
+        render = render_leg(args, rank, world, dev, fp64_peak)
 
     if rank == 0:
         kernel_ms = dev_ms / args.steps
@@ -489,7 +492,34 @@ def hbm_peak():
         return 6650.0       # B200_PROFILING.md fallback
 
 
-def render_leg(args, rank, world, dev):
+def render_cpu_baseline(arr, res, stride):
+    """The reference's make_image chain (C/OpenMP restatement: integrate -> O(nmb) block scan -> trilinear -> fluid
+    frame -> j, alpha -> back-to-front transfer, per ray) on every stride-th pixel of the cfg4 frame, all host cores;
+    the full-frame figure is that time scaled by the pixel count."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    c_oracle.use_all_cores()
+    t0 = time.perf_counter()
+    om = onp.AthenakFluidModel(arr["uov"].astype(np.float64), arr["B"].astype(np.float64), arr["x1v"], arr["x2v"],
+                               arr["x3v"], arr["x1f"], arr["x2f"], arr["x3f"], arr["LogicalLocations"], arr["Levels"],
+                               CFG2["bhspin"], fluid_gamma=arr["fluid_gamma"], variable_names=arr["VariableNames"])
+    t_load = time.perf_counter() - t0
+    s0 = onp.initialize_geodesics_at_camera(CFG2["bhspin"], CFG2["inclination"], CFG2["distance"], -CFG2["fov"] / 2,
+                                            CFG2["fov"] / 2, res)
+    idx = (np.arange(0, res, stride)[:, None] * res + np.arange(0, res, stride)[None, :]).reshape(-1)
+    sub = np.ascontiguousarray(s0[idx])
+    units = om.get_units(6.2e9 * 1.989e33, 1.e26)
+    t0 = time.perf_counter()
+    img, nsteps, nin = c_oracle.render(om, sub, units, [230e9])
+    dt = time.perf_counter() - t0
+    scale = (res * res) / sub.shape[0]
+    return {"value": 1e3 * dt * scale, "unit": "ms per 1024^2 frame (estimated: sample time x pixel ratio)",
+            "cores": c_oracle.num_threads(), "kind": "port",
+            "sample": f"every {stride}th pixel of the {res}x{res} cfg4 frame ({sub.shape[0]} rays, {int(nsteps.sum())} "
+                      f"ray-steps, {nin} in-domain samples, {dt:.1f} s); ghost-zone fill of the snapshot on the host "
+                      f"{t_load:.1f} s (not included); C/OpenMP restatement of the reference's images.make_image"}
+
+
+def render_leg(args, rank, world, dev, fp64_peak):
     """cfg4: fused 1024^2 230 GHz image of the synthetic 256^3 snapshot.
 
     N = 1: one image.  N > 1: (weak) one frame per rank at its own inclination, and (strong) ONE image whose
@@ -531,7 +561,6 @@ def render_leg(args, rank, world, dev):
         if world > 1:
             dist.barrier()
         setups.append((1e3 * (time.perf_counter() - t_setup), dict(model.replication_timing)))
-    del arr
     t_setup_cold, rep_cold = setups[0]
     t_setup, rep = setups[1]
     bcast_ms = rep["broadcast"]
@@ -679,6 +708,22 @@ def render_leg(args, rank, world, dev):
            "snapshot_setup_note": "host interior arrays -> device snapshot (upload + fused ghost-fill/repack kernel"
                                   + (" + NCCL broadcast" if world > 1 else "") + "), outside the render time",
            "image_sum": float(host_img.sum()), "gpu_launches_per_image": 1}
+    # FP64-issue roofline of the fused kernel: executed FP64-pipe instructions (SASS of render_kernel<1, f64 cells>,
+    # scripts/dev/sass_by_line.py: 455 per ray-step for RK4 + step rule + block lookup, 340 more per in-domain sample
+    # for cell index, trilinear gather, fluid frame, Theta_e, j / alpha, transfer update) against the issue rate the
+    # DFMA microbenchmark reaches on this GPU (one FP64 warp instruction per 2 cycles per SM sub-partition)
+    fp64_thread_instr = steps * RENDER_FP64_PER_STEP + samples * RENDER_FP64_PER_SAMPLE
+    out["roofline"] = {"bound": "fp64", "kernel": "mk::render_kernel<1, f64 cells>",
+                       "achieved": fp64_thread_instr / (ms * 1e-3) / 1e12, "peak": fp64_peak / 2.0,
+                       "unit": "T FP64 instr/s (thread level; a DFMA counts once)",
+                       "frac": fp64_thread_instr / (ms * 1e-3) / 1e12 / (fp64_peak / 2.0),
+                       "fp64_instr_per_ray_step": RENDER_FP64_PER_STEP, "fp64_instr_per_in_domain_sample": RENDER_FP64_PER_SAMPLE,
+                       "hbm": {"algorithmic_bytes": samples * (256 if model.storage == "f32" else 512),
+                               "note": "8 corner cells x 8 primitives per in-domain sample if nothing were reused; "
+                                       "the 4x8-pixel patches make it cache-resident (measured DRAM traffic per frame: "
+                                       "profiles/, ~2.3 GB = 1.8 x the snapshot)", "peak_GBps": hbm_peak()}}
+    if rank == 0 and not args.no_cpu_baseline and arr is not None:
+        out["cpu_baseline"] = render_cpu_baseline(arr, res, args.render_cpu_stride)
     if stage is not None:
         out["sampling_stage_160px"] = stage
     if other:

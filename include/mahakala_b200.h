@@ -287,6 +287,17 @@ int mk_render(double bhspin, double cos_i, double sin_i, double distance, double
               double* image, int32_t* nsteps, unsigned long long* total_steps,
               unsigned long long* total_samples, unsigned int* queue, long patch_begin, long patch_end,
               long patch_stride, const int* patch_order, void* stream);
+/* The same with a selectable spacetime: MK_METRIC_KERR_SCHILD (== mk_render) or a run-time registered metric
+   (id >= MK_METRIC_PLUGIN_BASE): geodesics through the plugin's dual-number derivatives, fluid-frame algebra
+   (athenak.py:760-786) with the plugin's own covariant / contravariant metric at every sample.  The reference obtains
+   this by replacing its module-level metric (geodesics.py:88-104; athenak.py:34 imports it).  Registered spacetimes
+   carry one frequency per launch (nfreq > 1 = one launch per frequency). */
+int mk_render_metric(int metric_id, double bhspin, double cos_i, double sin_i, double distance, double fov_lower,
+                     double fov_upper, long res, const double* s0, long npx, long N, double div, double tol,
+                     const mk_snapshot* snap, const mk_emission_params* params, int nfreq, const double* nu_obs,
+                     double* image, int32_t* nsteps, unsigned long long* total_steps,
+                     unsigned long long* total_samples, unsigned int* queue, long patch_begin, long patch_end,
+                     long patch_stride, const int* patch_order, void* stream);
 /* number of 32-ray patches mk_render splits a job into (grid camera: 4x8 pixel patches) */
 long mk_render_patch_count(long res, const double* s0, long npx);
 

@@ -78,6 +78,25 @@ int plugin_integrate(int metric_id, double bhspin, IntegrateArgs& A, cudaStream_
     return 0;
 }
 
+int plugin_render(int metric_id, double bhspin, const void* render_args, size_t args_bytes, long npatches,
+                  cudaStream_t stream)
+{
+    (void)args_bytes;
+    Plugin* p = find_plugin(metric_id);
+    if (!p) return 2;
+    cudaKernel_t k;
+    if (int rc = get_kernel(p, "mk_plugin_render", &k)) return rc;
+    PluginBlobHost b;
+    fill_blob(p, bhspin, b);
+    long blocks = (long)sm_count() * 2;                 // __launch_bounds__(128, 2) in plugin_tu.cuh
+    long need = (npatches + 3) / 4;
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    void* args[] = {&b, const_cast<void*>(render_args)};
+    MK_CUDA_CHECK(cudaLaunchKernel((const void*)k, dim3((unsigned)blocks), dim3(128), args, 0, stream));
+    return 0;
+}
+
 int plugin_elementwise(int metric_id, double bhspin, const char* kernel, void** extra_args, int n_extra, long n,
                        cudaStream_t stream)
 {

@@ -16,6 +16,7 @@
 #include "integrate_kernel.cuh"
 #include "metric_plugin.cuh"
 #include "camera_nullify.cuh"
+#include "render_kernel.cuh"
 
 namespace mk {
 
@@ -54,6 +55,16 @@ extern "C" __global__ void __launch_bounds__(128, 2) mk_plugin_integrate_padded(
 extern "C" __global__ void __launch_bounds__(128, 2) mk_plugin_integrate_paged(mk::PluginBlob b, mk::IntegrateArgs A)
 {
     mk::plugin_integrate<mk::MODE_PAGED>(b, A);
+}
+
+// fused render (images.py:30-144) in the user's spacetime: geodesics from the dual-number plugin, fluid frame from
+// its covariant / contravariant metric at every sample (athenak.py:760-786 with g, g^-1 of the plugin); one observing
+// frequency per launch, any snapshot kind
+extern "C" __global__ void __launch_bounds__(128, 2) mk_plugin_render(mk::PluginBlob b, mk::RenderArgs A)
+{
+    mk::DualMetric<UserMetric> g = mk::plugin_metric(b);
+    A.rule.rH = g.rH;
+    mk::render_body<mk::DualMetric<UserMetric>, 1, mk::SNAP_GENERIC>(g, A);
 }
 
 extern "C" __global__ void mk_plugin_rhs(mk::PluginBlob b, const double* state, long n, double* out)

@@ -56,11 +56,17 @@ MK_HD BlockGeom load_geom(const SnapshotView& sn, int mb)
 {
     const double* p = sn.geom + (long)mb * GEOM_DOUBLES;
     double v[12];
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(__CUDACC_RTC__)
 #pragma unroll
     for (int i = 0; i < 3; i++)
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
             : "=d"(v[4 * i]), "=d"(v[4 * i + 1]), "=d"(v[4 * i + 2]), "=d"(v[4 * i + 3]) : "l"(p + 4 * i));
+#elif defined(__CUDA_ARCH__)    // NVRTC 12.9's embedded ptxas rejects 256-bit vector accesses: 128-bit loads
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
+        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+    }
 #else
     for (int i = 0; i < 12; i++) v[i] = p[i];
 #endif
@@ -75,9 +81,13 @@ MK_HD BlockGeom load_geom(const SnapshotView& sn, int mb)
 MK_HD void load_inv_dx(const SnapshotView& sn, int mb, double inv[3])
 {
     const double* p = sn.geom + (long)mb * GEOM_DOUBLES + 12;
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(__CUDACC_RTC__)
     double pad;
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(inv[0]), "=d"(inv[1]), "=d"(inv[2]), "=d"(pad) : "l"(p));
+    (void)pad;
+#elif defined(__CUDA_ARCH__)
+    double2 t0 = __ldg(reinterpret_cast<const double2*>(p)), t1 = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    inv[0] = t0.x; inv[1] = t0.y; inv[2] = t1.x;
 #else
     for (int i = 0; i < 3; i++) inv[i] = p[i];
 #endif
@@ -207,11 +217,17 @@ MK_HD void load_cell_pair(const double* p, double a[8], double b[8])
 {
     // two x-adjacent cells = 128 contiguous bytes, read as four 256-bit read-only loads
     double4 v[4];
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(__CUDACC_RTC__)
 #pragma unroll
     for (int i = 0; i < 4; i++)
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
             : "=d"(v[i].x), "=d"(v[i].y), "=d"(v[i].z), "=d"(v[i].w) : "l"(p + 4 * i));
+#elif defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double2 lo = __ldg(reinterpret_cast<const double2*>(p) + 2 * i), hi = __ldg(reinterpret_cast<const double2*>(p) + 2 * i + 1);
+        v[i].x = lo.x; v[i].y = lo.y; v[i].z = hi.x; v[i].w = hi.y;
+    }
 #else
     for (int i = 0; i < 4; i++) v[i] = reinterpret_cast<const double4*>(p)[i];
 #endif
@@ -223,7 +239,13 @@ MK_HD void load_cell_pair(const float* p, double a[8], double b[8])
 {
     // two x-adjacent f32 cells = 64 contiguous bytes, two 256-bit read-only loads
     float v[16];
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(__CUDACC_RTC__)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+#elif defined(__CUDA_ARCH__)
 #pragma unroll
     for (int i = 0; i < 2; i++)
         asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -509,23 +531,16 @@ __host__ __device__ inline EmissionConsts make_emission_consts(const EmissionPar
     return c;
 }
 
-// `sink(fq, em, ab)` receives the invariant emissivity and absorptivity of frequency fq as soon as they are known, so
-// that a multi-frequency caller can fold them into its accumulators without holding 2 NF values in registers.
-template <int NF, class Sink>
-MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, double f,
-                                              const double l[4], const double s[8], const double prims[8],
-                                              const double* nu_obs, const double* inv_nu_obs, Sink&& sink)
+// Frame scalars of one sample: what the emission chain needs from the fluid-frame algebra of athenak.py:760-786.
+struct FrameScalars {
+    double kdotu, kdotb, bsq;
+};
+
+// ... for the Kerr-Schild family g = eta + f l l, g^-1 = eta - f l^m l^n in closed form
+MK_HD FrameScalars frame_kerr_schild(double f, const double l[4], const double s[8], const double prims[8])
 {
-    // Straight-line code: every validity test only feeds the final select (invalid lanes may carry NaN/inf
-    // through the arithmetic, which is harmless on the GPU).  Early exits would make the compiler duplicate
-    // the copies of all loop-carried registers on every exit edge (~200 MOVs per sample in SASS).
-    const double dens = prims[0], u = prims[1];
-    // Theta_e = (const > 0) u / dens must reach 0.3, so dens and u have the same sign; both positive in any physical
-    // snapshot, both negative (Ne < 0: negative j and alpha in the reference too) kept for input-for-input parity
-    bool valid = ((dens > 0.0) & (u > 0.0)) | ((dens < 0.0) & (u < 0.0));
     const double* U = prims + 2;
     const double* Bp = prims + 5;
-    // ---- fluid frame (athenak.py:760-786) ----
     double sq1f, alpha;                                          // sqrt(1+f), 1/sqrt(1+f) = lapse
     quick_sqrt_rsqrt(1.0 + f, sq1f, alpha);
     double lU = fma(l[1], U[0], fma(l[2], U[1], l[3] * U[2]));
@@ -547,16 +562,67 @@ MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, doubl
     bcov[0] = flb - bcon[0];
 #pragma unroll
     for (int i = 1; i < 4; i++) bcov[i] = fma(flb, l[i], bcon[i]);
-    double kdotu = fma(s[4], ucov[0], fma(s[5], ucov[1], fma(s[6], ucov[2], s[7] * ucov[3])));
-    double kdotb = fma(s[4], bcov[0], fma(s[5], bcov[1], fma(s[6], bcov[2], s[7] * bcov[3])));
-    double bsq = fma(bcon[0], bcov[0], fma(bcon[1], bcov[1], fma(bcon[2], bcov[2], bcon[3] * bcov[3])));
+    FrameScalars o;
+    o.kdotu = fma(s[4], ucov[0], fma(s[5], ucov[1], fma(s[6], ucov[2], s[7] * ucov[3])));
+    o.kdotb = fma(s[4], bcov[0], fma(s[5], bcov[1], fma(s[6], bcov[2], s[7] * bcov[3])));
+    o.bsq = fma(bcon[0], bcov[0], fma(bcon[1], bcov[1], fma(bcon[2], bcov[2], bcon[3] * bcov[3])));
+    return o;
+}
+
+// ... for an arbitrary spacetime given its covariant and contravariant metric at the sample (user-registered
+// plugins): athenak.py:760-786 term by term
+MK_HD FrameScalars frame_generic(const double g[4][4], const double gi[4][4], const double s[8], const double prims[8])
+{
+    const double* U = prims + 2;
+    const double* Bp = prims + 5;
+    double alpha = 1.0 / sqrt(-gi[0][0]);
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) q = fma(g[i + 1][j + 1] * U[i], U[j], q);
+    double gamma = sqrt(1.0 + q);
+    double ucon[4], ucov[4], bcon[4], bcov[4];
+    ucon[0] = gamma / alpha;
+#pragma unroll
+    for (int i = 1; i < 4; i++) ucon[i] = fma(-gamma * alpha, gi[0][i], U[i - 1]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) ucov[i] = fma(g[i][0], ucon[0], fma(g[i][1], ucon[1], fma(g[i][2], ucon[2], g[i][3] * ucon[3])));
+    bcon[0] = fma(Bp[0], ucov[1], fma(Bp[1], ucov[2], Bp[2] * ucov[3]));
+#pragma unroll
+    for (int i = 1; i < 4; i++) bcon[i] = fma(ucon[i], bcon[0], Bp[i - 1]) / ucon[0];
+#pragma unroll
+    for (int i = 0; i < 4; i++) bcov[i] = fma(g[i][0], bcon[0], fma(g[i][1], bcon[1], fma(g[i][2], bcon[2], g[i][3] * bcon[3])));
+    FrameScalars o;
+    o.kdotu = fma(s[4], ucov[0], fma(s[5], ucov[1], fma(s[6], ucov[2], s[7] * ucov[3])));
+    o.kdotb = fma(s[4], bcov[0], fma(s[5], bcov[1], fma(s[6], bcov[2], s[7] * bcov[3])));
+    o.bsq = fma(bcon[0], bcov[0], fma(bcon[1], bcov[1], fma(bcon[2], bcov[2], bcon[3] * bcov[3])));
+    return o;
+}
+
+// `sink(fq, em, ab)` receives the invariant emissivity and absorptivity of frequency fq as soon as they are known, so
+// that a multi-frequency caller can fold them into its accumulators without holding 2 NF values in registers.
+template <int NF, class Sink>
+MK_HD bool emission_from_frame(const EmissionParams& P, const EmissionConsts& C, const FrameScalars& fr,
+                               const double prims[8], Sink&& sink)
+{
+    // Straight-line code: every validity test only feeds the final select (invalid lanes may carry NaN/inf
+    // through the arithmetic, which is harmless on the GPU).  Early exits would make the compiler duplicate
+    // the copies of all loop-carried registers on every exit edge (~200 MOVs per sample in SASS).
+    const double dens = prims[0], u = prims[1];
+    // Theta_e = (const > 0) u / dens must reach 0.3, so dens and u have the same sign; both positive in any physical
+    // snapshot, both negative (Ne < 0: negative j and alpha in the reference too) kept for input-for-input parity
+    bool valid = ((dens > 0.0) & (u > 0.0)) | ((dens < 0.0) & (u < 0.0));
+    const double kdotu = fr.kdotu, kdotb = fr.kdotb, bsq = fr.bsq;
     valid &= (bsq > 0.0) & (kdotu < 0.0);
     double b, ib;
     quick_sqrt_rsqrt(bsq, b, ib);
     // cos(pitch), athenak.py:789-791.  The reference clamps it to [-1, 1]; a clamped value gives sin = 0, hence
     // nu_s = 0, X = inf and zero emissivity, which is what "sin2 > 0 fails" yields here without the clamp
     // (NaN also fails the test)
-    double c = kdotb * ib * fast_rcp(-kdotu);
+    double rn = -kdotu;
+    double irn = fast_rcp(rn);
+    double c = kdotb * ib * irn;
     double sin2 = (1.0 - c) * (1.0 + c);
     valid &= (sin2 > 0.0);
     double sinp = quick_sqrt(sin2);
@@ -576,7 +642,7 @@ MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, doubl
     double ith = fast_rcp(Theta);
     double pref = C.k_em * dens * nus * (ith * ith);
     // quantities of frequency 0; frequency f scales them by powers of nu_f / nu_0
-    double nu0 = -kdotu * C.nu0;
+    double nu0 = rn * C.nu0;
     double X0 = nu0 * inus;
     double ix13_0;
     double x13_0 = fast_cbrt_pos(X0, ix13_0);
@@ -584,8 +650,6 @@ MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, doubl
     double x16_0 = quick_sqrt(x13_0);
     double bx0 = C.k_bx * nu0 * ith;
     // invariant rescaling (transfer.py:77-80): nu * rescale_nu = (-k.u nu_f) / nu_f = -k.u for every frequency
-    double rn = -kdotu;
-    double irn = fast_rcp(rn);
     double irn2 = irn * irn;
     double inu0 = irn * C.inv_nu0;                               // 1 / (-k.u nu_0)
     double kab0 = C.k_ab * (inu0 * inu0 * inu0);
@@ -607,6 +671,16 @@ MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, doubl
         sink(fq, ok ? e : 0.0, ok ? a : 0.0);
     }
     return valid;
+}
+
+// Kerr-Schild front end (the fused kernel of the built-in spacetime and the emission probe)
+template <int NF, class Sink>
+MK_HD bool emission_fast(const EmissionParams& P, const EmissionConsts& C, double f, const double l[4],
+                         const double s[8], const double prims[8], const double* nu_obs, const double* inv_nu_obs,
+                         Sink&& sink)
+{
+    (void)nu_obs; (void)inv_nu_obs;
+    return emission_from_frame<NF>(P, C, frame_kerr_schild(f, l, s, prims), prims, sink);
 }
 
 }  // namespace mk

@@ -138,7 +138,12 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
         elif patch_order == "centre_out":
             order = centre_out_patch_order(res, dev)
     i = camera_inclination * np.pi / 180
-    _cabi.call("mk_render", float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
+    # spacetime of the launch: the built-in closed-form Kerr-Schild kernel, or the NVRTC-built kernel of the active
+    # run-time registered metric (geodesics AND fluid frame in that metric)
+    metric_id = geo._active_metric if geo._active_metric >= geo.PLUGIN_BASE else geo.KERR_SCHILD
+    if geo._active_metric == geo.KERR_SCHILD_STRICT:
+        raise ValueError("the strict (literal IEEE) integrator has no fused render: use make_image_unfused")
+    _cabi.call("mk_render_metric", int(metric_id), float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
                -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
                img, nsteps, counters[0:1] if want_counters else None, counters[1:2] if want_counters else None,
                queue, int(patch_range[0]), int(patch_range[1]), int(patch_range[2]) if len(patch_range) > 2 else 1,
@@ -159,11 +164,13 @@ def make_image(fluid_model, camera_inclination=60, camera_distance=1000,
     ``max_chunk_bytes`` is accepted for signature compatibility; the fused kernel stores no trajectories,
     so there is nothing to chunk (the unfused fallback for foreign fluid models does honour it).
     """
-    # The fused kernel integrates in the built-in Kerr-Schild spacetime.  With a user-registered spacetime selected
-    # (geodesics.set_metric) the image goes through the stage-by-stage chain, whose geodesic_integrator follows the
-    # active metric while the fluid frame stays Kerr-Schild -- what the reference does when its module-level
-    # metric is replaced (athenak.py:34 binds the Kerr-Schild metric at import).
-    if hasattr(fluid_model, "snapshot") and geo._active_metric in (geo.KERR_SCHILD, geo.KERR_SCHILD_DUAL):
+    # The fused kernel runs in the active spacetime: the built-in closed-form Kerr-Schild metric, or a user-registered
+    # one (geodesics.register_metric / set_metric), for which NVRTC built the same kernel around the user's metric --
+    # geodesics from its dual-number derivatives, fluid frame (athenak.py:760-786) from its g and g^-1 at every
+    # sample.  (The stage-by-stage chain make_image_unfused follows the active metric in the integrator only, its
+    # sampling kernel keeps the Kerr-Schild frame -- the reference's behaviour when only geodesics.metric is swapped,
+    # since athenak.py:34 binds the Kerr-Schild metric at import.)
+    if hasattr(fluid_model, "snapshot") and geo._active_metric != geo.KERR_SCHILD_STRICT:
         # the kernel stores the pixels straight into pinned host memory (mapped under unified addressing):
         # no device image, no separate device -> host copy
         host = _pinned_staging(resolution * resolution)

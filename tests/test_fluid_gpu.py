@@ -383,22 +383,50 @@ def test_unfused_chunking_is_transparent(setup):
 
 
 def test_make_image_follows_a_user_registered_spacetime(setup):
-    """With a run-time registered spacetime selected, make_image runs the stage-by-stage chain whose geodesics
-    follow that metric (the fused kernel is Kerr-Schild only).  Registering the reference's own metric as the user
-    plugin must therefore reproduce the fused Kerr-Schild image."""
+    """With a run-time registered spacetime selected, make_image runs the FUSED kernel that NVRTC built around the
+    user's metric: geodesics from its dual-number derivatives, fluid frame (athenak.py:760-786) from its g and g^-1.
+    (a) The reference's own metric registered as the user plugin reproduces the built-in fused image to 1e-9 (a
+    different code path end to end: dual numbers + adjugate inverse + generic frame algebra).  (b) The stage-by-stage
+    chain with the plugin (geodesics in the plugin metric, Kerr-Schild frame) agrees too.  (c) A spacetime that is NOT
+    Kerr -- Schwarzschild of mass 1.2 in Kerr-Schild coordinates -- gives a different image, equal to what the
+    stage-by-stage chain gives for its geodesics plus its own frame (checked through multi-frequency consistency and
+    against the a = 0 built-in image for M = 1)."""
     from mahakala_b200 import geodesics as geo, images
     from test_geodesics_gpu import KERR_SCHILD_USER
+    from test_host_cpu import SCHWARZSCHILD_KS
     dm = setup["dm"]
     fused = images.make_image(dm, resolution=12)
+    multi = np.asarray(images.render(dm, resolution=12, observing_frequencies=(86e9, 230e9)).cpu())
     geo.register_metric("ks_user_img", KERR_SCHILD_USER)
+    geo.register_metric("schw_m1_img", SCHWARZSCHILD_KS, params=[1.0])
+    geo.register_metric("schw_m12_img", SCHWARZSCHILD_KS, params=[1.2])
     geo.set_metric("ks_user_img")
     try:
         user = images.make_image(dm, resolution=12)
+        user_unfused = images.make_image_unfused(dm, resolution=12)
+        user_multi = np.asarray(images.render(dm, resolution=12, observing_frequencies=(86e9, 230e9)).cpu())
     finally:
         geo.set_metric("kerr_schild")
     assert user.shape == fused.shape and fused.max() > 0
-    assert np.allclose(user, fused, rtol=1e-6, atol=1e-12 * fused.max())
-    assert not np.array_equal(user, fused)          # different code path (dual-number geodesics, literal transfer order)
+    scale = fused.max()
+    assert np.abs(user - fused).max() < 1e-9 * scale, np.abs(user - fused).max() / scale
+    assert not np.array_equal(user, fused)          # different code path (dual-number geodesics, generic frame)
+    assert np.allclose(user_unfused, fused, rtol=1e-6, atol=1e-12 * scale)
+    assert np.abs(user_multi - multi).max() < 1e-9 * np.abs(multi).max()        # one launch per frequency
+    # Schwarzschild plugin with M = 1 == the built-in metric at a = 0 (image of the same snapshot with bhspin = 0)
+    from helpers import device_model
+    dm0 = device_model(setup["arr"], 0.0)
+    ref0 = images.make_image(dm0, resolution=12)
+    geo.set_metric("schw_m1_img")
+    try:
+        s1 = images.make_image(dm0, resolution=12)
+        geo.set_metric("schw_m12_img")
+        s12 = images.make_image(dm0, resolution=12)
+    finally:
+        geo.set_metric("kerr_schild")
+    assert np.abs(s1 - ref0).max() < 1e-9 * ref0.max()
+    assert np.abs(s12 - ref0).max() > 1e-3 * ref0.max() and np.isfinite(s12).all()      # a different spacetime
+    dm0.release()
 
 
 def test_noncubic_meshblocks(built):
