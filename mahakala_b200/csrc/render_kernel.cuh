@@ -100,8 +100,11 @@ template <> struct has_stage1_metric_functions<KerrSchild> { static constexpr bo
 #ifndef MK_RENDER_HI
 #define MK_RENDER_HI 4
 #endif
+// Largest NF that uses the stage-1-first loop.  Measured on B200 (cfg4, f64 cells, same box): one frequency 22.96-23.13
+// ms against 24.06 ms for the plain loop; two and more frequencies within noise of each other (25.6 / 27.1 / 31.6 vs
+// 25.6 / 26.6 / 31.4 ms for 2 / 4 / 8 frequencies), so only the single-frequency kernel takes it.
 #ifndef MK_RENDER_PIPE_MAX
-#define MK_RENDER_PIPE_MAX 0
+#define MK_RENDER_PIPE_MAX 1
 #endif
 // Experiment knob (off: 9 > max NF): from this many frequencies on, the (I, T) accumulators of a lane live in shared
 // memory ([2 NF][threads], conflict free) instead of registers.  Measured on B200 (cfg4, 8 frequencies): 40.1 ms

