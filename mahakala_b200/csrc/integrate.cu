@@ -15,7 +15,7 @@ namespace mk {
 // 4 CTAs (124 registers), the paged dump at 3 (its page bookkeeping fits in registers and the scattered
 // stores contend less): 25.9 -> 23.4 ms on cfg2.
 #ifndef MK_PAGED_CTAS
-#define MK_PAGED_CTAS 3
+#define MK_PAGED_CTAS 4
 #endif
 template <class Metric, int MODE, bool SHARED = false>
 __global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : 4)) integrate_kernel(const Metric g, const IntegrateArgs A)
@@ -80,7 +80,8 @@ static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_
     const bool shared = A.chunk_div > 0;       // set by mk_integrate_shared (number of GPUs on the queue)
     auto kern = A.pages ? (shared ? integrate_kernel<Metric, MODE_PAGED, true> : integrate_kernel<Metric, MODE_PAGED>)
                         : (A.S ? integrate_kernel<Metric, MODE_PADDED> : integrate_kernel<Metric, MODE_FINAL>);
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+    const size_t dyn_smem = (A.pages && MK_DUMP_TMA) ? 4 * DUMP_SMEM_PER_WARP : 0;      // TMA dump staging, 4 warps
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, dyn_smem));
     if (per_sm < 1) per_sm = 1;
     long warps_needed = (A.npx + 31) / 32;
     long blocks = (long)sm_count() * per_sm;
@@ -90,7 +91,7 @@ static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_
     IntegrateArgs B = A;
     B.chunk_div = (int)(4 * 4 * blocks) * (shared ? A.chunk_div : 1);     // 4 x warps x participating GPUs
     B.chunk_mul = (unsigned)(0x100000000ULL / (unsigned long long)B.chunk_div);
-    kern<<<(unsigned)blocks, 128, 0, stream>>>(g, B);
+    kern<<<(unsigned)blocks, 128, dyn_smem, stream>>>(g, B);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -13,7 +13,9 @@ namespace mk {
 // 256-bit global store (STG.E.256 on sm_100): one instruction per 32 B instead of two 128-bit stores
 __device__ __forceinline__ void store_256(double* p, double a, double b, double c, double d)
 {
-#ifndef __CUDACC_RTC__
+#if !defined(__CUDACC_RTC__) && defined(MK_DUMP_STREAMING)      // experiment: evict-first streaming stores for the dump
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#elif !defined(__CUDACC_RTC__)
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 #else   // NVRTC 12.9's embedded ptxas rejects 256-bit vector accesses: two 128-bit stores for run-time plugins
     reinterpret_cast<double2*>(p)[0] = make_double2(a, b);
@@ -53,6 +55,22 @@ struct IntegrateArgs {
 };
 
 constexpr int PAGE_SLOTS = 16;
+// Paged dump by direct 256-bit global stores (0, the product path) or through shared memory + TMA bulk stores (1, an
+// EXPERIMENT kept behind this switch; always 0 for run-time compiled metric plugins).  Measured on B200, cfg2, same
+// box, 4 CTAs/SM: direct stores 16.03 ms, TMA staging 17.28 ms (final-state mode without any dump: 14.9 ms).  The
+// staging costs more than it hides: the 64 B rows of 32 lanes conflict 4-way in shared memory (the layout in
+// shared memory has to be the layout in the page, a bulk copy is linear), plus two warp barriers and a proxy fence
+// per iteration, while the direct 256-bit stores were never the bottleneck of the write path -- the HBM write
+// stream itself is (2.5 TB/s of the 3.9 TB/s a write-only kernel reaches on this part).
+#ifndef MK_DUMP_TMA
+#define MK_DUMP_TMA 0
+#endif
+#ifdef __CUDACC_RTC__
+#undef MK_DUMP_TMA
+#define MK_DUMP_TMA 0
+#endif
+constexpr int DUMP_SLOT_BYTES = 32 * 72;            // 32 states of 64 B followed by 32 step sizes
+constexpr int DUMP_SMEM_PER_WARP = 2 * DUMP_SLOT_BYTES;
 // Rays are taken from the queue in chunks of up to QUEUE_CHUNK positions per warp, and the NEXT chunk is requested
 // while the current one is being consumed: the atomic's round trip (a few microseconds when the counter sits in a
 // peer GPU's memory across NVLink) overlaps the RK4 steps in between instead of stalling the warp at every refill.
@@ -111,6 +129,7 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
 {
     constexpr bool DUMP = (MODE == MODE_PADDED);
     int wpage = -1, wslot = 0, my_slot = 0;    // warp-uniform log position (MODE_PAGED)
+    int dump_count = 0;                        // slots handed to the TMA engine so far (warp-uniform)
     const unsigned lane = threadIdx.x & 31u;
     bool drained = false;           // queue exhausted (warp-uniform)
     long cur = 0, cur_end = 0;      // the warp's private range of queue positions (warp-uniform)
@@ -222,11 +241,11 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 A.page_first[2 * L.ray + 1] = my_slot * 32 + (int)lane;
             }
         }
-        if (!act) return true;
+        if (!(MODE == MODE_PAGED && MK_DUMP_TMA) && !act) return true;
 
         // ---- one iteration of geodesic_step ----
         double r_new = 0.0, dtn = 0.0;
-        if (L.dt != 0.0) {
+        if (act && L.dt != 0.0) {
             rk4_step(g, s, L.dt, sn, &cache);
             r_new = g.radius(sn, cn);
             dtn = A.rule(r_new);
@@ -240,7 +259,7 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 A.dt[(long)L.it * A.npx + L.ray] = frozen ? 0.0 : L.dt;
             }
         }
-        if (MODE == MODE_PAGED) {
+        if (MODE == MODE_PAGED && !MK_DUMP_TMA) {
             if (wpage >= 0) {
                 double* pg = A.pages + (long)wpage * PAGE_DOUBLES;
                 int rr = my_slot * 32 + (int)lane;
@@ -249,6 +268,41 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
                 pg[PAGE_SLOTS * 32 * 8 + rr] = frozen ? 0.0 : L.dt;
             }
         }
+#if MK_DUMP_TMA && !defined(__CUDACC_RTC__)
+        if (MODE == MODE_PAGED) {
+            // The warp's slot (32 rows of 64 B + 32 step sizes) is assembled in shared memory and leaves through the
+            // TMA engine as two bulk copies (2048 B + 256 B, UBLKCP in SASS): the lanes hand their rows to shared
+            // memory and go on stepping, they never wait on the HBM write path (2.5 TB/s of the 3.9 TB/s write-only
+            // bandwidth) as they do with direct stores.  Two buffers per warp; a buffer is reused once the bulk copy
+            // issued from it two iterations ago has read it (wait_group.read 1).  All 32 lanes arrive here (idle lanes
+            // skipped the step above), so lane 0 is always the issuer and owns the bulk async-groups.
+            if (wpage >= 0) {
+                extern __shared__ __align__(128) unsigned char mk_dump_smem[];
+                double* sbuf = reinterpret_cast<double*>(mk_dump_smem + ((threadIdx.x >> 5) * 2 + (dump_count & 1)) * DUMP_SLOT_BYTES);
+                if (lane == 0 && dump_count >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                if (act) {
+                    double2* row = reinterpret_cast<double2*>(sbuf + lane * 8);
+                    row[0] = make_double2(s[0], s[1]); row[1] = make_double2(s[2], s[3]);
+                    row[2] = make_double2(s[4], s[5]); row[3] = make_double2(s[6], s[7]);
+                    sbuf[256 + lane] = frozen ? 0.0 : L.dt;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    double* pg = A.pages + (long)wpage * PAGE_DOUBLES;
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(sbuf);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;"
+                                 :: "l"(pg + my_slot * 256), "r"(src) : "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;"
+                                 :: "l"(pg + PAGE_SLOTS * 256 + my_slot * 32), "r"(src + 2048u) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                dump_count++;
+            }
+            if (!act) return true;
+        }
+#endif
         bool done = frozen;
         bool capped = false;
         if (!frozen) {
@@ -292,6 +346,10 @@ __device__ __forceinline__ void integrate_body(const Metric& g, const IntegrateA
         if (!iteration(sa, ca, sb, cb)) break;      // live state: set A -> set B
         if (!iteration(sb, cb, sa, ca)) break;      // live state: set B -> set A
     }
+#if MK_DUMP_TMA && !defined(__CUDACC_RTC__)
+    if (MODE == MODE_PAGED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all slots have landed
+#endif
+    (void)dump_count;
     if (A.total_steps) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(FULL_MASK, my_steps, o);

@@ -35,15 +35,20 @@ static int launch_render(const KerrSchild& g, const RenderArgs& A, long npatches
 template <int NF, int KIND>
 static int launch_render_kind(const KerrSchild& g, const RenderArgs& A, long npatches, cudaStream_t stream)
 {
+#ifdef MK_RENDER_SMEM_STAGE
+    const size_t dyn_smem = (MK_RENDER_THREADS / 32) * (1728 + 8);
+#else
+    const size_t dyn_smem = 0;
+#endif
     int per_sm = 0;
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF, KIND>, MK_RENDER_THREADS, 0));
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<NF, KIND>, MK_RENDER_THREADS, dyn_smem));
     if (per_sm < 1) per_sm = 1;
     long blocks = (long)sm_count() * per_sm;
     const long warps = MK_RENDER_THREADS / 32;
     long need = (npatches + warps - 1) / warps;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
-    render_kernel<NF, KIND><<<(unsigned)blocks, MK_RENDER_THREADS, 0, stream>>>(g, A);
+    render_kernel<NF, KIND><<<(unsigned)blocks, MK_RENDER_THREADS, dyn_smem, stream>>>(g, A);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

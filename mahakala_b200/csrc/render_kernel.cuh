@@ -123,6 +123,23 @@ __device__ __forceinline__ void render_body(const Metric& G, const RenderArgs& A
 {
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long my_steps = 0, my_samples = 0;
+#ifdef MK_RENDER_SMEM_STAGE
+    // experiment: per-warp brick of staged cells + mbarrier in dynamic shared memory (f64 grid snapshots only)
+    extern __shared__ __align__(128) unsigned char mk_dyn_smem[];
+    CellStage stage;
+    stage.brick = reinterpret_cast<double*>(mk_dyn_smem) + (threadIdx.x >> 5) * 216;
+    stage.bar = reinterpret_cast<unsigned long long*>(mk_dyn_smem + (MK_RENDER_THREADS / 32) * 1728) + (threadIdx.x >> 5);
+    if (KIND == SNAP_F64_GRID_POW2) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(stage.bar)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+#define MK_INTERP(sn, s, prims) ((KIND == SNAP_F64_GRID_POW2) ? interp_prims_staged(sn, s, prims, stage) : interp_prims_kind<KIND>(sn, s, prims))
+#else
+#define MK_INTERP(sn, s, prims) interp_prims_kind<KIND>(sn, s, prims)
+#endif
 
     for (;;) {
         // ---- next patch ----
@@ -187,10 +204,27 @@ __device__ __forceinline__ void render_body(const Metric& G, const RenderArgs& A
                 if (active) {
                     double a1[4];
                     KerrSchild::MetricFunctions mf;
+#if defined(MK_RENDER_PREFETCH)
+                    // experiment: cell addresses first, a prefetch of the four rows, then the first RK4 stage, then the
+                    // gather -- the stage's ~90 FP64 operations cover the L2 latency of the rows
+                    CellRef cref;
+                    bool located = false;
+                    if (KIND == SNAP_F64_GRID_POW2 && pending) {
+                        located = locate_cells_f64(A.sn, s, cref);
+                        if (located) prefetch_cells_f64(A.sn, cref);
+                    }
+#endif
                     G.accel(s, s + 4, a1, &cache, &mf);
                     if (pending) {
                         double prims[8];
-                        if (interp_prims_kind<KIND>(A.sn, s, prims)) {
+#if defined(MK_RENDER_PREFETCH)
+                        bool inside = located;
+                        if (KIND == SNAP_F64_GRID_POW2) { if (located) gather_cells_f64(A.sn, cref, prims); }
+                        else inside = MK_INTERP(A.sn, s, prims);
+                        if (inside) {
+#else
+                        if (MK_INTERP(A.sn, s, prims)) {
+#endif
                             my_samples++;
                             const double l[4] = {1.0, mf.l1, mf.l2, mf.l3};
                             emission_fast<NF>(A.P, A.C, mf.f, l, s, prims, A.nu_obs, A.inv_nu_obs,
@@ -231,7 +265,7 @@ __device__ __forceinline__ void render_body(const Metric& G, const RenderArgs& A
                             active = false;         // row N is not part of the reference's scan output
                         } else {
                             double prims[8];
-                            if (interp_prims_kind<KIND>(A.sn, s, prims)) {
+                            if (MK_INTERP(A.sn, s, prims)) {
                                 my_samples++;
                                 // each frequency is folded into (I, T) as soon as its coefficients exist
                                 // (em = ab = 0 leaves them unchanged)

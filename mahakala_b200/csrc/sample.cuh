@@ -293,6 +293,158 @@ MK_HD void trilinear(const SnapshotView& sn, int mb, const BlockGeom& geo, const
     }
 }
 
+#if defined(MK_RENDER_SMEM_STAGE) && !defined(__CUDACC_RTC__)
+// EXPERIMENT (compiled only with -DMK_RENDER_SMEM_STAGE; scripts/build_variant.sh): the north_star's "hot cells staged in
+// shared memory".  The lanes of a warp sample a 4x8-pixel patch, far smaller than a cell, so the union of their 2x2x2
+// corner cells is almost always one 3x3x3 brick of a single meshblock.  One elected lane fetches that brick with nine
+// TMA bulk copies (cp.async.bulk, 3 cells = 192 B per row) signalled on the warp's mbarrier; every lane then reads its
+// eight corners from shared memory.  Measured against the direct 256-bit read-only loads: see DESIGN.md.
+struct CellStage {
+    double* brick;                 // [3][3][3][8] doubles of this warp
+    unsigned long long* bar;       // the warp's mbarrier
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void trilinear_staged(const SnapshotView& sn, int mb, const BlockGeom& geo, const double x[4],
+                                                 double prims[8], const CellStage& st)
+{
+    int i1, i2, i3;
+    double d1, d2, d3;
+    double inv[3];
+    load_inv_dx(sn, mb, inv);
+    cell_index(x[1], geo.v0[0], geo.dx[0], inv[0], true, i1, d1);
+    cell_index(x[2], geo.v0[1], geo.dx[1], inv[1], true, i2, d2);
+    cell_index(x[3], geo.v0[2], geo.dx[2], inv[2], true, i3, d3);
+    i1 = min(max(i1, 0), sn.ni); i2 = min(max(i2, 0), sn.nj); i3 = min(max(i3, 0), sn.nk);
+    const long sj = sn.sj, sk = sn.sk;
+    const unsigned mask = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    const int mb0 = __shfl_sync(mask, mb, leader);
+    const int m1 = __reduce_min_sync(mask, i1), m2 = __reduce_min_sync(mask, i2), m3 = __reduce_min_sync(mask, i3);
+    const int M1 = __reduce_max_sync(mask, i1), M2 = __reduce_max_sync(mask, i2), M3 = __reduce_max_sync(mask, i3);
+    // the brick starts at (m3, m2, m1) and spans 3 cells per axis; rows must stay inside the padded block
+    const bool fits = __all_sync(mask, mb == mb0) && (M1 - m1 <= 1) && (M2 - m2 <= 1) && (M3 - m3 <= 1) &&
+                      (m1 + 2 <= sn.ni + 1) && (m2 + 2 <= sn.nj + 1) && (m3 + 2 <= sn.nk + 1);
+    const double e1 = 1.0 - d1, e2 = 1.0 - d2, e3 = 1.0 - d3;
+#pragma unroll
+    for (int q = 0; q < 8; q++) prims[q] = 0.0;
+    if (fits) {
+        unsigned long long token = 0;
+        const unsigned bar = smem_addr(st.bar);
+        if ((int)lane == leader) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // earlier generic reads of the brick are done
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(token) : "r"(bar), "r"(27 * 64) : "memory");
+            const double* base = reinterpret_cast<const double*>(sn.cells) + (mb0 * sn.sb + m3 * sk + m2 * sj + (long)(m1 * 8));
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                const double* src = base + (r / 3) * sk + (r % 3) * sj;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_addr(st.brick + r * 24)), "l"(src), "r"(192), "r"(bar) : "memory");
+            }
+        }
+        token = __shfl_sync(mask, token, leader);
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "l"(token) : "memory");
+        const double* cell = st.brick + (((i3 - m3) * 3 + (i2 - m2)) * 3 + (i1 - m1)) * 8;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double w = ((c & 2) ? d3 : e3) * ((c & 1) ? d2 : e2);
+            const double w0 = w * e1, w1 = w * d1;
+            const double* p = cell + ((c & 2) ? 72 : 0) + ((c & 1) ? 24 : 0);
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) {
+                const double2 a = *reinterpret_cast<const double2*>(p + q), b = *reinterpret_cast<const double2*>(p + 8 + q);
+                prims[q] = fma(w0, a.x, fma(w1, b.x, prims[q]));
+                prims[q + 1] = fma(w0, a.y, fma(w1, b.y, prims[q + 1]));
+            }
+        }
+        __syncwarp(mask);          // every lane has read its corners before the brick is overwritten again
+    } else {
+        const double* base = reinterpret_cast<const double*>(sn.cells) + (mb * sn.sb + i3 * sk + i2 * sj + (long)(i1 * 8));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double w = ((c & 2) ? d3 : e3) * ((c & 1) ? d2 : e2);
+            const double w0 = w * e1, w1 = w * d1;
+            double a[8], b[8];
+            load_cell_pair(base + ((c & 2) ? sk : 0) + ((c & 1) ? sj : 0), a, b);
+#pragma unroll
+            for (int q = 0; q < 8; q++) prims[q] = fma(w0, a[q], fma(w1, b[q], prims[q]));
+        }
+    }
+}
+
+__device__ __forceinline__ bool interp_prims_staged(const SnapshotView& sn, const double x[4], double prims[8], const CellStage& st)
+{
+    BlockGeom geo;
+    int mb = locate_block_grid(sn, x, geo);
+    if (mb < 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) prims[q] = 0.0;
+        return false;
+    }
+    trilinear_staged(sn, mb, geo, x, prims, st);
+    return true;
+}
+#endif
+
+// Split form of the specialised f64 sampling path: locate (block, cell, weights) first, gather later -- lets a caller
+// put independent work (and a prefetch of the four 128 B cell rows) between the address and its first use.
+struct CellRef {
+    const double* base;        // first of the eight corner cells
+    double d1, d2, d3;         // fractional position inside the cell
+};
+
+MK_HD bool locate_cells_f64(const SnapshotView& sn, const double x[4], CellRef& ref)
+{
+    BlockGeom geo;
+    int mb = locate_block_grid(sn, x, geo);
+    if (mb < 0) return false;
+    int i1, i2, i3;
+    double inv[3];
+    load_inv_dx(sn, mb, inv);
+    cell_index(x[1], geo.v0[0], geo.dx[0], inv[0], true, i1, ref.d1);
+    cell_index(x[2], geo.v0[1], geo.dx[1], inv[1], true, i2, ref.d2);
+    cell_index(x[3], geo.v0[2], geo.dx[2], inv[2], true, i3, ref.d3);
+    i1 = min(max(i1, 0), sn.ni); i2 = min(max(i2, 0), sn.nj); i3 = min(max(i3, 0), sn.nk);
+    ref.base = reinterpret_cast<const double*>(sn.cells) + (mb * sn.sb + i3 * sn.sk + i2 * sn.sj + (long)(i1 * 8));
+    return true;
+}
+
+MK_HD void prefetch_cells_f64(const SnapshotView& sn, const CellRef& ref)
+{
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const double* p = ref.base + ((c & 2) ? sn.sk : 0) + ((c & 1) ? sn.sj : 0);
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 15));          // a cell pair may straddle two 128 B lines
+    }
+#else
+    (void)sn; (void)ref;
+#endif
+}
+
+MK_HD void gather_cells_f64(const SnapshotView& sn, const CellRef& ref, double prims[8])
+{
+    const double d1 = ref.d1, d2 = ref.d2, d3 = ref.d3;
+    const double e1 = 1.0 - d1, e2 = 1.0 - d2, e3 = 1.0 - d3;
+#pragma unroll
+    for (int q = 0; q < 8; q++) prims[q] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const double w = ((c & 2) ? d3 : e3) * ((c & 1) ? d2 : e2);
+        const double w0 = w * e1, w1 = w * d1;
+        double a[8], b[8];
+        load_cell_pair(ref.base + ((c & 2) ? sn.sk : 0) + ((c & 1) ? sn.sj : 0), a, b);
+#pragma unroll
+        for (int q = 0; q < 8; q++) prims[q] = fma(w0, a[q], fma(w1, b[q], prims[q]));
+    }
+}
+
 // Analytic torus primitives in canonical order; zero outside r <= r_out (the model's "domain").  Same formulas as
 // mahakala_b200/synthetic.py::torus_fields (no waves); divisions, square roots and the two Gaussians use the
 // MUFU-seeded FP64 helpers (<= few ulp; the exponentials flush results below 1e-307 to zero).

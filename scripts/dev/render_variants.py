@@ -18,6 +18,7 @@ def timeit(fn, n=4):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return min(ts)
 m = model(); m64 = model(storage="f64")
+print("%%-8s image sums f32 cells %%.15e  f64 cells %%.15e" %% (sys.argv[1], float(images.render(m, resolution=1024).sum()), float(images.render(m64, resolution=1024).sum())), flush=True)
 F8 = [43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9]
 print("%%-8s 1f %%.2f  1f-f64cells %%.2f  2f %%.2f  4f %%.2f  8f %%.2f ms" %% (sys.argv[1], timeit(lambda: images.render(m, resolution=1024)),
       timeit(lambda: images.render(m64, resolution=1024)), timeit(lambda: images.render(m, resolution=1024, observing_frequencies=F8[2:4])),
