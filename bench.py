@@ -440,8 +440,10 @@ def run_b200(args):
                          "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "peak_source": "measured on this GPU by mk_measure_fp64_peak (DFMA microbenchmark); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
-                         "flop_per_ray_step": FLOP_PER_RAY_STEP, "traffic": measured_traffic(bool(pages_used), args.res),
-                         "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                         "flop_per_ray_step": FLOP_PER_RAY_STEP, "traffic": measured_traffic(bool(pages_used), args.res)[0],
+                         "traffic_source": "static: " + str(measured_traffic(bool(pages_used), args.res)[1]) +
+                                           " (committed ncu capture of this kernel at this shape, dram__bytes_read.sum + "
+                                           "dram__bytes_write.sum of one launch; not re-measured in this run)",
                          "hbm": {"dump_bytes_per_launch": dump_bytes,
                                  "achieved_GBps": dump_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "peak_GBps": hbm_peak()}},
@@ -474,15 +476,18 @@ def run_b200(args):
 
 def measured_traffic(paged, res):
     """dram__bytes_read + dram__bytes_write of one launch of the dominant kernel at cfg2, from the committed
-    single-pass ncu measurement (profiles/r01_traffic.json); None for other shapes."""
+    single-pass ncu measurement (newest profiles/rNN_traffic.json); (None, None) for other shapes."""
     if res != 1024:
-        return None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = [k for k in t if ("MODE_PAGED" if paged else "MODE_FINAL") in k][0]
-        return int(t[key]["dram_bytes_read"]) + int(t[key]["dram_bytes_write"])
-    except Exception:
-        return None
+        return None, None
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")), reverse=True):
+        try:
+            t = json.load(open(path))
+            key = [k for k in t if ("MODE_PAGED" if paged else "MODE_FINAL") in k][0]
+            return int(t[key]["dram_bytes_read"]) + int(t[key]["dram_bytes_write"]), os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 def hbm_peak():

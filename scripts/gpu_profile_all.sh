@@ -1,8 +1,9 @@
 #!/bin/bash
 # Run on a B200 (gpurun): collects everything scripts/refresh_profiles.sh turns into profiles/.
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_r01_n1.json 2> gpurun_out/bench_n1.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r01_ref.json 2> gpurun_out/bench_ref.err
+R=${ROUND:-r02}
+python bench.py > gpurun_out/bench_${R}_n1.json 2> gpurun_out/bench_n1.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${R}_ref.json 2> gpurun_out/bench_ref.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --strong-res 0 > gpurun_out/launches_bench.log 2>&1
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
