@@ -187,7 +187,10 @@ def workload_config(args, mode):
             "l2_policy": "256 MiB scratch write between timed iterations (L2 flush); the dump itself is >> L2",
             "multi_gpu": ("N frames (one per GPU, inclinations " + ", ".join(f"{i:g}" for i in WEAK_INCLINATIONS) +
                           " deg in rank order) integrated by ALL GPUs together: one dynamic ray queue in rank 0's "
-                          "memory shared over NVLink (system-scope atomics, chunked + prefetched), longest rays first, "
+                          "memory shared over NVLink (system-scope atomics, chunked + prefetched), rays handed out in " +
+                          ("pixel order with the frames interleaved, " if os.environ.get("MK_BENCH_ORDER", "pixel") == "pixel"
+                           else "centre-out order (long photon-ring rays first) with the frames interleaved, ") +
+                          "N = 1: the plain public call on the GPU's own queue; "
                           "per-ray results stored by the kernels straight into rank 0's memory (in-kernel gather), "
                           "trajectories paged where they are computed; weak scaling, no data-path collective")}
 
@@ -235,16 +238,19 @@ def run_b200(args):
     launches = [0]
     shared = None
     from mahakala_b200 import multigpu
+    ORDER = os.environ.get("MK_BENCH_ORDER", "pixel")          # 'pixel' (frames interleaved) | 'centre' (centre-out)
+    make_order = multigpu.interleaved_pixel_ray_order if ORDER == "pixel" else multigpu.longest_first_ray_order
     if world == 1:
-        # the same launch as the N > 1 job with N = 1: rays handed out longest first from a (here local) queue
-        order = torch.from_numpy(multigpu.longest_first_ray_order(res, 1)).to(dev)
+        # one GPU: the plain public call (the GPU's own queue, pixel order).  MK_BENCH_SHARED=1 runs the launch of the
+        # N > 1 job with N = 1 instead (measured 16.3 ms in pixel order, 17.1 ms centre-out, against 16.1 ms)
+        order = torch.from_numpy(make_order(res, 1)).to(dev) if os.environ.get("MK_BENCH_SHARED") == "1" else None
         local_queue = torch.zeros(64, dtype=torch.int32, device=dev)
     if world > 1:
         # BASELINE north_star split: ONE job of `world` frames, every GPU holds all bundles, rays come from one queue
         frames = [WEAK_INCLINATIONS[f % len(WEAK_INCLINATIONS)] for f in range(world)]
         s0_all = torch.cat([ma.initialize_geodesics_at_camera(a, frames[f], CFG2["distance"], -CFG2["fov"] / 2,
                                                               CFG2["fov"] / 2, res) for f in range(world)])
-        order = torch.from_numpy(multigpu.longest_first_ray_order(res, world)).to(dev)
+        order = torch.from_numpy(make_order(res, world)).to(dev)
         shared = multigpu.SharedRays(world * npx)
         job_store = geo.TrajectoryStore.allocate(world * npx, CFG2["N"], mem_fraction=0.45)
     store = geo.TrajectoryStore.allocate(npx, CFG2["N"], mem_fraction=0.55 if world > 1 else 0.6)
@@ -257,8 +263,11 @@ def run_b200(args):
                                 page_id_offset=rank << multigpu.PAGE_RANK_SHIFT, participants=world)
             launches[0] += 1
             return job_store.total_steps
-        out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store, queue=local_queue,
-                                  ray_order=order)                                        # resets the store
+        if order is None:
+            out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store)        # resets the store
+        else:
+            out = geo.integrate_paged(CFG2["N"], s0, CFG2["div"], CFG2["tol"], a, store=store, queue=local_queue,
+                                      ray_order=order)
         launches[0] += 1
         return out.total_steps
 

@@ -174,6 +174,17 @@ def longest_first_ray_order(res, frames=1):
     return order.astype(np.int32)
 
 
+def interleaved_pixel_ray_order(res, frames=1):
+    """Queue order for ``frames`` bundles stored back to back: pixel order, frames interleaved (queue position q ->
+    frame q % frames, pixel q // frames), so that all frames progress together and every GPU sees the same mix of long
+    and short rays at any time.  Measured on B200 (cfg2, paged dump, one GPU, L2 flushed between launches,
+    ``scripts/dev/order_matrix_probe.py``): pixel order 16.3 ms against 17.1 ms centre-out -- with the dump, warps that
+    all hold rays of the same length stay in lock-step and their slot stores arrive in bursts."""
+    pix = np.arange(res * res, dtype=np.int64)
+    order = (np.arange(frames, dtype=np.int64)[None, :] * (res * res) + pix[:, None]).reshape(-1)
+    return order.astype(np.int32)
+
+
 def integrate_distributed(N, s0, div, tol, bhspin, store, shared, ray_order=None):
     """Integrate ONE bundle ``s0`` (n, 8), resident on every rank, with all ranks together (trajectory-dump mode).
 
