@@ -605,7 +605,7 @@ def render_leg(args, rank, world, dev, fp64_peak):
         if learned:
             images.learn_patch_order(CFG2["bhspin"], camera_inclination=CFG2["inclination"], resolution=sres)
         else:
-            images._learned_order.clear()
+            images._learned_order.clear(); images._learned_lengths.clear()
         shared = multigpu.SharedImage(1, sres * sres) if world > 1 else None
         st = []
         for it in range(1 + reps):
@@ -618,7 +618,8 @@ def render_leg(args, rank, world, dev, fp64_peak):
             e0.record()
             if world > 1:
                 images.render(model, camera_inclination=CFG2["inclination"], resolution=sres,
-                              observing_frequencies=(230e9,), image_out=shared.image_ptr, queue=shared.queue_ptr)
+                              observing_frequencies=(230e9,), image_out=shared.image_ptr, queue=shared.queue_ptr,
+                              long_queue=shared.ring_queue_ptr, participants=world)
             else:
                 out = images.render(model, camera_inclination=CFG2["inclination"], resolution=sres,
                                     observing_frequencies=(230e9,))
@@ -704,7 +705,7 @@ def render_leg(args, rank, world, dev, fp64_peak):
     strong, flux, same, worst = strong_leg(res, 3) if world > 1 else (0.0, 0.0, None, None)
     strong_l, _, same_l, _ = strong_leg(res, 3, learned=True)
     strong_big, flux_big, same_big, worst_big = strong_leg(args.strong_res, 2) if args.strong_res > 0 else (0.0, 0.0, None, None)
-    images._learned_order.clear()
+    images._learned_order.clear(); images._learned_lengths.clear()
     t = torch.tensor([float(np.mean(times)), float(np.mean(e2e_times)), strong, bcast_ms, strong_big, strong_l], dtype=torch.float64, device=dev)
     w = torch.tensor([float(counters[0]), float(counters[1])], dtype=torch.float64, device=dev)
     if world > 1:

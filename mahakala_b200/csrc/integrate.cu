@@ -17,8 +17,11 @@ namespace mk {
 #ifndef MK_PAGED_CTAS
 #define MK_PAGED_CTAS 4
 #endif
+#ifndef MK_INT_CTAS           // experiment knob: resident CTAs of the final / padded modes (1 -> 255 registers)
+#define MK_INT_CTAS 4
+#endif
 template <class Metric, int MODE, bool SHARED = false>
-__global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : 4)) integrate_kernel(const Metric g, const IntegrateArgs A)
+__global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : MK_INT_CTAS)) integrate_kernel(const Metric g, const IntegrateArgs A)
 {
     integrate_body<Metric, MODE, SHARED>(g, A);
 }

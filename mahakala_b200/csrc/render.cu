@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "render_kernel.cuh"
+#include "render_pipeline.cuh"
 #include "snapshot.cuh"
 #include "plugin.cuh"
 #include "../../include/mahakala_b200.h"
@@ -14,6 +15,28 @@ template <int NF, int KIND>
 __global__ void MK_RENDER_BOUNDS render_kernel(const KerrSchild g, const RenderArgs A)
 {
     render_body<KerrSchild, NF, KIND>(g, A);
+}
+
+// long-patch variant: producer warp (geodesic) + consumer warps (sample, emission), see render_pipeline.cuh
+template <int KIND>
+__global__ void __launch_bounds__(PIPE_THREADS, 4) render_pipeline_kernel(const KerrSchild g, const RenderArgs A)
+{
+    render_pipeline_body<KIND>(g, A);
+}
+
+template <int KIND>
+static int launch_pipeline_kind(const KerrSchild& g, const RenderArgs& A, long npatches, int ctas_per_sm, cudaStream_t stream)
+{
+    int per_sm = 0;
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pipeline_kernel<KIND>, PIPE_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (ctas_per_sm >= 1 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
+    long blocks = (long)sm_count() * per_sm;        // one patch per CTA at a time
+    if (npatches < blocks) blocks = npatches;
+    if (blocks < 1) blocks = 1;
+    render_pipeline_kernel<KIND><<<(unsigned)blocks, PIPE_THREADS, 0, stream>>>(g, A);
+    MK_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 // (Round 1 kept an experimental lane-refill variant of this kernel here: incoherent warps lose the L1 locality of
@@ -68,7 +91,7 @@ static int render_impl(int metric_id, double bhspin, double cos_i, double sin_i,
                        const double* nu_obs, double* image, int32_t* nsteps,
                        unsigned long long* total_steps, unsigned long long* total_samples,
                        unsigned int* queue, long patch_begin, long patch_end, long patch_stride,
-                       const int* patch_order, cudaStream_t stream)
+                       const int* patch_order, cudaStream_t stream, int pipeline_ctas_per_sm = -1)
 {
     MK_REQUIRE(snap && params && nu_obs && image, "null pointer");
     MK_REQUIRE(nfreq >= 1 && nfreq <= 8, "nfreq must be in 1..8");
@@ -121,6 +144,15 @@ static int render_impl(int metric_id, double bhspin, double cos_i, double sin_i,
                "the fused render runs with the built-in Kerr-Schild spacetime or a registered one");
     A.queue = queue ? queue : queue_counter(stream, 1);
     if (!A.queue) return 1;
+    if (pipeline_ctas_per_sm >= 0) {
+        MK_REQUIRE(nfreq == 1 && metric_id == MK_METRIC_KERR_SCHILD,
+                   "the long-patch pipeline carries one frequency in the built-in Kerr-Schild spacetime");
+        switch (snapshot_kind(A.sn)) {
+            case SNAP_F64_GRID_POW2: return launch_pipeline_kind<SNAP_F64_GRID_POW2>(g, A, span, pipeline_ctas_per_sm, stream);
+            case SNAP_F32_GRID_POW2: return launch_pipeline_kind<SNAP_F32_GRID_POW2>(g, A, span, pipeline_ctas_per_sm, stream);
+            default: return launch_pipeline_kind<SNAP_GENERIC>(g, A, span, pipeline_ctas_per_sm, stream);
+        }
+    }
     if (nfreq == 1) return launch_render<1>(g, A, span, stream);
     if (nfreq == 2) return launch_render<2>(g, A, span, stream);
     if (nfreq == 3) return launch_render<3>(g, A, span, stream);
@@ -142,6 +174,19 @@ extern "C" int mk_render(double bhspin, double cos_i, double sin_i, double dista
     return render_impl(MK_METRIC_KERR_SCHILD, bhspin, cos_i, sin_i, distance, fov_lower, fov_upper, res, s0, npx, N, div,
                        tol, snap, params, nfreq, nu_obs, image, nsteps, total_steps, total_samples, queue, patch_begin,
                        patch_end, patch_stride, patch_order, (cudaStream_t)stream_);
+}
+
+extern "C" int mk_render_long(double bhspin, double cos_i, double sin_i, double distance, double fov_lower,
+                              double fov_upper, long res, const double* s0, long npx, long N, double div,
+                              double tol, const mk_snapshot* snap, const mk_emission_params* params, int nfreq,
+                              const double* nu_obs, double* image, int32_t* nsteps,
+                              unsigned long long* total_steps, unsigned long long* total_samples,
+                              unsigned int* queue, long patch_begin, long patch_end, long patch_stride,
+                              const int* patch_order, int ctas_per_sm, void* stream_)
+{
+    return render_impl(MK_METRIC_KERR_SCHILD, bhspin, cos_i, sin_i, distance, fov_lower, fov_upper, res, s0, npx, N, div,
+                       tol, snap, params, nfreq, nu_obs, image, nsteps, total_steps, total_samples, queue, patch_begin,
+                       patch_end, patch_stride, patch_order, (cudaStream_t)stream_, ctas_per_sm < 0 ? 0 : ctas_per_sm);
 }
 
 extern "C" int mk_render_metric(int metric_id, double bhspin, double cos_i, double sin_i, double distance,

@@ -54,6 +54,29 @@ def centre_out_patch_order(res, device):
 
 
 _learned_order = {}
+_learned_lengths = {}        # same keys: steps of the longest ray of every patch, in the learned (descending) order
+_priority_streams = {}
+
+
+def _priority_stream(dev):
+    if dev not in _priority_streams:
+        _priority_streams[dev] = torch.cuda.Stream(device=dev, priority=-1)
+    return _priority_streams[dev]
+
+
+def long_patch_count(lengths, participants=1, threshold=None, device=None):
+    """How many patches at the head of a learned (longest-first) order go to the warp-specialised long-patch kernel
+    (``mk_render_long``): those whose longest ray takes at least ``threshold`` x the longest ray of the frame (default
+    0.3, ``MK_LONG_THRESHOLD``), at most one per SM of every participating GPU -- each of them then owns a CTA from
+    time zero, and three quarters of every SM stay with the bulk kernel."""
+    import os
+    if lengths is None or len(lengths) == 0 or lengths[0] <= 0:
+        return 0
+    if threshold is None:
+        threshold = float(os.environ.get("MK_LONG_THRESHOLD", "0.3"))
+    n = int((lengths >= threshold * float(lengths[0])).sum())
+    sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+    return max(0, min(n, int(participants) * sms))
 
 
 def _camera_key(bhspin, camera_inclination, camera_distance, fov, resolution, max_nsteps, div, tol, device):
@@ -79,20 +102,27 @@ def learn_patch_order(bhspin, camera_inclination=60, camera_distance=1000, fov=2
     img[:res, :res] = nsteps.view(res, res)
     longest = img.view(px_n, 4, py_n, 8).amax(dim=(1, 3)).reshape(-1)          # patch index = px * py_n + py
     order = torch.argsort(longest, descending=True, stable=True).to(torch.int32)
-    _learned_order[_camera_key(bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)] = order
+    key = _camera_key(bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)
+    _learned_order[key] = order
+    _learned_lengths[key] = longest[order.long()].cpu().numpy()
     return order
 
 
 def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26, M_bh=6.2e9 * Msun,
            r_high=40, observing_frequencies=(230.e9,), fov=20, resolution=160, max_nsteps=10000, s0=None,
            div=40, tol=1e-4, image_out=None, queue=None, patch_range=(0, -1, 1), want_counters=False,
-           patch_order="auto"):
+           patch_order="auto", long_patches="auto", long_queue=None, participants=1):
     """Fused multi-frequency render.  Returns ``image (nfreq, npx)`` on the device (plus counters).
 
     ``s0`` (npx, 8) replaces the grid camera by explicit rays.  ``image_out`` / ``queue`` may be tensors
     or raw device pointers (possibly in a peer GPU's memory) — see ``mahakala_b200.multigpu``.
     ``patch_order``: 'auto' = the order learned for this camera by ``learn_patch_order`` if there is one, else
     'centre_out'; 'centre_out'; None = row-major; or an int32 device tensor.
+    ``long_patches``: how many patches at the head of ``patch_order`` run through the warp-specialised long-patch kernel
+    (``mk_render_long``: the sample leaves the critical path of the ray's dependent RK4 steps) on a high-priority
+    stream next to the bulk launch; 'auto' = ``long_patch_count`` of the learned order (0 without one); one frequency,
+    built-in spacetime, grid camera, whole frames only.  ``long_queue``: its queue counter when ``queue`` is shared by
+    several GPUs (``participants`` of them); pixels are bit-identical either way.
     """
     dev = require_gpu()
     snap = fluid_model.snapshot()
@@ -127,12 +157,14 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
     nsteps = None
     counters = torch.zeros(2, dtype=torch.int64, device=dev) if want_counters else None
     order = None
+    lengths = None
     if s0d is None:
         if isinstance(patch_order, torch.Tensor):
             order = patch_order
         elif patch_order == "auto":
-            order = _learned_order.get(_camera_key(fluid_model.bhspin, camera_inclination, camera_distance, fov, res,
-                                                   max_nsteps, div, tol, dev))
+            key = _camera_key(fluid_model.bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)
+            order = _learned_order.get(key)
+            lengths = _learned_lengths.get(key) if order is not None else None
             if order is None:
                 order = centre_out_patch_order(res, dev)
         elif patch_order == "centre_out":
@@ -143,11 +175,31 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
     metric_id = geo._active_metric if geo._active_metric >= geo.PLUGIN_BASE else geo.KERR_SCHILD
     if geo._active_metric == geo.KERR_SCHILD_STRICT:
         raise ValueError("the strict (literal IEEE) integrator has no fused render: use make_image_unfused")
+    whole = tuple(patch_range[:2]) == (0, -1) and (len(patch_range) < 3 or patch_range[2] == 1)
+    n_long = 0
+    if order is not None and whole and nfreq == 1 and metric_id == geo.KERR_SCHILD and (queue is None) == (long_queue is None):
+        if long_patches == "auto":
+            n_long = long_patch_count(lengths, participants, device=dev)
+        elif long_patches:
+            n_long = min(int(long_patches), int(order.numel()))
+    c_steps = counters[0:1] if want_counters else None
+    c_samples = counters[1:2] if want_counters else None
+    if n_long > 0:
+        # positions [0, n_long) of the order: long-patch kernel, launched first on a high-priority stream (its CTAs are
+        # placed before the bulk kernel's, one per SM); the rest: the fused kernel on the caller's stream
+        cur, side = torch.cuda.current_stream(), _priority_stream(dev)
+        side.wait_stream(cur)
+        _cabi.call("mk_render_long", float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
+                   -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
+                   img, nsteps, c_steps, c_samples, long_queue, 0, n_long, 1, order, 1, side.cuda_stream)
+        patch_range = (n_long, -1, 1)
     _cabi.call("mk_render_metric", int(metric_id), float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
                -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
-               img, nsteps, counters[0:1] if want_counters else None, counters[1:2] if want_counters else None,
+               img, nsteps, c_steps, c_samples,
                queue, int(patch_range[0]), int(patch_range[1]), int(patch_range[2]) if len(patch_range) > 2 else 1,
                order, stream_ptr())
+    if n_long > 0:
+        cur.wait_stream(side)
     if want_counters:
         return img, counters
     return img

@@ -330,7 +330,8 @@ def render_distributed(model, mode="queue", shared=None, dst=0, **render_kwargs)
             shared = SharedImage(len(nus), npx, owner=dst)
         shared.reset()
         dist.barrier()
-        images.render(model, image_out=shared.image_ptr, queue=shared.queue_ptr, **render_kwargs)
+        images.render(model, image_out=shared.image_ptr, queue=shared.queue_ptr, long_queue=shared.ring_queue_ptr,
+                      participants=nranks, **render_kwargs)
         torch.cuda.synchronize()
         dist.barrier()
         out = None

@@ -60,6 +60,25 @@ if rank == 0:
 dist.barrier()
 shared.close()
 
+# ---- one frequency with a learned patch order: the photon-ring patches go through the warp-specialised long-patch
+# kernel (its own shared queue counter), the rest through the fused kernel; all ranks together vs rank 0 alone, and
+# both against the plain fused kernel with no learned order
+kw1 = dict(resolution=res, observing_frequencies=(230e9,))
+plain = images.render(m, **kw1) if rank == 0 else None
+images.learn_patch_order(0.94, resolution=res)
+alone = images.render(m, **kw1) if rank == 0 else None
+shared1 = multigpu.SharedImage(1, res * res)
+img = multigpu.render_distributed(m, mode="queue", shared=shared1, **kw1)
+if rank == 0:
+    key = next(iter(images._learned_lengths))
+    n_long = images.long_patch_count(images._learned_lengths[key], world)
+    same = bool(torch.equal(img, alone)) and bool(torch.equal(img, plain))
+    print(f"[{world} ranks] long-patch pipeline ({n_long} patches): identical to the fused single-GPU image: {same}")
+    assert same and n_long > 0
+images._learned_order.clear(); images._learned_lengths.clear()
+dist.barrier()
+shared1.close()
+
 # ---- distributed integration: `world` frames in one job ----
 a, N, tol = 0.94, 10000, 1e-4
 incl = [60.0, 17.0, 30.0, 80.0, 45.0, 70.0, 25.0, 52.0]

@@ -230,6 +230,7 @@ def test_distributed_render_two_ranks(built):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mode=queue: identical to single-GPU image: True" in r.stdout
     assert "mode=static: identical to single-GPU image: True" in r.stdout
+    assert "identical to the fused single-GPU image: True" in r.stdout
     assert "shared ray queue: identical to single-GPU integration: True" in r.stdout
     assert "identical to the single-GPU dump: True" in r.stdout
 
@@ -264,6 +265,67 @@ def test_two_level_mesh_sampling(built):
         m.release()
     mb_ref = om._meshblock_indices(S)[0]
     assert set(np.unique(mb_ref)) == set(range(-1, 15))            # every block (and "outside") is exercised
+
+
+def test_long_patch_pipeline_is_bit_identical(setup):
+    """mk_render_long (producer warp = geodesic, consumer warps = sample + emission through a shared-memory ring) against
+    the fused kernel: the same device functions on the same operands in the same order, so every pixel, step count and
+    counter must be IDENTICAL -- whole frame through the pipeline kernel alone, a learned order with the head of it on
+    the pipeline kernel (two concurrent launches), an odd resolution (NaN centre ray, partial patches), the iteration
+    cap, explicit rays, f32 cells and the analytic torus."""
+    import torch
+    import mahakala_b200 as ma
+    from mahakala_b200 import images
+    from mahakala_b200.grmhd import AnalyticTorusFluidModel
+    dm = setup["dm"]
+    for kw in (dict(resolution=40), dict(resolution=21), dict(resolution=24, max_nsteps=300),
+               dict(resolution=32, camera_inclination=17, fov=14.0)):
+        ref, cref = images.render(dm, want_counters=True, patch_order="centre_out", **kw)
+        npatch = (-(-kw["resolution"] // 4)) * (-(-kw["resolution"] // 8))
+        order = images.centre_out_patch_order(kw["resolution"], ref.device)
+        for n_long in (npatch, npatch // 3):
+            img, c = images.render(dm, want_counters=True, patch_order=order, long_patches=n_long, **kw)
+            assert torch.equal(img, ref), (kw, n_long, float((img - ref).abs().max()))
+            assert torch.equal(c, cref), (kw, n_long, c, cref)
+    # learned order: 'auto' sends the photon-ring patches to the pipeline kernel
+    ref = images.render(dm, resolution=48)
+    images.learn_patch_order(A, resolution=48)
+    try:
+        key = next(iter(images._learned_lengths))
+        assert images.long_patch_count(images._learned_lengths[key]) > 0
+        assert torch.equal(images.render(dm, resolution=48), ref)
+        assert np.array_equal(images.make_image(dm, resolution=48).reshape(-1), np.asarray(ref.cpu())[0])
+    finally:
+        images._learned_order.clear(); images._learned_lengths.clear()
+    # explicit rays (ragged), f32 cells, analytic torus
+    s0 = ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 14)[3:3 + 150]
+    ref = images.render(dm, s0=s0)
+    assert torch.equal(_render_long_only(dm, s0=s0), ref)
+    d32 = device_model(setup["arr"], A, storage="f32")
+    assert torch.equal(_render_long_only(d32, resolution=24), images.render(d32, resolution=24))
+    tm = AnalyticTorusFluidModel(A)
+    assert torch.equal(_render_long_only(tm, resolution=24), images.render(tm, resolution=24))
+
+
+def _render_long_only(model, **kw):
+    """every patch through mk_render_long (explicit rays have no patch order: call the ABI entry directly)"""
+    import ctypes
+    import torch
+    from mahakala_b200 import _cabi, images
+    from mahakala_b200._device import as_device, stream_ptr
+    snap = model.snapshot()
+    P, _ = images._params_for(model, M_BH, MASS_SCALE, 40)
+    nu = (ctypes.c_double * 8)(*([230e9] * 8))
+    s0 = kw.get("s0")
+    res = 0 if s0 is not None else int(kw["resolution"])
+    s0d = as_device(s0) if s0 is not None else None
+    npx = s0d.shape[0] if s0 is not None else res * res
+    img = torch.full((1, npx), -1.0, dtype=torch.float64, device="cuda")
+    i = np.pi / 3
+    _cabi.call("mk_render_long", float(model.bhspin), float(np.cos(i)), float(np.sin(i)), 1000.0, -10.0, 10.0, res, s0d, npx,
+               10000, 40.0, 1e-4, snap, P, 1, nu, img, None, None, None, None, 0, -1, 1, None, 0, stream_ptr())
+    torch.cuda.synchronize()
+    return img
 
 
 def test_odd_resolution_dead_centre_pixel_and_cap(setup):
