@@ -292,14 +292,18 @@ int mk_render(double bhspin, double cos_i, double sin_i, double distance, double
    shared-memory ring, so that the snapshot sample leaves the critical path of the dependent RK4 steps (0.64 instead of
    1.95 us per step for a lone patch on B200).  Pixels are bit-identical to mk_render's.  Meant for the few hundred
    patches that contain photon-ring rays (patch_begin .. patch_end of a longest-first patch_order), launched on a
-   high-priority stream next to an mk_render launch for the rest; nfreq must be 1.  ctas_per_sm: resident CTAs per SM
-   (0 = as many as fit; 1 leaves three quarters of every SM to the concurrent bulk launch). */
+   high-priority stream next to an mk_render launch for the rest; nfreq must be 1.
+   exclusive = 0: 128-thread CTAs (one patch each) that share their SM with other resident CTAs; exclusive = 1..4:
+   512-thread CTAs that fill the register file of an SM, so that no warp of another launch competes with the producers
+   for FP64 issue slots, with that many patch groups at work (one producer per SM sub-partition; the warps of the
+   other groups exit at once).  max_ctas > 0 caps the grid (several GPUs
+   pulling from one queue: about (patches / 4) / GPUs each, so that the long patches spread over all of them). */
 int mk_render_long(double bhspin, double cos_i, double sin_i, double distance, double fov_lower,
                    double fov_upper, long res, const double* s0, long npx, long N, double div, double tol,
                    const mk_snapshot* snap, const mk_emission_params* params, int nfreq, const double* nu_obs,
                    double* image, int32_t* nsteps, unsigned long long* total_steps,
                    unsigned long long* total_samples, unsigned int* queue, long patch_begin, long patch_end,
-                   long patch_stride, const int* patch_order, int ctas_per_sm, void* stream);
+                   long patch_stride, const int* patch_order, int exclusive, int max_ctas, void* stream);
 /* The same with a selectable spacetime: MK_METRIC_KERR_SCHILD (== mk_render) or a run-time registered metric
    (id >= MK_METRIC_PLUGIN_BASE): geodesics through the plugin's dual-number derivatives, fluid-frame algebra
    (athenak.py:760-786) with the plugin's own covariant / contravariant metric at every sample.  The reference obtains

@@ -52,7 +52,7 @@ SIGNATURES = {
     "mk_emission_from_states": "ppdpl" "d" "ppp",
     "mk_emission_probe": "pdppl" "ip" "i" "ppp",
     "mk_render": "dddddd" "l" "p" "ll" "dd" "pp" "i" "p" "ppppp" "lll" "pp",
-    "mk_render_long": "dddddd" "l" "p" "ll" "dd" "pp" "i" "p" "ppppp" "lll" "p" "i" "p",
+    "mk_render_long": "dddddd" "l" "p" "ll" "dd" "pp" "i" "p" "ppppp" "lll" "p" "ii" "p",
     "mk_render_metric": "i" "dddddd" "l" "p" "ll" "dd" "pp" "i" "p" "ppppp" "lll" "pp",
     "mk_ipc_alloc": "lpp",
     "mk_ipc_open": "pp",

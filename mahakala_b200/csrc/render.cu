@@ -18,25 +18,44 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const KerrSchild g, const RenderA
 }
 
 // long-patch variant: producer warp (geodesic) + consumer warps (sample, emission), see render_pipeline.cuh
-template <int KIND>
-__global__ void __launch_bounds__(PIPE_THREADS, 4) render_pipeline_kernel(const KerrSchild g, const RenderArgs A)
+template <int KIND, int GROUPS>
+__global__ void __launch_bounds__(PIPE_THREADS * GROUPS, GROUPS == 1 ? 4 : 1) render_pipeline_kernel(const KerrSchild g, const RenderArgs A)
 {
-    render_pipeline_body<KIND>(g, A);
+    render_pipeline_body<KIND, GROUPS>(g, A);
+}
+
+template <int KIND, int GROUPS>
+static int launch_pipeline_groups(const KerrSchild& g, const RenderArgs& A, long npatches, int max_ctas, cudaStream_t stream)
+{
+    const size_t smem = GROUPS * (size_t)PIPE_GROUP_BYTES;
+    static bool configured = false;         // per instantiation
+    if (!configured) {
+        MK_CUDA_CHECK(cudaFuncSetAttribute(render_pipeline_kernel<KIND, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int per_sm = 0;
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pipeline_kernel<KIND, GROUPS>, PIPE_THREADS * GROUPS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long blocks = (long)sm_count() * per_sm;        // one patch per group at a time
+    const int working = (GROUPS == 1) ? 1 : A.pipe_groups;
+    const long need = (npatches + working - 1) / working;
+    if (need < blocks) blocks = need;
+    if (max_ctas > 0 && max_ctas < blocks) blocks = max_ctas;
+    if (blocks < 1) blocks = 1;
+    render_pipeline_kernel<KIND, GROUPS><<<(unsigned)blocks, PIPE_THREADS * GROUPS, smem, stream>>>(g, A);
+    MK_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 template <int KIND>
-static int launch_pipeline_kind(const KerrSchild& g, const RenderArgs& A, long npatches, int ctas_per_sm, cudaStream_t stream)
+static int launch_pipeline_kind(const KerrSchild& g, const RenderArgs& A, long npatches, int exclusive, int max_ctas, cudaStream_t stream)
 {
-    int per_sm = 0;
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pipeline_kernel<KIND>, PIPE_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (ctas_per_sm >= 1 && ctas_per_sm < per_sm) per_sm = ctas_per_sm;
-    long blocks = (long)sm_count() * per_sm;        // one patch per CTA at a time
-    if (npatches < blocks) blocks = npatches;
-    if (blocks < 1) blocks = 1;
-    render_pipeline_kernel<KIND><<<(unsigned)blocks, PIPE_THREADS, 0, stream>>>(g, A);
-    MK_CUDA_CHECK(cudaGetLastError());
-    return 0;
+    if (exclusive) {
+        RenderArgs B = A;
+        B.pipe_groups = exclusive > PIPE_GROUPS_EXCLUSIVE ? PIPE_GROUPS_EXCLUSIVE : exclusive;
+        return launch_pipeline_groups<KIND, PIPE_GROUPS_EXCLUSIVE>(g, B, npatches, max_ctas, stream);
+    }
+    return launch_pipeline_groups<KIND, 1>(g, A, npatches, max_ctas, stream);
 }
 
 // (Round 1 kept an experimental lane-refill variant of this kernel here: incoherent warps lose the L1 locality of
@@ -91,7 +110,7 @@ static int render_impl(int metric_id, double bhspin, double cos_i, double sin_i,
                        const double* nu_obs, double* image, int32_t* nsteps,
                        unsigned long long* total_steps, unsigned long long* total_samples,
                        unsigned int* queue, long patch_begin, long patch_end, long patch_stride,
-                       const int* patch_order, cudaStream_t stream, int pipeline_ctas_per_sm = -1)
+                       const int* patch_order, cudaStream_t stream, int pipeline = 0, int exclusive = 0, int max_ctas = 0)
 {
     MK_REQUIRE(snap && params && nu_obs && image, "null pointer");
     MK_REQUIRE(nfreq >= 1 && nfreq <= 8, "nfreq must be in 1..8");
@@ -122,6 +141,7 @@ static int render_impl(int metric_id, double bhspin, double cos_i, double sin_i,
     A.patch_end = (patch_end < 0 || patch_end > npatches) ? npatches : patch_end;
     A.patch_stride = patch_stride < 1 ? 1 : patch_stride;
     A.patch_order = patch_order;
+    A.pipe_groups = 1;
     if (A.patch_begin >= A.patch_end) return 0;
     long span = (A.patch_end - A.patch_begin + A.patch_stride - 1) / A.patch_stride;
     if (metric_id >= MK_METRIC_PLUGIN_BASE) {
@@ -144,13 +164,13 @@ static int render_impl(int metric_id, double bhspin, double cos_i, double sin_i,
                "the fused render runs with the built-in Kerr-Schild spacetime or a registered one");
     A.queue = queue ? queue : queue_counter(stream, 1);
     if (!A.queue) return 1;
-    if (pipeline_ctas_per_sm >= 0) {
+    if (pipeline) {
         MK_REQUIRE(nfreq == 1 && metric_id == MK_METRIC_KERR_SCHILD,
                    "the long-patch pipeline carries one frequency in the built-in Kerr-Schild spacetime");
         switch (snapshot_kind(A.sn)) {
-            case SNAP_F64_GRID_POW2: return launch_pipeline_kind<SNAP_F64_GRID_POW2>(g, A, span, pipeline_ctas_per_sm, stream);
-            case SNAP_F32_GRID_POW2: return launch_pipeline_kind<SNAP_F32_GRID_POW2>(g, A, span, pipeline_ctas_per_sm, stream);
-            default: return launch_pipeline_kind<SNAP_GENERIC>(g, A, span, pipeline_ctas_per_sm, stream);
+            case SNAP_F64_GRID_POW2: return launch_pipeline_kind<SNAP_F64_GRID_POW2>(g, A, span, exclusive, max_ctas, stream);
+            case SNAP_F32_GRID_POW2: return launch_pipeline_kind<SNAP_F32_GRID_POW2>(g, A, span, exclusive, max_ctas, stream);
+            default: return launch_pipeline_kind<SNAP_GENERIC>(g, A, span, exclusive, max_ctas, stream);
         }
     }
     if (nfreq == 1) return launch_render<1>(g, A, span, stream);
@@ -182,11 +202,11 @@ extern "C" int mk_render_long(double bhspin, double cos_i, double sin_i, double 
                               const double* nu_obs, double* image, int32_t* nsteps,
                               unsigned long long* total_steps, unsigned long long* total_samples,
                               unsigned int* queue, long patch_begin, long patch_end, long patch_stride,
-                              const int* patch_order, int ctas_per_sm, void* stream_)
+                              const int* patch_order, int exclusive, int max_ctas, void* stream_)
 {
     return render_impl(MK_METRIC_KERR_SCHILD, bhspin, cos_i, sin_i, distance, fov_lower, fov_upper, res, s0, npx, N, div,
                        tol, snap, params, nfreq, nu_obs, image, nsteps, total_steps, total_samples, queue, patch_begin,
-                       patch_end, patch_stride, patch_order, (cudaStream_t)stream_, ctas_per_sm < 0 ? 0 : ctas_per_sm);
+                       patch_end, patch_stride, patch_order, (cudaStream_t)stream_, 1, exclusive, max_ctas);
 }
 
 extern "C" int mk_render_metric(int metric_id, double bhspin, double cos_i, double sin_i, double distance,

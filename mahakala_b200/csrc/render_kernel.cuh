@@ -50,6 +50,7 @@ struct RenderArgs {
     unsigned int* queue;
     long patch_begin, patch_end, patch_stride;
     const int* patch_order;    // optional permutation of the patch indices (scheduling order)
+    int pipe_groups;           // long-patch kernel, exclusive CTAs: patch groups that work (1..4), the others exit at once
 };
 
 

@@ -10,11 +10,12 @@
 // patch at a time = four warps:
 //   warp 0   (producer)  integrates the 32 rays exactly like render_body's stage-1-first loop and, instead of sampling,
 //            pushes {state, f, l, weight} of every lane that may be inside the snapshot into a ring of PIPE_RING slots in
-//            shared memory (one elected mbarrier arrive per slot);
+//            shared memory (straight-line: 13 stores and one mbarrier arrive per lane);
 //   warps 1-3 (consumers) take slots round-robin, do block lookup + trilinear gather + fluid frame + j_nu, alpha_nu for
-//            their lane's record and write (j, alpha) back into the slot;
-//   warp 0   folds finished slots IN ORDER into its lane's (I, T) accumulators (two FMAs per sample) when the ring slot is
-//            needed again, and at the end of the patch.
+//            their lane's record, then fold it IN ORDER into the lane's (I, T): they read (I, T) as the previous slot
+//            left it (waiting for that slot's mbarrier), apply the two FMAs of the transfer update and leave the result
+//            in their own slot; only those two FMAs are serial across the consumers;
+//   warp 0   reads the last slot's I at the end of the patch and stores the pixel.
 // Every number is produced by the same device functions with the same operands in the same order as in render_body, so
 // the pixels are bit-identical to the fused kernel's (tests/test_fluid_gpu.py::test_long_patch_pipeline_is_bit_identical).
 // With 16 warps resident per SM the producer advances at its share of the FP64 pipe (455 instead of 795 FP64 instructions
@@ -31,32 +32,64 @@ namespace mk {
 constexpr int PIPE_RING = 8;            // slots per CTA
 constexpr int PIPE_CONSUMERS = 3;       // warps 1..3
 constexpr int PIPE_FIELDS = 13;         // s[8], f, l1, l2, l3, weight
-constexpr int PIPE_THREADS = 32 * (1 + PIPE_CONSUMERS);
+constexpr int PIPE_THREADS = 32 * (1 + PIPE_CONSUMERS);      // threads per patch group
+// Patch groups per CTA.  1: a 128-thread CTA that shares its SM with whatever else is resident (e.g. three CTAs of the
+// bulk launch, whose warps then compete with the producer for FP64 issue slots).  4: a 512-thread CTA = the whole
+// register file of an SM, nothing else can be resident; the warps are arranged so that every SM sub-partition holds
+// ONE producer and three consumers of the other groups (warp w sits on sub-partition w % 4: group = w / 4, the
+// producer of group g is warp 5 g).
+constexpr int PIPE_GROUPS_EXCLUSIVE = 4;
 
-struct PipeShared {
-    double rec[PIPE_RING][PIPE_FIELDS][32];         // [slot][field][lane]: a lane touches only its own column
-    unsigned long long full[PIPE_RING];             // producer -> consumer
-    unsigned long long done[PIPE_RING];             // consumer -> producer
-    unsigned mask[PIPE_RING];                       // lanes that carry a record
-    unsigned inside[PIPE_RING];                     // lanes whose record was inside the snapshot (contribute)
-    int type[PIPE_RING];                            // 0 = samples, 1 = exit
-};
+// Per-group shared memory, addressed with 32-bit shared-window addresses (st.shared / ld.shared / mbarrier on
+// shared::cta): generic pointers to dynamic shared memory make the compiler rebuild the window base from SR_CgaCtaId at
+// every use, which a lone latency-bound warp pays for in full.
+//   rec   [PIPE_RING][PIPE_FIELDS][32] f64   a lane touches only its own column; fields 0, 1 are overwritten with the
+//                                            lane's (I, T) after this slot
+//   full  [PIPE_RING] mbarrier (32 arrivals) producer lanes -> consumer
+//   done  [PIPE_RING] mbarrier (32 arrivals) consumer lanes -> next consumer (fold) and producer (slot reuse)
+//   mask  [PIPE_RING] u32                    lanes that carry a record
+//   type  [PIPE_RING] i32                    0 = samples, 2 = samples, first slot of a patch, 1 = exit
+constexpr unsigned PIPE_OFF_FULL = PIPE_RING * PIPE_FIELDS * 32 * 8;
+constexpr unsigned PIPE_OFF_DONE = PIPE_OFF_FULL + PIPE_RING * 8;
+constexpr unsigned PIPE_OFF_MASK = PIPE_OFF_DONE + PIPE_RING * 8;
+constexpr unsigned PIPE_OFF_TYPE = PIPE_OFF_MASK + PIPE_RING * 4;
+constexpr unsigned PIPE_GROUP_BYTES = PIPE_OFF_TYPE + PIPE_RING * 4;
 
-__device__ __forceinline__ unsigned pipe_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void pipe_mbar_init(unsigned long long* b, unsigned count)
+__device__ __forceinline__ void pipe_mbar_init(unsigned bar, unsigned count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(pipe_smem_addr(b)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void pipe_mbar_arrive(unsigned long long* b)
+__device__ __forceinline__ void pipe_mbar_arrive(unsigned bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(pipe_smem_addr(b)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");      // release.cta: the lane's stores first
 }
-__device__ __forceinline__ void pipe_mbar_wait(unsigned long long* b, unsigned parity)
+__device__ __forceinline__ void pipe_mbar_wait(unsigned bar, unsigned parity)
 {
     unsigned ok = 0;
     while (!ok)     // try_wait suspends the warp in hardware for a bounded time: waiting warps do not spin on issue slots
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(pipe_smem_addr(b)), "r"(parity) : "memory");
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ unsigned pipe_mbar_test(unsigned bar, unsigned parity)       // non-blocking
+{
+    unsigned ok;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void pipe_sts(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ double pipe_lds(unsigned addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pipe_sts32(unsigned addr, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned pipe_lds32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
 }
 
 // conservative "could this point be sampled?" (a superset of the exact membership test the consumer applies)
@@ -67,66 +100,89 @@ __device__ __forceinline__ bool pipe_maybe_inside(const SnapshotView& sn, const 
            (sn.bbox_lo[2] <= s[3]) & (s[3] <= sn.bbox_hi[2]);
 }
 
-template <int KIND>
+template <int KIND, int GROUPS>
 __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const RenderArgs& A)
 {
-    __shared__ PipeShared sh;
+    extern __shared__ __align__(16) unsigned char mk_pipe_smem[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned group = 0, role = warp;                // role 0 = producer, 1..3 = consumers
+    if (GROUPS > 1) {
+        const unsigned q = warp >> 2, r = warp & 3u;
+        group = q;
+        role = (r == q) ? 0u : 1u + (r > q ? r - 1u : r);
+    }
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(mk_pipe_smem);
     if (threadIdx.x == 0) {
-        for (int k = 0; k < PIPE_RING; k++) { pipe_mbar_init(&sh.full[k], 1); pipe_mbar_init(&sh.done[k], 1); }
+        for (int g = 0; g < GROUPS; g++)
+            for (int k = 0; k < 2 * PIPE_RING; k++) pipe_mbar_init(smem0 + g * PIPE_GROUP_BYTES + PIPE_OFF_FULL + 8 * k, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // exclusive CTAs may run with fewer than four working groups: the CTA still owns the SM's register file (nothing
+    // else becomes resident), and the producers share the FP64 pipe with fewer neighbours
+    if (GROUPS > 1 && (int)group >= A.pipe_groups) return;
+    const unsigned sh = smem0 + group * PIPE_GROUP_BYTES;       // this group's block
+    const unsigned col = sh + lane * 8;                         // + (slot * PIPE_FIELDS + field) * 256: this lane's cell
+    auto rec = [&](unsigned k, unsigned q) { return col + (k * PIPE_FIELDS + q) * 256u; };
 
-    if (warp != 0) {
+    if (role != 0) {
         // ------------------------------------------------ consumers ------------------------------------------------
         unsigned long long my_samples = 0;
-        for (unsigned n = warp - 1;; n += PIPE_CONSUMERS) {
+        for (unsigned n = role - 1;; n += PIPE_CONSUMERS) {
             const unsigned k = n % PIPE_RING;
-            pipe_mbar_wait(&sh.full[k], (n / PIPE_RING) & 1u);
-            if (sh.type[k] != 0) break;
-            const unsigned m = sh.mask[k];
+            pipe_mbar_wait(sh + PIPE_OFF_FULL + 8 * k, (n / PIPE_RING) & 1u);
+            const unsigned ty = pipe_lds32(sh + PIPE_OFF_TYPE + 4 * k);
+            if (ty == 1u) break;
+            const unsigned m = pipe_lds32(sh + PIPE_OFF_MASK + 4 * k);
             bool inside = false;
+            double e_out = 0.0, a_out = 0.0, w = 0.0;
             if ((m >> lane) & 1u) {
                 double s[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) s[q] = sh.rec[k][q][lane];
-                const double f = sh.rec[k][8][lane];
-                const double l[4] = {1.0, sh.rec[k][9][lane], sh.rec[k][10][lane], sh.rec[k][11][lane]};
+                for (int q = 0; q < 8; q++) s[q] = pipe_lds(rec(k, q));
+                const double f = pipe_lds(rec(k, 8));
+                const double l[4] = {1.0, pipe_lds(rec(k, 9)), pipe_lds(rec(k, 10)), pipe_lds(rec(k, 11))};
+                w = pipe_lds(rec(k, 12));
                 double prims[8];
+#ifdef MK_PIPE_NOCONSUME       // experiment: consumers that do nothing (pixels are wrong)
+                if (false) {
+#else
                 if (interp_prims_kind<KIND>(A.sn, s, prims)) {
+#endif
                     inside = true;
-                    double e_out = 0.0, a_out = 0.0;
                     emission_fast<1>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
                                      [&](int, double e, double a) { e_out = e; a_out = a; });
-                    sh.rec[k][0][lane] = e_out;
-                    sh.rec[k][1][lane] = a_out;
                 }
             }
+            // in-order fold: (I, T) after the previous slot of this patch (written by whichever consumer had it) -> after
+            // this one.  Only these two FMAs are serial across the consumers; the sample above is not.
+            double I = 0.0, T = 1.0;
+            if (ty != 2u) {
+                const unsigned kp = (n - 1u) % PIPE_RING;
+                pipe_mbar_wait(sh + PIPE_OFF_DONE + 8 * kp, ((n - 1u) / PIPE_RING) & 1u);
+                I = pipe_lds(rec(kp, 0));
+                T = pipe_lds(rec(kp, 1));
+            }
+            if (inside) {
+                const double Tf = T;                 // the update of render_body, operand for operand
+                I = fma(Tf, w * e_out, I);
+                T = Tf * fma(-w, a_out, 1.0);
+            }
+            pipe_sts(rec(k, 0), I);
+            pipe_sts(rec(k, 1), T);
+            pipe_mbar_arrive(sh + PIPE_OFF_DONE + 8 * k);
             const unsigned im = __ballot_sync(FULL_MASK, inside);
-            if (lane == 0) { sh.inside[k] = im; my_samples += (unsigned long long)__popc(im); }
-            __syncwarp();
-            if (lane == 0) pipe_mbar_arrive(&sh.done[k]);
+            if (lane == 0) my_samples += (unsigned long long)__popc(im);
         }
         if (lane == 0 && A.total_samples && my_samples) atomicAdd(A.total_samples, my_samples);
         return;
     }
 
     // -------------------------------------------------- producer --------------------------------------------------
-    unsigned push_ptr = 0, fold_ptr = 0;
-    double I = 0.0, T = 1.0;
+    unsigned push_ptr = 0, done_ptr = 0;     // slots pushed / slots known to be finished (both warp-uniform)
     unsigned long long my_steps = 0;
-    auto fold_one = [&]() {
-        const unsigned k = fold_ptr % PIPE_RING;
-        pipe_mbar_wait(&sh.done[k], (fold_ptr / PIPE_RING) & 1u);
-        if ((sh.inside[k] >> lane) & 1u) {
-            const double e = sh.rec[k][0][lane], a = sh.rec[k][1][lane], w = sh.rec[k][12][lane];
-            const double Tf = T;                     // the update of render_body, operand for operand
-            I = fma(Tf, w * e, I);
-            T = Tf * fma(-w, a, 1.0);
-        }
-        fold_ptr++;
-    };
+    // Slot m may overwrite slot m - RING only when slot m - RING + 1 is finished too (its consumer reads the (I, T) that
+    // slot m - RING left behind): the producer keeps push_ptr + 2 <= done_ptr + RING before every push.
 
     for (;;) {
         unsigned pq = 0;
@@ -160,7 +216,7 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
             }
         }
         const bool valid = active;
-        I = 0.0; T = 1.0;
+        const unsigned patch_first = push_ptr;
         int it = 0;
         double dt = 0.0;
         KerrSchild::Cache cache;
@@ -170,23 +226,37 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
         bool pending = false;
         while (__any_sync(FULL_MASK, active)) {
             double a1[4];
-            KerrSchild::MetricFunctions mf;
+            KerrSchild::MetricFunctions mf = {0.0, 0.0, 0.0, 0.0};
+            // room for one push: when the ring is one slot short, the oldest slot's barrier is TESTED before the first
+            // RK4 stage and its answer used after it, so the round trip to the barrier hides behind ~90 FP64 operations
+            // instead of stalling the chain (an iteration pushes at most one slot, so one retirement keeps up)
+            const bool need_room = push_ptr + 2u > done_ptr + (unsigned)PIPE_RING;
+            const unsigned old_bar = sh + PIPE_OFF_DONE + 8 * (done_ptr % PIPE_RING), old_par = (done_ptr / PIPE_RING) & 1u;
+            unsigned room_ok = 1u;
+            if (need_room) room_ok = pipe_mbar_test(old_bar, old_par);
             if (active) G.accel(s, s + 4, a1, &cache, &mf);
+            if (need_room) {
+                if (!room_ok) pipe_mbar_wait(old_bar, old_par);
+                done_ptr++;
+            }
             // hand the state to the consumers (render_body samples it here)
+#ifdef MK_PIPE_NOPUSH          // experiment: the producer alone (no slot is ever pushed; pixels are wrong)
+            const bool want = false;
+#else
             const bool want = active && pending && pipe_maybe_inside(A.sn, s);
+#endif
             const unsigned pm = __ballot_sync(FULL_MASK, want);
             if (pm) {
-                while (push_ptr - fold_ptr >= (unsigned)PIPE_RING) fold_one();
                 const unsigned k = push_ptr % PIPE_RING;
-                if (want) {
+                // straight-line: every lane stores its column (the mask says which ones count) and arrives itself, the
+                // two control words are written by all lanes with the same value
 #pragma unroll
-                    for (int q = 0; q < 8; q++) sh.rec[k][q][lane] = s[q];
-                    sh.rec[k][8][lane] = mf.f; sh.rec[k][9][lane] = mf.l1; sh.rec[k][10][lane] = mf.l2;
-                    sh.rec[k][11][lane] = mf.l3; sh.rec[k][12][lane] = wdt;
-                }
-                if (lane == 0) { sh.mask[k] = pm; sh.type[k] = 0; }
-                __syncwarp();
-                if (lane == 0) pipe_mbar_arrive(&sh.full[k]);
+                for (int q = 0; q < 8; q++) pipe_sts(rec(k, q), s[q]);
+                pipe_sts(rec(k, 8), mf.f); pipe_sts(rec(k, 9), mf.l1); pipe_sts(rec(k, 10), mf.l2);
+                pipe_sts(rec(k, 11), mf.l3); pipe_sts(rec(k, 12), wdt);
+                pipe_sts32(sh + PIPE_OFF_MASK + 4 * k, pm);
+                pipe_sts32(sh + PIPE_OFF_TYPE + 4 * k, (push_ptr == patch_first) ? 2u : 0u);
+                pipe_mbar_arrive(sh + PIPE_OFF_FULL + 8 * k);
                 push_ptr++;
             }
             if (active) {
@@ -203,9 +273,12 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
                 }
             }
         }
-        while (fold_ptr != push_ptr) fold_one();
+        while (done_ptr != push_ptr) {
+            pipe_mbar_wait(sh + PIPE_OFF_DONE + 8 * (done_ptr % PIPE_RING), (done_ptr / PIPE_RING) & 1u);
+            done_ptr++;
+        }
         if (valid) {
-            A.image[ray] = I;
+            A.image[ray] = (push_ptr != patch_first) ? pipe_lds(rec((push_ptr - 1u) % PIPE_RING, 0)) : 0.0;
             if (A.nsteps) A.nsteps[ray] = it;
             my_steps += (unsigned long long)it;
         }
@@ -213,9 +286,9 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
     // release the consumers: one exit slot for each of them (consecutive slot numbers cover all residues)
     for (int j = 0; j < PIPE_CONSUMERS; j++) {
         const unsigned k = push_ptr % PIPE_RING;
-        if (lane == 0) { sh.mask[k] = 0u; sh.type[k] = 1; }
-        __syncwarp();
-        if (lane == 0) pipe_mbar_arrive(&sh.full[k]);
+        pipe_sts32(sh + PIPE_OFF_MASK + 4 * k, 0u);
+        pipe_sts32(sh + PIPE_OFF_TYPE + 4 * k, 1u);
+        pipe_mbar_arrive(sh + PIPE_OFF_FULL + 8 * k);
         push_ptr++;
     }
 #pragma unroll

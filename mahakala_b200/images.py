@@ -64,16 +64,33 @@ def _priority_stream(dev):
     return _priority_streams[dev]
 
 
+import os as _os
+_DEV_SKIP_BULK = False      # scripts/dev/strong_probe.py: time the long-patch launch alone
+_LONG_EXCLUSIVE = int(_os.environ.get("MK_LONG_EXCLUSIVE", "2"))     # 0 = shared SMs; 1..4 = groups per exclusive CTA
+
+
+def _long_grid_cap(n_long, participants):
+    """CTAs of the long-patch launch per GPU: its share of the long patches (+ 25 %), so that with several GPUs on
+    one queue they spread over all of them instead of being taken by the GPU that starts first"""
+    per_cta = max(1, int(_LONG_EXCLUSIVE))
+    if participants <= 1:
+        return 0
+    return max(1, int(np.ceil(1.25 * n_long / per_cta / participants)))
+
+
 def long_patch_count(lengths, participants=1, threshold=None, device=None):
     """How many patches at the head of a learned (longest-first) order go to the warp-specialised long-patch kernel
     (``mk_render_long``): those whose longest ray takes at least ``threshold`` x the longest ray of the frame (default
-    0.3, ``MK_LONG_THRESHOLD``), at most one per SM of every participating GPU -- each of them then owns a CTA from
-    time zero, and three quarters of every SM stay with the bulk kernel."""
+    0.25, ``MK_LONG_THRESHOLD``), at most one per SM of every participating GPU, so that each of them has a CTA from
+    time zero.  Measured on 8 B200s, one 1024^2 cfg4 frame (``scripts/dev/strong_probe.py``): 9.1-10.1 ms without the
+    long-patch launch, 7.2 / 5.6 / 4.6-5.0 / 4.4-4.5 / 4.8-5.0 ms for thresholds 0.5 / 0.4 / 0.3 / 0.25 / 0.2 -- below
+    0.25 the long-patch kernel (68 % of the fused kernel's throughput per SM) takes too much of the machine, above it the
+    longest patch left to the fused kernel (3.1 us per step at full occupancy) sets the time."""
     import os
     if lengths is None or len(lengths) == 0 or lengths[0] <= 0:
         return 0
     if threshold is None:
-        threshold = float(os.environ.get("MK_LONG_THRESHOLD", "0.3"))
+        threshold = float(os.environ.get("MK_LONG_THRESHOLD", "0.25"))
     n = int((lengths >= threshold * float(lengths[0])).sum())
     sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
     return max(0, min(n, int(participants) * sms))
@@ -191,9 +208,11 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
         side.wait_stream(cur)
         _cabi.call("mk_render_long", float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
                    -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
-                   img, nsteps, c_steps, c_samples, long_queue, 0, n_long, 1, order, 1, side.cuda_stream)
+                   img, nsteps, c_steps, c_samples, long_queue, 0, n_long, 1, order, int(_LONG_EXCLUSIVE),
+                   _long_grid_cap(n_long, participants), side.cuda_stream)
         patch_range = (n_long, -1, 1)
-    _cabi.call("mk_render_metric", int(metric_id), float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
+    if not (n_long > 0 and _DEV_SKIP_BULK):
+        _cabi.call("mk_render_metric", int(metric_id), float(fluid_model.bhspin), float(np.cos(i)), float(np.sin(i)), float(camera_distance),
                -fov / 2., fov / 2., res, s0d, npx, int(max_nsteps), float(div), float(tol), snap, P, nfreq, c_nu,
                img, nsteps, c_steps, c_samples,
                queue, int(patch_range[0]), int(patch_range[1]), int(patch_range[2]) if len(patch_range) > 2 else 1,

@@ -29,7 +29,7 @@ def timeit(fn, reps=5):
     return min(ts)
 def long_only(sub, img):
     _cabi.call("mk_render_long", a, float(np.cos(np.pi / 3)), float(np.sin(np.pi / 3)), 1000.0, -10.0, 10.0, 0, sub, sub.shape[0],
-               10000, 40.0, 1e-4, snap, P, 1, nu, img, None, None, None, None, 0, -1, 1, None, 0, stream_ptr())
+               10000, 40.0, 1e-4, snap, P, 1, nu, img, None, None, None, None, 0, -1, 1, None, int(os.environ.get('MK_LONG_EXCLUSIVE', '1')), 0, stream_ptr())
 for label, idx in (("32 longest rays (one patch)", order[:32]), ("1 longest ray", order[:1]), ("148 x 32 longest", order[:148 * 32]),
                    ("592 x 32 longest", order[:592 * 32]), ("32 median rays", order[len(order) // 2:len(order) // 2 + 32])):
     sub = s0[torch.from_numpy(idx.copy()).cuda()].contiguous()

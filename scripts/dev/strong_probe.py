@@ -23,7 +23,8 @@ key = next(iter(images._learned_lengths))
 L = images._learned_lengths[key]
 shared = multigpu.SharedImage(1, res * res)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-def leg(n_long, reps=4):
+def leg(n_long, reps=4, patch_range=(0, -1, 1), skip_bulk=False):
+    images._DEV_SKIP_BULK = skip_bulk
     ts = []
     for it in range(reps + 1):
         flush.fill_(it)
@@ -31,16 +32,23 @@ def leg(n_long, reps=4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         images.render(m, resolution=res, image_out=shared.image_ptr, queue=shared.queue_ptr, long_queue=shared.ring_queue_ptr,
-                      participants=world, long_patches=n_long)
+                      participants=world, long_patches=n_long, patch_range=patch_range)
         e1.record(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
         if it: ts.append(float(t))
     same = bool(torch.equal(shared.local_view()[1], ref)) if rank == 0 else None
     return min(ts), float(np.mean(ts)), same
-for thr in (None, 0.5, 0.4, 0.3, 0.25, 0.2, 0.15):
+for thr in (None, 0.3, 0.25):
     n_long = 0 if thr is None else min(int((L >= thr * L[0]).sum()), world * 148)
     r = leg(n_long)
     if rank == 0:
-        print(f"[{world} GPUs, {res}^2] threshold {thr}: {n_long:5d} long patches: min {r[0]:.2f} ms mean {r[1]:.2f} ms identical {r[2]}", flush=True)
+        print(f"[{world} GPUs, {res}^2, exclusive={images._LONG_EXCLUSIVE}] threshold {thr}: {n_long:5d} long patches: min {r[0]:.2f} ms mean {r[1]:.2f} ms identical {r[2]}", flush=True)
+n_long = min(int((L >= 0.3 * L[0]).sum()), world * 148)
+r = leg(n_long, skip_bulk=True)
+if rank == 0: print(f"[{world} GPUs] long-patch launch alone ({n_long} patches): min {r[0]:.2f} ms mean {r[1]:.2f}", flush=True)
+r = leg(0, patch_range=(n_long, -1, 1))
+if rank == 0: print(f"[{world} GPUs] bulk launch alone (patches {n_long}..): min {r[0]:.2f} ms mean {r[1]:.2f}", flush=True)
+r = leg(0, patch_range=(len(L) - 64, -1, 1))
+if rank == 0: print(f"[{world} GPUs] 64 shortest patches only (fixed cost of a frame): min {r[0]:.2f} ms mean {r[1]:.2f}", flush=True)
 dist.barrier(); shared.close(); dist.destroy_process_group()

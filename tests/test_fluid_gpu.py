@@ -267,16 +267,19 @@ def test_two_level_mesh_sampling(built):
     assert set(np.unique(mb_ref)) == set(range(-1, 15))            # every block (and "outside") is exercised
 
 
-def test_long_patch_pipeline_is_bit_identical(setup):
+@pytest.mark.parametrize("exclusive", [0, 2, 4])
+def test_long_patch_pipeline_is_bit_identical(setup, exclusive, monkeypatch):
     """mk_render_long (producer warp = geodesic, consumer warps = sample + emission through a shared-memory ring) against
     the fused kernel: the same device functions on the same operands in the same order, so every pixel, step count and
     counter must be IDENTICAL -- whole frame through the pipeline kernel alone, a learned order with the head of it on
     the pipeline kernel (two concurrent launches), an odd resolution (NaN centre ray, partial patches), the iteration
-    cap, explicit rays, f32 cells and the analytic torus."""
+    cap, explicit rays, f32 cells and the analytic torus; 128-thread CTAs (one patch) and 512-thread CTAs (four patches,
+    an SM to themselves)."""
     import torch
     import mahakala_b200 as ma
     from mahakala_b200 import images
     from mahakala_b200.grmhd import AnalyticTorusFluidModel
+    monkeypatch.setattr(images, "_LONG_EXCLUSIVE", int(exclusive))
     dm = setup["dm"]
     for kw in (dict(resolution=40), dict(resolution=21), dict(resolution=24, max_nsteps=300),
                dict(resolution=32, camera_inclination=17, fov=14.0)):
@@ -300,14 +303,14 @@ def test_long_patch_pipeline_is_bit_identical(setup):
     # explicit rays (ragged), f32 cells, analytic torus
     s0 = ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 14)[3:3 + 150]
     ref = images.render(dm, s0=s0)
-    assert torch.equal(_render_long_only(dm, s0=s0), ref)
+    assert torch.equal(_render_long_only(dm, exclusive, s0=s0), ref)
     d32 = device_model(setup["arr"], A, storage="f32")
-    assert torch.equal(_render_long_only(d32, resolution=24), images.render(d32, resolution=24))
+    assert torch.equal(_render_long_only(d32, exclusive, resolution=24), images.render(d32, resolution=24))
     tm = AnalyticTorusFluidModel(A)
-    assert torch.equal(_render_long_only(tm, resolution=24), images.render(tm, resolution=24))
+    assert torch.equal(_render_long_only(tm, exclusive, resolution=24), images.render(tm, resolution=24))
 
 
-def _render_long_only(model, **kw):
+def _render_long_only(model, exclusive, **kw):
     """every patch through mk_render_long (explicit rays have no patch order: call the ABI entry directly)"""
     import ctypes
     import torch
@@ -323,7 +326,7 @@ def _render_long_only(model, **kw):
     img = torch.full((1, npx), -1.0, dtype=torch.float64, device="cuda")
     i = np.pi / 3
     _cabi.call("mk_render_long", float(model.bhspin), float(np.cos(i)), float(np.sin(i)), 1000.0, -10.0, 10.0, res, s0d, npx,
-               10000, 40.0, 1e-4, snap, P, 1, nu, img, None, None, None, None, 0, -1, 1, None, 0, stream_ptr())
+               10000, 40.0, 1e-4, snap, P, 1, nu, img, None, None, None, None, 0, -1, 1, None, int(exclusive), 0, stream_ptr())
     torch.cuda.synchronize()
     return img
 
