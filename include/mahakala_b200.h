@@ -96,6 +96,17 @@ int mk_initial_condition(double bhspin, const double* s0_x, const double* s0_v, 
 int mk_integrate(int metric_id, double bhspin, long N, long npx, const double* s0, double div, double tol,
                  double* final_state, int32_t* nsteps, double* r_last, double* S, double* dt, long nrows,
                  unsigned long long* total_steps, void* stream);
+/* OPTIONAL integrator, not in the reference: embedded Dormand-Prince 5(4) with step-size
+   control (csrc/adaptive.cuh) instead of classical RK4 under the fixed rule of geodesics.py:246-269.  Same termination
+   test (a ray lives while tol <= radius - r_H <= 1500), same freeze semantics (a step that would end outside that
+   range is rejected), h < 0, and |h| <= cap (radius - r_H).  Per-step error bound atol + rtol |y| on position and
+   wavevector.  metric_id: MK_METRIC_KERR_SCHILD, MK_METRIC_KERR_SCHILD_DUAL or a registered metric (its radius() and
+   horizon() only decide when a ray has ended; the step size no longer depends on them).
+     final_state (npx, 8), nsteps (npx,) accepted steps, nrejected (npx,) rejected trial steps, r_last (npx,) radius of
+     the final state (~r_H + tol: captured; hundreds of M: escaped) -- all optional. */
+int mk_integrate_adaptive(int metric_id, double bhspin, long N, long npx, const double* s0, double rtol, double atol,
+                          double tol, double cap, double* final_state, int32_t* nsteps, int32_t* nrejected,
+                          double* r_last, void* stream);
 int mk_fill_frozen_rows(double* S, double* dt, const double* final_state, const int32_t* nsteps, long npx,
                         long nrows, void* stream);
 /*

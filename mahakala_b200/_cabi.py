@@ -27,6 +27,7 @@ SIGNATURES = {
     "mk_camera_points": "ddddpplipp",
     "mk_initial_condition": "dpplpp",
     "mk_integrate": "idllpddpppppl" "pp",
+    "mk_integrate_adaptive": "idllp" "dddd" "pppp" "p",
     "mk_fill_frozen_rows": "ppppllp",
     "mk_integrate_paged": "idllpdd" "ppp" "pppp" "l" "pp" "p",
     "mk_integrate_shared": "idllpdd" "ppp" "pppp" "l" "pp" "pp" "li" "p",

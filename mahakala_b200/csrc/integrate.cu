@@ -4,6 +4,7 @@
 // plugins and the C-ABI launchers.
 #include "common.cuh"
 #include "integrate_kernel.cuh"
+#include "adaptive.cuh"
 #include "ks_metric.cuh"
 #include "metric_plugin.cuh"
 #include "plugin.cuh"
@@ -156,6 +157,57 @@ static int dispatch_integrate(int metric_id, double bhspin, IntegrateArgs& A, cu
         return 2;
     }
     return rc;
+}
+
+// ---- optional adaptive integrator (embedded Dormand-Prince 5(4), adaptive.cuh) -------------------------------------
+template <class Metric>
+__global__ void __launch_bounds__(128) integrate_adaptive_kernel(const Metric g, const AdaptiveArgs A)
+{
+    integrate_adaptive_body(g, A);
+}
+
+template <class Metric>
+static int launch_adaptive(const Metric& g, const AdaptiveArgs& A, cudaStream_t stream)
+{
+    long blocks = (A.npx + 127) / 128;
+    const long cap = (long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    integrate_adaptive_kernel<Metric><<<(unsigned)blocks, 128, 0, stream>>>(g, A);
+    MK_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mk_integrate_adaptive(int metric_id, double bhspin, long N, long npx, const double* s0, double rtol,
+                                     double atol, double tol, double cap, double* final_state, int32_t* nsteps,
+                                     int32_t* nrejected, double* r_last, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MK_REQUIRE(npx >= 0 && N >= 0 && N < (1L << 31) - 2, "npx / N out of range");
+    MK_REQUIRE(npx == 0 || s0 != nullptr, "s0 is null");
+    MK_REQUIRE(rtol > 0.0 && atol >= 0.0, "rtol must be positive, atol non-negative");
+    MK_REQUIRE(cap > 0.0 && cap < 1.0, "cap must be in (0, 1): a step never reaches the horizon");
+    if (npx == 0) return 0;
+    AdaptiveArgs A;
+    A.s0 = s0; A.npx = npx; A.N = (int)N;
+    A.rule.rtol = rtol; A.rule.atol = atol; A.rule.tol = tol; A.rule.far = 1500.0; A.rule.cap = cap; A.rule.div0 = 40.0;
+    A.final_state = final_state; A.nsteps = nsteps; A.nrejected = nrejected; A.r_last = r_last;
+    if (metric_id == MK_METRIC_KERR_SCHILD) {
+        KerrSchild g; g.set_spin(bhspin);
+        A.rule.rH = g.rH;
+        return launch_adaptive(g, A, stream);
+    }
+    if (metric_id == MK_METRIC_KERR_SCHILD_DUAL) {
+        DualMetric<KerrSchildFn> g; g.fn.a = bhspin; g.rH = 1.0 + sqrt(1.0 - bhspin * bhspin);
+        A.rule.rH = g.rH;
+        return launch_adaptive(g, A, stream);
+    }
+    if (metric_id >= MK_METRIC_PLUGIN_BASE) {
+        A.rule.rH = 0.0;        // set from the plugin's horizon() in the kernel
+        void* extra[] = {&A};
+        return plugin_elementwise(metric_id, bhspin, "mk_plugin_integrate_adaptive", extra, 1, npx, stream);
+    }
+    set_error("the adaptive integrator runs with the Kerr-Schild metrics or a registered one (metric id %d)", metric_id);
+    return 2;
 }
 
 extern "C" int mk_fill_frozen_rows(double* S, double* dt, const double* final_state, const int32_t* nsteps,

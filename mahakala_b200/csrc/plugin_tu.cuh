@@ -14,6 +14,7 @@
 // derivative comes from forward-mode dual numbers exactly as jax.jacfwd provides it there.
 #pragma once
 #include "integrate_kernel.cuh"
+#include "adaptive.cuh"
 #include "metric_plugin.cuh"
 #include "camera_nullify.cuh"
 #include "render_kernel.cuh"
@@ -55,6 +56,15 @@ extern "C" __global__ void __launch_bounds__(128, 2) mk_plugin_integrate_padded(
 extern "C" __global__ void __launch_bounds__(128, 2) mk_plugin_integrate_paged(mk::PluginBlob b, mk::IntegrateArgs A)
 {
     mk::plugin_integrate<mk::MODE_PAGED>(b, A);
+}
+
+// optional adaptive integrator (adaptive.cuh) in the user's spacetime: the step follows the local error, not the
+// Kerr-specific rule (r - r_H)/div; radius() and horizon() only decide when a ray has ended
+extern "C" __global__ void __launch_bounds__(128, 2) mk_plugin_integrate_adaptive(mk::PluginBlob b, mk::AdaptiveArgs A)
+{
+    mk::DualMetric<UserMetric> g = mk::plugin_metric(b);
+    A.rule.rH = g.rH;
+    mk::integrate_adaptive_body(g, A);
 }
 
 // fused render (images.py:30-144) in the user's spacetime: geodesics from the dual-number plugin, fluid frame from

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cuda_runtime.h>
 #include "../../mahakala_b200/csrc/integrate_kernel.cuh"
+#include "../../mahakala_b200/csrc/adaptive.cuh"
 #include "../../mahakala_b200/csrc/ks_metric.cuh"
 #include "../../mahakala_b200/csrc/sample.cuh"
 
@@ -49,6 +50,25 @@ extern "C" void hk_integrate(long n, const double* s0, int N, double div, double
         r_last[p] = integrate_one(g, rule, s, N, it);
         std::memcpy(final_state + 8 * p, s, sizeof s);
         nsteps[p] = it;
+    }
+}
+
+// the per-ray loop of adaptive.cuh (embedded Dormand-Prince 5(4))
+extern "C" void hk_integrate_adaptive(long n, const double* s0, int N, double rtol, double atol, double tol, double cap,
+                                      double a, double* final_state, int* nsteps, int* nrejected, double* r_last)
+{
+    KerrSchild g = make_ks(a);
+    AdaptiveRule R;
+    R.rtol = rtol; R.atol = atol; R.tol = tol; R.far = 1500.0; R.rH = g.rH; R.cap = cap; R.div0 = 40.0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long p = 0; p < n; p++) {
+        double s[8];
+        std::memcpy(s, s0 + 8 * p, sizeof s);
+        int it = 0, rej = 0;
+        r_last[p] = integrate_one_adaptive(g, R, s, N, it, rej);
+        std::memcpy(final_state + 8 * p, s, sizeof s);
+        nsteps[p] = it;
+        nrejected[p] = rej;
     }
 }
 

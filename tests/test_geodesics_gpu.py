@@ -449,6 +449,61 @@ def test_camera_rays_are_null_in_the_registered_spacetime(ma):
     assert st.pages_used == used and int(st.total_steps.item()) == total and not st.overflowed
 
 
+def test_adaptive_integrator_option(ma):
+    """mk_integrate_adaptive (embedded Dormand-Prince 5(4), csrc/adaptive.cuh; an option the reference does not have):
+    the CUDA kernel against the host build of the same source (tests/host_harness) -- identical step counts, states
+    to rounding --, the same captured / escaped classification as the fixed-rule integrator, the dual-number twin and a
+    run-time registered spacetime through the same entry point, the shadow finder's classifier with adaptive=True."""
+    import ctypes
+    import torch
+    from host_harness import build
+    from mahakala_b200 import geodesics as geo
+    from oracle import mahakala_oracle as onp
+    from test_host_cpu import SCHWARZSCHILD_KS
+    from test_host_harness_cpu import _adaptive, constants_of_motion
+    hk = build.lib()
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 64))
+    fin, ns, nr, rl = geo.integrate_adaptive(100000, s0, 1e-2, A)
+    fin, ns, nr, rl = (np.asarray(t.cpu()) for t in (fin, ns, nr, rl))
+    hf, hn, hr, hl = _adaptive(hk, s0, 1e-9)
+    _, _, r_fixed = geo.integrate_final(2000, s0, 40, 1e-2, A)
+    cap = rl < 100
+    assert np.array_equal(cap, np.asarray(r_fixed.cpu()) < 100) and cap.sum() == 792
+    assert np.array_equal(cap, hl < 100)
+    # device and host build of the same source: the MUFU seeds differ, the error estimate (a difference of nearly
+    # cancelling terms) carries that at the 1e-4 level into every step size, so the rays freeze at slightly different
+    # affine parameters: step counts agree to a step or two, end states to the integration error (rtol x steps)
+    assert np.abs(ns.astype(int) - hn).max() <= 2 and (ns != hn).mean() < 0.05, (np.abs(ns.astype(int) - hn).max(), (ns != hn).mean())
+    same = ns == hn
+    err = np.abs(fin - hf)[same & ~cap].max(axis=1) / np.abs(hf[same & ~cap]).max(axis=1)
+    assert err.max() < 1e-7, err.max()
+    assert nr.sum() == 0
+    E0, L0, _ = constants_of_motion(s0, A)
+    E1, L1, n1 = constants_of_motion(fin, A)
+    assert np.abs(E1 / E0 - 1)[~cap].max() < 1e-7 and np.abs(n1)[~cap].max() < 1e-7
+    # dual-number twin of the closed form, and a registered spacetime (Schwarzschild, M = 1.5: shadow radius sqrt(27) M)
+    try:
+        geo.set_metric("kerr_schild_dual")
+        f2, n2, _, r2 = geo.integrate_adaptive(100000, s0[::7], 1e-2, A)
+        assert np.array_equal(np.asarray(r2.cpu()) < 100, cap[::7])
+        assert np.abs(np.asarray(n2.cpu()).astype(int) - ns[::7]).max() <= 2
+        if "schw_adapt" not in geo._METRICS:
+            geo.register_metric("schw_adapt", SCHWARZSCHILD_KS, params=[1.5])
+        geo.set_metric("schw_adapt")
+        ang = np.linspace(0, 2 * np.pi, 9)[:-1]
+        b_crit = np.sqrt(27.) * 1.5
+        for b, captured in ((0.98 * b_crit, True), (1.02 * b_crit, False)):
+            r_end = np.asarray(geo.select_photons_integrator(40, ang, np.full(8, b), 0.0, adaptive=True))
+            assert ((r_end < 100) == captured).all(), (b, r_end)
+    finally:
+        geo.set_metric("kerr_schild")
+    # empty bundle, step cap
+    e = geo.integrate_adaptive(10, np.zeros((0, 8)), 1e-2, A)
+    assert e[0].shape == (0, 8) and e[1].shape == (0,)
+    _, n7, _, _ = geo.integrate_adaptive(7, s0[:64], 1e-2, A)
+    assert int(n7.max()) == 7
+
+
 def test_classification_sweep_spins_and_inclinations(ma):
     """Shadow classification (captured vs escaped) is bit-exact against the oracle across spins, inclinations,
     fields of view and both tolerance settings used by the reference (1e-2 shadow finder, 1e-4 imaging)."""

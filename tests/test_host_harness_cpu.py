@@ -91,6 +91,65 @@ def test_ray_loop_matches_the_oracle(hk, res, N, tol, sub):
     assert np.allclose(rl[esc], ref["r_last"][esc], rtol=1e-9)
 
 
+def _adaptive(hk, s0, rtol, tol=1e-2, N=100000, cap=0.5, atol=1e-12):
+    n = s0.shape[0]
+    fin, ns, nr, rl = np.empty((n, 8)), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32), np.empty(n)
+    ip = ctypes.POINTER(ctypes.c_int)
+    hk.hk_integrate_adaptive(ctypes.c_long(n), _d(s0), ctypes.c_int(N), ctypes.c_double(rtol), ctypes.c_double(atol),
+                             ctypes.c_double(tol), ctypes.c_double(cap), ctypes.c_double(A), _d(fin),
+                             ns.ctypes.data_as(ip), nr.ctypes.data_as(ip), _d(rl))
+    return fin, ns, nr, rl
+
+
+def constants_of_motion(S, a):
+    """energy -k_t, axial angular momentum k_phi = x k_y - y k_x (covariant components) and the norm g(k, k)"""
+    from oracle import mahakala_oracle as onp
+    g = np.stack([onp.metric(x[:4], a) for x in S])
+    kcov = np.einsum('nij,nj->ni', g, S[:, 4:])
+    return -kcov[:, 0], S[:, 1] * kcov[:, 2] - S[:, 2] * kcov[:, 1], np.einsum('ni,ni->n', kcov, S[:, 4:])
+
+
+def test_adaptive_integrator_option(hk):
+    """The optional embedded Dormand-Prince 5(4) integrator (csrc/adaptive.cuh; not in the reference)
+    on BASELINE config 1: same captured / escaped classification as the reference's fixed-rule RK4 (792 captured),
+    constants of motion conserved in proportion to rtol and better than the fixed rule does with twice the
+    acceleration evaluations, no rejected steps at the default tolerance, frozen states inside the live range, the
+    step cap N."""
+    from oracle import c_oracle, mahakala_oracle as onp
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 64))
+    ref = c_oracle.integrate(2000, s0, 40, 1e-2, A)
+    cap_ref = ref["r_last"] < 100
+    E0, L0, _ = constants_of_motion(s0, A)
+    rH = onp.radius_EH(A)
+    worst = {}
+    for rtol in (1e-6, 1e-9, 1e-11):
+        fin, ns, nr, rl = _adaptive(hk, s0, rtol)
+        cap = rl < 100
+        assert np.array_equal(cap, cap_ref) and cap.sum() == 792
+        assert np.isfinite(fin).all()
+        assert np.allclose(rl, onp.radius_cal(fin, A), rtol=1e-12)
+        assert ((rl - rH >= 1e-2) & (rl - rH <= 1500)).all()               # frozen inside the live range
+        assert (rl[cap] - rH).max() < 2e-2 and rl[~cap].min() > 500        # ... right at its two ends
+        E1, L1, n1 = constants_of_motion(fin, A)
+        worst[rtol] = max(np.abs(E1 / E0 - 1)[~cap].max(), (np.abs(L1 - L0) / np.abs(L0).max())[~cap].max(),
+                          np.abs(n1)[~cap].max())
+        if rtol <= 1e-9:
+            assert nr.sum() == 0
+        if rtol == 1e-9:
+            assert 6 * ns.sum() < 0.6 * 4 * ref["nsteps"].sum()            # fewer acceleration evaluations than RK4 ...
+            assert np.abs(E1 / E0 - 1)[cap].max() < 1e-5                   # ... and captured rays stay under control
+    Er, Lr, nrm = constants_of_motion(ref["final"], A)
+    rk4 = max(np.abs(Er / E0 - 1)[~cap_ref].max(), (np.abs(Lr - L0) / np.abs(L0).max())[~cap_ref].max(),
+              np.abs(nrm)[~cap_ref].max())
+    assert worst[1e-6] < 1e-3 and worst[1e-9] < 1e-7 and worst[1e-11] < 1e-9 and worst[1e-9] < rk4
+    # step cap, and a ray that starts outside the live range
+    fin, ns, nr, rl = _adaptive(hk, s0[:64], 1e-9, N=7)
+    assert ns.max() == 7
+    far = s0[:4].copy(); far[:, 1:4] *= 3.0                                # r = 3000 M > r_H + 1500
+    fin, ns, nr, rl = _adaptive(hk, np.ascontiguousarray(far), 1e-9)
+    assert (ns == 0).all() and np.array_equal(fin, far)
+
+
 def test_fused_emission_chain_on_adversarial_inputs(hk, monkeypatch):
     """The adversarial cases of tests/test_emission_gpu.py (sigma cut, Theta_e floor, X range, Planck switch, aligned /
     reversed / null wavevectors, degenerate primitives, exp underflow) run through the HOST build of emission_fast."""
