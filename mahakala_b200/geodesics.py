@@ -524,14 +524,18 @@ def integrate_paged_streamed(N, s0_host, div, tol, bhspin, store, host_out, chun
 # -------------------------------------------------------------------------------------------------
 # shadow finder
 # -------------------------------------------------------------------------------------------------
-def select_photons_integrator(inc, angle, radius, bhspin, distance=1000, max_steps=2000, adaptive=False):
-    """geodesics.py:354-378: last-point radius of each photon (used to classify captured / escaped).
-    ``adaptive=True`` (extension) classifies with ``integrate_adaptive`` instead of the reference's fixed rule."""
+def select_photons_integrator(inc, angle, radius, bhspin, distance=1000, max_steps=2000):
+    """geodesics.py:354-378: last-point radius of each photon (used to classify captured / escaped)."""
     s0 = _camera_pixels_state(inc, distance, radius, angle, bhspin)
-    if adaptive:
-        return DeviceArray.wrap(integrate_adaptive(max_steps, s0, 1e-2, bhspin)[3])
     _, _, r_last = integrate_final(max_steps, s0, 40, 1e-2, bhspin)
     return DeviceArray.wrap(r_last)
+
+
+def select_photons_adaptive(inc, angle, radius, bhspin, distance=1000, max_steps=2000):
+    """``select_photons_integrator`` with the optional adaptive integrator (extension, see ``integrate_adaptive``): the
+    radius at which each photon ended, in the active spacetime -- no Kerr-specific step rule involved."""
+    s0 = _camera_pixels_state(inc, distance, radius, angle, bhspin)
+    return DeviceArray.wrap(integrate_adaptive(max_steps, s0, 1e-2, bhspin)[3])
 
 
 def find_shadow_bisection(bhspin, inc, num_angles, max_steps=2000, error_allowed=0.001, max_it=40):

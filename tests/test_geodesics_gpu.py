@@ -493,7 +493,7 @@ def test_adaptive_integrator_option(ma):
         ang = np.linspace(0, 2 * np.pi, 9)[:-1]
         b_crit = np.sqrt(27.) * 1.5
         for b, captured in ((0.98 * b_crit, True), (1.02 * b_crit, False)):
-            r_end = np.asarray(geo.select_photons_integrator(40, ang, np.full(8, b), 0.0, adaptive=True))
+            r_end = np.asarray(geo.select_photons_adaptive(40, ang, np.full(8, b), 0.0))
             assert ((r_end < 100) == captured).all(), (b, r_end)
     finally:
         geo.set_metric("kerr_schild")
