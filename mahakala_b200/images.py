@@ -78,7 +78,7 @@ def _long_grid_cap(n_long, participants):
     return max(1, int(np.ceil(1.25 * n_long / per_cta / participants)))
 
 
-def long_patch_count(lengths, participants=1, threshold=None, device=None):
+def long_patch_count(lengths, participants=1, threshold=None, device=None, sms=None):
     """How many patches at the head of a learned (longest-first) order go to the warp-specialised long-patch kernel
     (``mk_render_long``): those whose longest ray takes at least ``threshold`` x the longest ray of the frame (default
     0.25, ``MK_LONG_THRESHOLD``), at most one per SM of every participating GPU, so that each of them has a CTA from
@@ -92,7 +92,8 @@ def long_patch_count(lengths, participants=1, threshold=None, device=None):
     if threshold is None:
         threshold = float(os.environ.get("MK_LONG_THRESHOLD", "0.25"))
     n = int((lengths >= threshold * float(lengths[0])).sum())
-    sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+    if sms is None:
+        sms = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
     return max(0, min(n, int(participants) * sms))
 
 

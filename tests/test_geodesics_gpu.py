@@ -453,7 +453,7 @@ def test_adaptive_integrator_option(ma):
     """mk_integrate_adaptive (embedded Dormand-Prince 5(4), csrc/adaptive.cuh; an option the reference does not have):
     the CUDA kernel against the host build of the same source (tests/host_harness) -- identical step counts, states
     to rounding --, the same captured / escaped classification as the fixed-rule integrator, the dual-number twin and a
-    run-time registered spacetime through the same entry point, the shadow finder's classifier with adaptive=True."""
+    run-time registered spacetime through the same entry point, the shadow finder's classifier (select_photons_adaptive)."""
     import ctypes
     import torch
     from host_harness import build

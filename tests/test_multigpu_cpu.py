@@ -85,3 +85,25 @@ def test_longest_first_ray_order_is_an_interleaved_permutation(built):
     assert np.array_equal(multigpu.longest_first_ray_order(5, 1), multigpu.longest_first_ray_order(5))
     # SharedRays layout: offsets of the four result arrays (bytes) behind the 512 B of queue counters
     assert multigpu.HEADER_BYTES == 512
+
+
+def test_pixel_interleaved_order_and_long_patch_split(built):
+    """Host logic of the round-2 schedulers: the pixel-order / frames-interleaved queue of the multi-frame integration job
+    (multigpu.interleaved_pixel_ray_order) and the split of a learned patch order between the warp-specialised
+    long-patch kernel and the fused kernel (images.long_patch_count, images._long_grid_cap)."""
+    from mahakala_b200 import images, multigpu
+    res, frames = 10, 4
+    n = res * res
+    order = multigpu.interleaved_pixel_ray_order(res, frames)
+    assert order.dtype == np.int32 and np.array_equal(np.sort(order), np.arange(frames * n))
+    assert np.array_equal(order.reshape(n, frames) // n, np.tile(np.arange(frames), (n, 1)))      # frames interleaved
+    assert np.array_equal(order.reshape(n, frames)[:, 2] % n, np.arange(n))                       # pixel order in a frame
+    assert np.array_equal(multigpu.interleaved_pixel_ray_order(7, 1), np.arange(49))
+    # learned lengths (descending): patches >= threshold x the longest, at most one per SM of every participant
+    L = np.array([3765] * 10 + [2000] * 50 + [1000] * 400 + [900] * 3000 + [400] * 20000)
+    assert images.long_patch_count(L, 1, threshold=0.5, sms=148) == 60
+    assert images.long_patch_count(L, 1, threshold=0.25, sms=148) == 148           # capped: one per SM
+    assert images.long_patch_count(L, 8, threshold=0.25, sms=148) == 460
+    assert images.long_patch_count(L, 8, threshold=0.2, sms=148) == 8 * 148
+    assert images.long_patch_count(None, 8, sms=148) == 0 and images.long_patch_count(np.zeros(4), 1, sms=148) == 0
+    assert images._long_grid_cap(460, 1) == 0 and images._long_grid_cap(460, 8) >= 460 // (8 * max(1, images._LONG_EXCLUSIVE))
