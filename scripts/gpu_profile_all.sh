@@ -15,5 +15,7 @@ ncu --set full --clock-control none --import-source on -k regex:integrate_kernel
     python scripts/profile_target.py paged > gpurun_out/prof_integrate_paged.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:render_kernel -s 1 -c 1 -f -o gpurun_out/prof_render \
     python scripts/profile_target.py render 256 > gpurun_out/prof_render.log 2>&1
+MK_LONG_EXCLUSIVE=0 ncu --set full --clock-control none --import-source on -k regex:render_pipeline_kernel -s 1 -c 1 -f -o gpurun_out/prof_render_long \
+    python scripts/profile_target.py long > gpurun_out/prof_render_long.log 2>&1
 python scripts/parity_report.py > gpurun_out/parity_report.log 2>&1
 ls -la gpurun_out | tail -20

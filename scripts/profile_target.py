@@ -24,6 +24,16 @@ if what in ("all", "paged"):
         geo.integrate_paged(10000, s0, 40, 1e-4, a, store=store)
     torch.cuda.synchronize()
     del store
+if what == "long":
+    # the warp-specialised long-patch kernel on the 592 longest patches of the 1024^2 cfg4 frame (learned order)
+    arr = make_synthetic_snapshot(ncells=256, block=32, extent=32.0, seed=0)
+    m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
+                                      arr["x3f"], arr["LogicalLocations"], arr["Levels"], a, fluid_gamma=arr["fluid_gamma"],
+                                      storage="f64")
+    images.learn_patch_order(a, resolution=1024)
+    for _ in range(2):
+        images.render(m, resolution=1024, observing_frequencies=(230e9,), long_patches=592)
+    torch.cuda.synchronize()
 if what in ("all", "render"):
     nc = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     arr = make_synthetic_snapshot(ncells=nc, block=32, extent=32.0, seed=0)

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 export R=${ROUND:-r02}
-for k in integrate_final integrate_paged render; do
+for k in integrate_final integrate_paged render render_long; do
   [ -f gpurun_out/prof_$k.ncu-rep ] && python scripts/summarize_ncu.py gpurun_out/prof_$k.ncu-rep profiles/${R}_${k}_ncu.txt > /dev/null
 done
 python - <<'PY'
