@@ -40,6 +40,7 @@ E2E_CHUNKS = int(os.environ.get("MK_E2E_CHUNKS", "0"))
 # cell storage of the cfg4 snapshot: float64 cells render ~3 % faster than float32 cells (no F2F conversions in the
 # gather; the kernel is FP64/latency-bound, not traffic-bound) at twice the HBM footprint; images are bit-identical
 RENDER_STORAGE = os.environ.get("MK_RENDER_STORAGE", "f64")
+DUAL_FP64_PER_STEP = 2003     # executed FP64-pipe instructions per ray-step of the dual-number plugin (SASS count)
 FLOP_PER_RAY_STEP = 859          # 312 add + 523 mul + 12 div + 12 sqrt
 RENDER_FP64_PER_STEP = 455       # executed FP64-pipe instructions of the fused kernel per ray-step (SASS count) ...
 RENDER_FP64_PER_SAMPLE = 340     # ... and per in-domain sample on top of that
@@ -421,6 +422,32 @@ def run_b200(args):
     value = work * args.steps / (dev_ms_max * 1e-3)
     e2e_value = e2e_work * args.steps / e2e_s_max
 
+    # ---- SURVEY 8(d) extras (rank 0): the dual-number plugin's own count, the reference's scan overhead ----
+    plugin_line = None
+    if rank == 0:
+        sub = ma.initialize_geodesics_at_camera(a, CFG2["inclination"], CFG2["distance"], -CFG2["fov"] / 2, CFG2["fov"] / 2, 512)
+        geo.set_metric("kerr_schild_dual")
+        try:
+            geo.integrate_final(CFG2["N"], sub, CFG2["div"], CFG2["tol"], a)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            _, _, _, ptot = geo.integrate_final(CFG2["N"], sub, CFG2["div"], CFG2["tol"], a, want_total=True)
+            p1.record()
+            torch.cuda.synchronize()
+            psteps, pms = int(ptot.item()), p0.elapsed_time(p1)
+        finally:
+            geo.set_metric("kerr_schild")
+        plugin_line = {"metric": "Kerr-Schild typed generically (DualMetric<KerrSchildFn>: forward-mode dual numbers "
+                                 "through the metric functor + adjugate inverse, the path of every user-registered "
+                                 "spacetime), 512x512 rays of the cfg2 camera, final-state mode",
+                       "ray_steps": psteps, "ms": pms, "ray_steps_per_s": psteps / (pms * 1e-3),
+                       "fp64_instr_per_ray_step": DUAL_FP64_PER_STEP,
+                       "fp64_issue_frac": psteps * DUAL_FP64_PER_STEP / (pms * 1e-3) / 1e12 / (fp64_peak / 2.0),
+                       "note": "the plugin's own executed FP64-pipe instructions per ray-step (SASS of its step function, "
+                               "cuobjdump: 2003 DFMA/DMUL/DADD against 430 for the closed form) over the issue rate of the "
+                               "DFMA microbenchmark; SURVEY 8(d): reported separately from the closed-form roofline"}
+
     render = None
     pages_used = store.pages_used if world == 1 else pages_job
     store = None
@@ -461,6 +488,12 @@ def run_b200(args):
                                  "achieved_GBps": dump_bytes / (kernel_ms * 1e-3) / 1e9,
                                  "peak_GBps": hbm_peak()}},
         }
+        line["reference_scan_overhead"] = {
+            "N": CFG2["N"], "mean_steps_per_ray": steps_per_pass / float(rays_here), "factor": CFG2["N"] * rays_here / float(steps_per_pass),
+            "note": "the reference's lax.scan runs all N iterations for every ray (geodesics.py:272) although a ray needs "
+                    "mean_steps of them; neither arm's timing includes that factor (the CPU arm exits early too)"}
+        if plugin_line is not None:
+            line["generic_metric_plugin"] = plugin_line
         if split is not None:
             line["split"] = split
         if render is not None:

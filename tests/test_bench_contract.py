@@ -54,3 +54,8 @@ def test_b200_arm_line(built):
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] > 1e4 and cb["cores"] >= 1
     assert d["render"]["ms"] > 0 and d["render"]["in_domain_samples"] > 0
+    ov = d["reference_scan_overhead"]
+    assert ov["N"] == 10000 and 5 < ov["factor"] < 40 and abs(ov["factor"] * ov["mean_steps_per_ray"] - 10000) < 1e-6
+    gp = d["generic_metric_plugin"]
+    assert gp["ray_steps_per_s"] > 1e8 and gp["fp64_instr_per_ray_step"] == 2003 and 0.05 < gp["fp64_issue_frac"] < 1.05
+    assert "parity_note" in d["config"] and d["roofline"]["traffic_source"].startswith("static")
