@@ -1,7 +1,6 @@
 """CUDA path against the vectors produced by the whole reference package (tests/golden/reference_fluid_golden.npz).
 
-Kept in its own module, collected last: it was written after the round's GPU budget was spent, so unlike every other
-`-m gpu` test it had not run on a B200 when it was committed (it follows the validated smoke / sampling / image tests).
+Kept in its own module, collected last (written at the end of round 1; green on B200 since round 2).
 """
 import numpy as np
 import pytest
