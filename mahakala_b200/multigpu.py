@@ -238,16 +238,17 @@ def _cells_tensor(model):
 
 
 def broadcast_large(w, src=0):
-    """Broadcast of a large 1-D device tensor as SCATTER + ALL-GATHER (van de Geijn): the root sends each rank one
-    n-th of the buffer, then every rank collects the other pieces from its peers.  On an NVSwitch node the root's
-    egress is then (n-1)/n of the buffer ONCE and all links work at the same time, where NCCL's ring broadcast moves
-    the whole buffer through a chain of GPUs (measured on 8 B200s, 0.64 GB: see DESIGN 6).  In place: every rank's
-    piece is a view of its own buffer.  Small tensors, two ranks, or a non-NCCL backend: plain ``dist.broadcast``."""
+    """Broadcast of a large 1-D device tensor.  Default: ``dist.broadcast`` -- NCCL's broadcast moves the 0.64 GB of
+    float32 cells of the cfg4 snapshot to 8 B200s in 1.23 ms = 524 GB/s (``scripts/dev/bcast_probe.py``,
+    ``profiles/r02_bcast_probe.txt``).  ``MK_BCAST=sag`` selects the scatter + all-gather formulation (van de Geijn: the
+    root sends each rank one n-th, every rank collects the rest from its peers, in place), built to beat the ring and
+    measured SLOWER on the NVSwitch node: 1.79 ms = 359 GB/s.  What the replication's ``broadcast`` phase costs beyond
+    the wire (5-6 ms in all) is the float64 -> float32 -> float64 conversion and the 0.64 GB temporary on either side."""
     import os
     rank, n = world()
     numel = w.numel()
     if (n <= 2 or dist.get_backend() != "nccl" or numel * w.element_size() < (32 << 20) or numel % n != 0
-            or os.environ.get("MK_BCAST", "sag") != "sag"):
+            or os.environ.get("MK_BCAST", "nccl") != "sag"):
         dist.broadcast(w, src=src)
         return
     pieces = w.view(n, numel // n)
@@ -267,7 +268,7 @@ def replicate_snapshot(model=None, src=0, wire="auto"):
     checked on the device) -- half the bytes on the wire, expanded again by the receivers; float32 snapshots always
     travel as stored.  Returns the (replica) model on every rank; ``model.replication_timing`` holds the phases in
     ms: host_prep / upload / ghost_fill (rank ``src``; zero elsewhere), meta (geometry exchange), broadcast (device
-    time of the collective INCLUDING the wire conversion on both sides), collective (the scatter + all-gather alone,
+    time of the collective INCLUDING the wire conversion on both sides), collective (the NCCL broadcast alone,
     ``broadcast_large``), wire_bytes, effective GB/s of both.
     """
     import time
