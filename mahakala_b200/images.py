@@ -65,6 +65,7 @@ def _priority_stream(dev):
 
 
 import os as _os
+QUICK_ORDER = _os.environ.get("MK_QUICK_ORDER", "1") == "1"    # coarse pre-pass in front of a cold multi-GPU frame
 _DEV_SKIP_BULK = False      # scripts/dev/strong_probe.py: time the long-patch launch alone
 _LONG_EXCLUSIVE = int(_os.environ.get("MK_LONG_EXCLUSIVE", "2"))     # 0 = shared SMs; 1..4 = groups per exclusive CTA
 
@@ -123,7 +124,49 @@ def learn_patch_order(bhspin, camera_inclination=60, camera_distance=1000, fov=2
     key = _camera_key(bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)
     _learned_order[key] = order
     _learned_lengths[key] = longest[order.long()].cpu().numpy()
+    _quick_long.pop(key, None)
     return order
+
+
+_quick_long = {}            # camera key -> number of long patches found by quick_patch_order (absolute rule)
+
+
+def forget_patch_orders():
+    """Drop every learned / quick patch order (scheduling state only)."""
+    _learned_order.clear(); _learned_lengths.clear(); _quick_long.clear()
+
+
+def quick_patch_order(bhspin, camera_inclination=60, camera_distance=1000, fov=20, resolution=160, max_nsteps=10000,
+                      div=40, tol=1e-4, coarse=8, cap=1024, long_factor=2.5):
+    """A COARSE, CAPPED version of ``learn_patch_order`` that is cheap enough to run in front of a single cold frame:
+    geodesics only, every ``coarse``-th pixel per axis, at most ``cap`` steps (~0.8 ms on B200: 1024 dependent steps of
+    0.64 us; the full pass of ``learn_patch_order`` costs the longest ray's 3765 steps plus 15 ms of throughput at 1024^2).
+    A patch counts as LONG when the coarse rays around it (3x3 dilation: the photon ring is thinner than a coarse
+    pixel, its neighbourhood is not) need at least ``long_factor`` x the shortest ray of the frame -- the absolute form of
+    "a quarter of the longest ray", which a capped pass cannot know.  Patches are ordered by that estimate, longest
+    first.  Deterministic, so every rank of a multi-GPU job computes the same order by itself.  ``render`` calls it on
+    its own when several GPUs share one frame and nothing better has been learned (``patch_order='auto'``); results
+    never depend on it.  Returns ``(order, n_long)``."""
+    dev = require_gpu()
+    res = int(resolution)
+    px_n, py_n = -(-res // 4), -(-res // 8)
+    cres = max(8, -(-res // int(coarse)))
+    s0 = geo.initialize_geodesics_at_camera(bhspin, camera_inclination, camera_distance, -fov / 2., fov / 2., cres)
+    _, nsteps, _ = geo.integrate_final(min(int(cap), int(max_nsteps)), s0, div, tol, bhspin)
+    est = nsteps.view(1, 1, cres, cres).to(torch.float32)
+    est = torch.nn.functional.max_pool2d(est, kernel_size=3, stride=1, padding=1)            # 3x3 dilation
+    # patch (px, py) covers pixels [4 px, 4 px + 4) x [8 py, 8 py + 8): its centre in coarse-pixel units
+    cx = ((torch.arange(px_n, device=dev, dtype=torch.float32) * 4 + 2.0) * (cres / float(res))).long().clamp_(0, cres - 1)
+    cy = ((torch.arange(py_n, device=dev, dtype=torch.float32) * 8 + 4.0) * (cres / float(res))).long().clamp_(0, cres - 1)
+    longest = est[0, 0][cx][:, cy].reshape(-1)                                                # patch index = px * py_n + py
+    order = torch.argsort(longest, descending=True, stable=True).to(torch.int32)
+    shortest = float(nsteps[nsteps > 0].min()) if bool((nsteps > 0).any()) else 0.0
+    n_long = int((longest >= long_factor * shortest).sum()) if shortest > 0 else 0
+    key = _camera_key(bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)
+    _learned_order[key] = order
+    _learned_lengths[key] = longest[order.long()].cpu().numpy()
+    _quick_long[key] = n_long
+    return order, n_long
 
 
 def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=1.e26, M_bh=6.2e9 * Msun,
@@ -176,13 +219,21 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
     counters = torch.zeros(2, dtype=torch.int64, device=dev) if want_counters else None
     order = None
     lengths = None
+    quick_n = None
     if s0d is None:
         if isinstance(patch_order, torch.Tensor):
             order = patch_order
         elif patch_order == "auto":
             key = _camera_key(fluid_model.bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)
             order = _learned_order.get(key)
+            if (order is None and participants > 1 and nfreq == 1 and QUICK_ORDER and long_patches == "auto"
+                    and geo._active_metric == geo.KERR_SCHILD and queue is not None and long_queue is not None):
+                # several GPUs share ONE frame and nothing is known about this camera: a coarse, capped geodesics-only
+                # pre-pass (~1 ms, once per camera, identical on every rank) finds the photon-ring patches
+                order, _ = quick_patch_order(fluid_model.bhspin, camera_inclination, camera_distance, fov, res,
+                                             max_nsteps, div, tol)
             lengths = _learned_lengths.get(key) if order is not None else None
+            quick_n = _quick_long.get(key) if order is not None else None
             if order is None:
                 order = centre_out_patch_order(res, dev)
         elif patch_order == "centre_out":
@@ -196,7 +247,9 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
     whole = tuple(patch_range[:2]) == (0, -1) and (len(patch_range) < 3 or patch_range[2] == 1)
     n_long = 0
     if order is not None and whole and nfreq == 1 and metric_id == geo.KERR_SCHILD and (queue is None) == (long_queue is None):
-        if long_patches == "auto":
+        if long_patches == "auto" and quick_n is not None:
+            n_long = min(int(quick_n), int(participants) * torch.cuda.get_device_properties(dev).multi_processor_count)
+        elif long_patches == "auto":
             n_long = long_patch_count(lengths, participants, device=dev)
         elif long_patches:
             n_long = min(int(long_patches), int(order.numel()))

@@ -75,7 +75,15 @@ if rank == 0:
     same = bool(torch.equal(img, alone)) and bool(torch.equal(img, plain))
     print(f"[{world} ranks] long-patch pipeline ({n_long} patches): identical to the fused single-GPU image: {same}")
     assert same and n_long > 0
-images._learned_order.clear(); images._learned_lengths.clear()
+images.forget_patch_orders()
+# nothing learned: render() runs the coarse, capped pre-pass (images.quick_patch_order) on every rank by itself
+img = multigpu.render_distributed(m, mode="queue", shared=shared1, **kw1)
+if rank == 0:
+    nq = list(images._quick_long.values())
+    same = bool(torch.equal(img, plain))
+    print(f"[{world} ranks] quick patch order ({nq} long patches): identical to the fused single-GPU image: {same}")
+    assert same and len(nq) == 1 and nq[0] > 0
+images.forget_patch_orders()
 dist.barrier()
 shared1.close()
 

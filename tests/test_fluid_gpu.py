@@ -230,7 +230,8 @@ def test_distributed_render_two_ranks(built):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mode=queue: identical to single-GPU image: True" in r.stdout
     assert "mode=static: identical to single-GPU image: True" in r.stdout
-    assert "identical to the fused single-GPU image: True" in r.stdout
+    assert "long-patch pipeline" in r.stdout and "quick patch order" in r.stdout
+    assert r.stdout.count("identical to the fused single-GPU image: True") == 2
     assert "shared ray queue: identical to single-GPU integration: True" in r.stdout
     assert "identical to the single-GPU dump: True" in r.stdout
 
@@ -299,7 +300,14 @@ def test_long_patch_pipeline_is_bit_identical(setup, exclusive, monkeypatch):
         assert torch.equal(images.render(dm, resolution=48), ref)
         assert np.array_equal(images.make_image(dm, resolution=48).reshape(-1), np.asarray(ref.cpu())[0])
     finally:
-        images._learned_order.clear(); images._learned_lengths.clear()
+        images.forget_patch_orders()
+    # the coarse, capped pre-pass used in front of a cold multi-GPU frame: finds long patches, same pixels
+    order, n_long = images.quick_patch_order(A, resolution=48)
+    try:
+        assert n_long > 0 and sorted(order.tolist()) == list(range(12 * 6))
+        assert torch.equal(images.render(dm, resolution=48, long_patches=n_long), ref)
+    finally:
+        images.forget_patch_orders()
     # explicit rays (ragged), f32 cells, analytic torus
     s0 = ma.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 14)[3:3 + 150]
     ref = images.render(dm, s0=s0)
