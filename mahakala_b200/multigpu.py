@@ -328,12 +328,18 @@ def replicate_snapshot(model=None, src=0, wire="auto"):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     wire_ms = w0.elapsed_time(w1)
+    # the root enqueues its broadcast first and then waits for the receivers (still allocating): the rank that arrives
+    # LAST sees the transfer alone, so the minimum over ranks is the wire time
+    wmin = torch.tensor([wire_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+    wire_min = float(wmin)
     base = getattr(model, "setup_timing", {}) if rank == src else {}
     model.replication_timing = dict(host_prep=base.get("host_prep", 0.0), upload=base.get("upload", 0.0),
                                     ghost_fill=base.get("ghost_fill", 0.0), meta=t_meta, broadcast=ms,
                                     wire_bytes=int(wire_bytes), wire_format=meta[0]["wire"],
                                     broadcast_GBps=wire_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
-                                    collective=wire_ms, collective_GBps=wire_bytes / (wire_ms * 1e-3) / 1e9 if wire_ms > 0 else 0.0)
+                                    collective=wire_ms, collective_min=wire_min,
+                                    collective_GBps=wire_bytes / (wire_min * 1e-3) / 1e9 if wire_min > 0 else 0.0)
     return model
 
 
