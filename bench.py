@@ -477,6 +477,9 @@ def run_b200(args):
                     "explicit_copy_pipeline": {"value": e2e_work * args.steps / e2e_copy_s_max, "unit": "ray-steps/s",
                                                "ms_per_step": 1e3 * e2e_copy_s_max / args.steps,
                                                "note": "same step with cudaMemcpyAsync H2D / D2H on side streams, 4 chunks"},
+                    "l2_note": "no flush in this loop: the inputs come from pinned host memory (never L2-resident) and the 40 GB "
+                               "dump is >> L2; the device-timed loop writes 256 MiB through L2 before every launch, whose "
+                               "write-back costs that launch ~0.3 ms -- which is why this figure can exceed `value` at small N",
                     "transfer": ("zero-copy: the kernel reads s0 from / writes results to pinned host memory over PCIe"
                                  if E2E_CHUNKS <= 0 else f"{E2E_CHUNKS}-chunk H2D / kernel / D2H pipeline")},
             "gpu_launches": n_launch,
