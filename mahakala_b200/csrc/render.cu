@@ -28,11 +28,8 @@ template <int KIND, int GROUPS>
 static int launch_pipeline_groups(const KerrSchild& g, const RenderArgs& A, long npatches, int max_ctas, cudaStream_t stream)
 {
     const size_t smem = GROUPS * (size_t)PIPE_GROUP_BYTES;
-    static bool configured = false;         // per instantiation
-    if (!configured) {
-        MK_CUDA_CHECK(cudaFuncSetAttribute(render_pipeline_kernel<KIND, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per device and cheap: set on every launch rather than cached per process
+    MK_CUDA_CHECK(cudaFuncSetAttribute(render_pipeline_kernel<KIND, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pipeline_kernel<KIND, GROUPS>, PIPE_THREADS * GROUPS, smem));
     if (per_sm < 1) per_sm = 1;
