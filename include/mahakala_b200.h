@@ -303,7 +303,7 @@ int mk_render(double bhspin, double cos_i, double sin_i, double distance, double
    shared-memory ring, so that the snapshot sample leaves the critical path of the dependent RK4 steps (0.64 instead of
    1.95 us per step for a lone patch on B200).  Pixels are bit-identical to mk_render's.  Meant for the few hundred
    patches that contain photon-ring rays (patch_begin .. patch_end of a longest-first patch_order), launched on a
-   high-priority stream next to an mk_render launch for the rest; nfreq must be 1.
+   high-priority stream next to an mk_render launch for the rest; nfreq <= 8 like mk_render.
    exclusive = 0: 128-thread CTAs (one patch each) that share their SM with other resident CTAs; exclusive = 1..4:
    512-thread CTAs that fill the register file of an SM, so that no warp of another launch competes with the producers
    for FP64 issue slots, with that many patch groups at work (one producer per SM sub-partition; the warps of the

@@ -4,7 +4,6 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "render_kernel.cuh"
-#include "render_pipeline.cuh"
 #include "snapshot.cuh"
 #include "plugin.cuh"
 #include "../../include/mahakala_b200.h"
@@ -17,43 +16,9 @@ __global__ void MK_RENDER_BOUNDS render_kernel(const KerrSchild g, const RenderA
     render_body<KerrSchild, NF, KIND>(g, A);
 }
 
-// long-patch variant: producer warp (geodesic) + consumer warps (sample, emission), see render_pipeline.cuh
-template <int KIND, int GROUPS>
-__global__ void __launch_bounds__(PIPE_THREADS * GROUPS, GROUPS == 1 ? 4 : 1) render_pipeline_kernel(const KerrSchild g, const RenderArgs A)
-{
-    render_pipeline_body<KIND, GROUPS>(g, A);
-}
-
-template <int KIND, int GROUPS>
-static int launch_pipeline_groups(const KerrSchild& g, const RenderArgs& A, long npatches, int max_ctas, cudaStream_t stream)
-{
-    const size_t smem = GROUPS * (size_t)PIPE_GROUP_BYTES;
-    // per device and cheap: set on every launch rather than cached per process
-    MK_CUDA_CHECK(cudaFuncSetAttribute(render_pipeline_kernel<KIND, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pipeline_kernel<KIND, GROUPS>, PIPE_THREADS * GROUPS, smem));
-    if (per_sm < 1) per_sm = 1;
-    long blocks = (long)sm_count() * per_sm;        // one patch per group at a time
-    const int working = (GROUPS == 1) ? 1 : A.pipe_groups;
-    const long need = (npatches + working - 1) / working;
-    if (need < blocks) blocks = need;
-    if (max_ctas > 0 && max_ctas < blocks) blocks = max_ctas;
-    if (blocks < 1) blocks = 1;
-    render_pipeline_kernel<KIND, GROUPS><<<(unsigned)blocks, PIPE_THREADS * GROUPS, smem, stream>>>(g, A);
-    MK_CUDA_CHECK(cudaGetLastError());
-    return 0;
-}
-
-template <int KIND>
-static int launch_pipeline_kind(const KerrSchild& g, const RenderArgs& A, long npatches, int exclusive, int max_ctas, cudaStream_t stream)
-{
-    if (exclusive) {
-        RenderArgs B = A;
-        B.pipe_groups = exclusive > PIPE_GROUPS_EXCLUSIVE ? PIPE_GROUPS_EXCLUSIVE : exclusive;
-        return launch_pipeline_groups<KIND, PIPE_GROUPS_EXCLUSIVE>(g, B, npatches, max_ctas, stream);
-    }
-    return launch_pipeline_groups<KIND, 1>(g, A, npatches, max_ctas, stream);
-}
+// long-patch variant (render_long.cu): producer warp (geodesic) + consumer warps (sample, emission)
+int launch_render_pipeline(const KerrSchild& g, const RenderArgs& A, int nfreq, long npatches, int exclusive, int max_ctas,
+                           cudaStream_t stream);
 
 // (Round 1 kept an experimental lane-refill variant of this kernel here: incoherent warps lose the L1 locality of
 // the gathers, 1.25-1.95x slower than whole patches on cfg4; numbers in DESIGN.md.)
@@ -162,13 +127,8 @@ static int render_impl(int metric_id, double bhspin, double cos_i, double sin_i,
     A.queue = queue ? queue : queue_counter(stream, 1);
     if (!A.queue) return 1;
     if (pipeline) {
-        MK_REQUIRE(nfreq == 1 && metric_id == MK_METRIC_KERR_SCHILD,
-                   "the long-patch pipeline carries one frequency in the built-in Kerr-Schild spacetime");
-        switch (snapshot_kind(A.sn)) {
-            case SNAP_F64_GRID_POW2: return launch_pipeline_kind<SNAP_F64_GRID_POW2>(g, A, span, exclusive, max_ctas, stream);
-            case SNAP_F32_GRID_POW2: return launch_pipeline_kind<SNAP_F32_GRID_POW2>(g, A, span, exclusive, max_ctas, stream);
-            default: return launch_pipeline_kind<SNAP_GENERIC>(g, A, span, exclusive, max_ctas, stream);
-        }
+        MK_REQUIRE(metric_id == MK_METRIC_KERR_SCHILD, "the long-patch pipeline runs in the built-in Kerr-Schild spacetime");
+        return launch_render_pipeline(g, A, nfreq, span, exclusive, max_ctas, stream);
     }
     if (nfreq == 1) return launch_render<1>(g, A, span, stream);
     if (nfreq == 2) return launch_render<2>(g, A, span, stream);

@@ -21,8 +21,8 @@
 // With 16 warps resident per SM the producer advances at its share of the FP64 pipe (455 instead of 795 FP64 instructions
 // per step on its chain), and once the GPU drains at 0.64 us per step.
 //
-// Built-in Kerr-Schild spacetime, one observing frequency (the latency-critical single-frame case); everything else
-// goes through render_body.  Replaces nothing new in the reference: same contract as render_kernel.cuh
+// Built-in Kerr-Schild spacetime, 1 to 8 observing frequencies (the consumers evaluate all of them for a sample and
+// fold each into its own (I_f, T_f)); registered spacetimes go through render_body.  Replaces nothing new in the reference: same contract as render_kernel.cuh
 // (/root/reference/mahakala/images.py:56-144).
 #pragma once
 #include "render_kernel.cuh"
@@ -31,7 +31,9 @@ namespace mk {
 
 constexpr int PIPE_RING = 8;            // slots per CTA
 constexpr int PIPE_CONSUMERS = 3;       // warps 1..3
-constexpr int PIPE_FIELDS = 13;         // s[8], f, l1, l2, l3, weight
+constexpr int PIPE_IN_FIELDS = 13;      // s[8], f, l1, l2, l3, weight
+// fields per slot: the 13 inputs, overwritten after use by the lane's (I, T) of every frequency (2 NF values)
+constexpr int pipe_fields(int nf) { return 2 * nf > PIPE_IN_FIELDS ? 2 * nf : PIPE_IN_FIELDS; }
 constexpr int PIPE_THREADS = 32 * (1 + PIPE_CONSUMERS);      // threads per patch group
 // Patch groups per CTA.  1: a 128-thread CTA that shares its SM with whatever else is resident (e.g. three CTAs of the
 // bulk launch, whose warps then compete with the producer for FP64 issue slots).  4: a 512-thread CTA = the whole
@@ -43,17 +45,21 @@ constexpr int PIPE_GROUPS_EXCLUSIVE = 4;
 // Per-group shared memory, addressed with 32-bit shared-window addresses (st.shared / ld.shared / mbarrier on
 // shared::cta): generic pointers to dynamic shared memory make the compiler rebuild the window base from SR_CgaCtaId at
 // every use, which a lone latency-bound warp pays for in full.
-//   rec   [PIPE_RING][PIPE_FIELDS][32] f64   a lane touches only its own column; fields 0, 1 are overwritten with the
-//                                            lane's (I, T) after this slot
+//   rec   [PIPE_RING][FIELDS][32] f64        a lane touches only its own column; fields 0 .. 2 NF - 1 are overwritten with
+//                                            the lane's (I_f, T_f) after this slot
 //   full  [PIPE_RING] mbarrier (32 arrivals) producer lanes -> consumer
 //   done  [PIPE_RING] mbarrier (32 arrivals) consumer lanes -> next consumer (fold) and producer (slot reuse)
 //   mask  [PIPE_RING] u32                    lanes that carry a record
 //   type  [PIPE_RING] i32                    0 = samples, 2 = samples, first slot of a patch, 1 = exit
-constexpr unsigned PIPE_OFF_FULL = PIPE_RING * PIPE_FIELDS * 32 * 8;
-constexpr unsigned PIPE_OFF_DONE = PIPE_OFF_FULL + PIPE_RING * 8;
-constexpr unsigned PIPE_OFF_MASK = PIPE_OFF_DONE + PIPE_RING * 8;
-constexpr unsigned PIPE_OFF_TYPE = PIPE_OFF_MASK + PIPE_RING * 4;
-constexpr unsigned PIPE_GROUP_BYTES = PIPE_OFF_TYPE + PIPE_RING * 4;
+template <int NF>
+struct PipeLayout {
+    static constexpr unsigned FIELDS = pipe_fields(NF);
+    static constexpr unsigned OFF_FULL = PIPE_RING * FIELDS * 32 * 8;
+    static constexpr unsigned OFF_DONE = OFF_FULL + PIPE_RING * 8;
+    static constexpr unsigned OFF_MASK = OFF_DONE + PIPE_RING * 8;
+    static constexpr unsigned OFF_TYPE = OFF_MASK + PIPE_RING * 4;
+    static constexpr unsigned GROUP_BYTES = OFF_TYPE + PIPE_RING * 4;
+};
 
 __device__ __forceinline__ void pipe_mbar_init(unsigned bar, unsigned count)
 {
@@ -100,9 +106,12 @@ __device__ __forceinline__ bool pipe_maybe_inside(const SnapshotView& sn, const 
            (sn.bbox_lo[2] <= s[3]) & (s[3] <= sn.bbox_hi[2]);
 }
 
-template <int KIND, int GROUPS>
+template <int NF, int KIND, int GROUPS>
 __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const RenderArgs& A)
 {
+    typedef PipeLayout<NF> LY;
+    constexpr unsigned PIPE_FIELDS = LY::FIELDS, PIPE_OFF_FULL = LY::OFF_FULL, PIPE_OFF_DONE = LY::OFF_DONE,
+                       PIPE_OFF_MASK = LY::OFF_MASK, PIPE_OFF_TYPE = LY::OFF_TYPE, PIPE_GROUP_BYTES = LY::GROUP_BYTES;
     extern __shared__ __align__(16) unsigned char mk_pipe_smem[];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     unsigned group = 0, role = warp;                // role 0 = producer, 1..3 = consumers
@@ -135,7 +144,9 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
             if (ty == 1u) break;
             const unsigned m = pipe_lds32(sh + PIPE_OFF_MASK + 4 * k);
             bool inside = false;
-            double e_out = 0.0, a_out = 0.0, w = 0.0;
+            double e_out[NF], a_out[NF], w = 0.0;
+#pragma unroll
+            for (int fq = 0; fq < NF; fq++) { e_out[fq] = 0.0; a_out[fq] = 0.0; }
             if ((m >> lane) & 1u) {
                 double s[8];
 #pragma unroll
@@ -150,26 +161,29 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
                 if (interp_prims_kind<KIND>(A.sn, s, prims)) {
 #endif
                     inside = true;
-                    emission_fast<1>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
-                                     [&](int, double e, double a) { e_out = e; a_out = a; });
+                    emission_fast<NF>(A.P, A.C, f, l, s, prims, A.nu_obs, A.inv_nu_obs,
+                                      [&](int fq, double e, double a) { e_out[fq] = e; a_out[fq] = a; });
                 }
             }
             // in-order fold: (I, T) after the previous slot of this patch (written by whichever consumer had it) -> after
             // this one.  Only these two FMAs are serial across the consumers; the sample above is not.
-            double I = 0.0, T = 1.0;
-            if (ty != 2u) {
-                const unsigned kp = (n - 1u) % PIPE_RING;
-                pipe_mbar_wait(sh + PIPE_OFF_DONE + 8 * kp, ((n - 1u) / PIPE_RING) & 1u);
-                I = pipe_lds(rec(kp, 0));
-                T = pipe_lds(rec(kp, 1));
+            const unsigned kp = (n - 1u) % PIPE_RING;
+            if (ty != 2u) pipe_mbar_wait(sh + PIPE_OFF_DONE + 8 * kp, ((n - 1u) / PIPE_RING) & 1u);
+#pragma unroll
+            for (int fq = 0; fq < NF; fq++) {
+                double I = 0.0, T = 1.0;
+                if (ty != 2u) {
+                    I = pipe_lds(rec(kp, 2 * fq));
+                    T = pipe_lds(rec(kp, 2 * fq + 1));
+                }
+                if (inside) {
+                    const double Tf = T;             // the update of render_body, operand for operand
+                    I = fma(Tf, w * e_out[fq], I);
+                    T = Tf * fma(-w, a_out[fq], 1.0);
+                }
+                pipe_sts(rec(k, 2 * fq), I);
+                pipe_sts(rec(k, 2 * fq + 1), T);
             }
-            if (inside) {
-                const double Tf = T;                 // the update of render_body, operand for operand
-                I = fma(Tf, w * e_out, I);
-                T = Tf * fma(-w, a_out, 1.0);
-            }
-            pipe_sts(rec(k, 0), I);
-            pipe_sts(rec(k, 1), T);
             pipe_mbar_arrive(sh + PIPE_OFF_DONE + 8 * k);
             const unsigned im = __ballot_sync(FULL_MASK, inside);
             if (lane == 0) my_samples += (unsigned long long)__popc(im);
@@ -252,6 +266,9 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
                 // two control words are written by all lanes with the same value
 #pragma unroll
                 for (int q = 0; q < 8; q++) pipe_sts(rec(k, q), s[q]);
+                // metric functions of the sample: whatever render_body<NF> feeds its fluid-frame algebra -- the first
+                // RK4 stage's (f, l) in the stage-1-first loop, the point cache's in the plain loop (bit-identity)
+                if constexpr (NF > MK_RENDER_PIPE_MAX) G.fl(s, cache, mf.f, mf.l1, mf.l2, mf.l3);
                 pipe_sts(rec(k, 8), mf.f); pipe_sts(rec(k, 9), mf.l1); pipe_sts(rec(k, 10), mf.l2);
                 pipe_sts(rec(k, 11), mf.l3); pipe_sts(rec(k, 12), wdt);
                 pipe_sts32(sh + PIPE_OFF_MASK + 4 * k, pm);
@@ -278,7 +295,9 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
             done_ptr++;
         }
         if (valid) {
-            A.image[ray] = (push_ptr != patch_first) ? pipe_lds(rec((push_ptr - 1u) % PIPE_RING, 0)) : 0.0;
+#pragma unroll
+            for (int fq = 0; fq < NF; fq++)
+                A.image[(long)fq * A.npx + ray] = (push_ptr != patch_first) ? pipe_lds(rec((push_ptr - 1u) % PIPE_RING, 2 * fq)) : 0.0;
             if (A.nsteps) A.nsteps[ray] = it;
             my_steps += (unsigned long long)it;
         }

@@ -181,8 +181,8 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
     'centre_out'; 'centre_out'; None = row-major; or an int32 device tensor.
     ``long_patches``: how many patches at the head of ``patch_order`` run through the warp-specialised long-patch kernel
     (``mk_render_long``: the sample leaves the critical path of the ray's dependent RK4 steps) on a high-priority
-    stream next to the bulk launch; 'auto' = ``long_patch_count`` of the learned order (0 without one); one frequency,
-    built-in spacetime, grid camera, whole frames only.  ``long_queue``: its queue counter when ``queue`` is shared by
+    stream next to the bulk launch; 'auto' = ``long_patch_count`` of the learned order (0 without one); built-in
+    spacetime, grid camera, whole frames only.  ``long_queue``: its queue counter when ``queue`` is shared by
     several GPUs (``participants`` of them); pixels are bit-identical either way.
     """
     dev = require_gpu()
@@ -226,7 +226,7 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
         elif patch_order == "auto":
             key = _camera_key(fluid_model.bhspin, camera_inclination, camera_distance, fov, res, max_nsteps, div, tol, dev)
             order = _learned_order.get(key)
-            if (order is None and participants > 1 and nfreq == 1 and QUICK_ORDER and long_patches == "auto"
+            if (order is None and participants > 1 and QUICK_ORDER and long_patches == "auto"
                     and geo._active_metric == geo.KERR_SCHILD and queue is not None and long_queue is not None):
                 # several GPUs share ONE frame and nothing is known about this camera: a coarse, capped geodesics-only
                 # pre-pass (~1 ms, once per camera, identical on every rank) finds the photon-ring patches
@@ -246,7 +246,7 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
         raise ValueError("the strict (literal IEEE) integrator has no fused render: use make_image_unfused")
     whole = tuple(patch_range[:2]) == (0, -1) and (len(patch_range) < 3 or patch_range[2] == 1)
     n_long = 0
-    if order is not None and whole and nfreq == 1 and metric_id == geo.KERR_SCHILD and (queue is None) == (long_queue is None):
+    if order is not None and whole and metric_id == geo.KERR_SCHILD and (queue is None) == (long_queue is None):
         if long_patches == "auto" and quick_n is not None:
             n_long = min(int(quick_n), int(participants) * torch.cuda.get_device_properties(dev).multi_processor_count)
         elif long_patches == "auto":

@@ -7,6 +7,8 @@ from mahakala_b200 import images, multigpu
 from mahakala_b200.grmhd import AthenakFluidModel
 from mahakala_b200.synthetic import make_synthetic_snapshot
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+NUS = [43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9][:int(sys.argv[2])] if len(sys.argv) > 2 else [230e9]
+MS = 2e24 if len(NUS) > 1 else 1e26
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -17,11 +19,11 @@ if rank == 0:
     m = AthenakFluidModel.from_arrays(arr["uov"], arr["B"], arr["x1v"], arr["x2v"], arr["x3v"], arr["x1f"], arr["x2f"],
                                       arr["x3f"], arr["LogicalLocations"], arr["Levels"], 0.94, fluid_gamma=arr["fluid_gamma"], storage="f64")
 m = multigpu.replicate_snapshot(m)
-ref = images.render(m, resolution=res) if rank == 0 else None
+ref = images.render(m, resolution=res, observing_frequencies=NUS, mass_scale=MS) if rank == 0 else None
 images.learn_patch_order(0.94, resolution=res)
 key = next(iter(images._learned_lengths))
 L = images._learned_lengths[key]
-shared = multigpu.SharedImage(1, res * res)
+shared = multigpu.SharedImage(len(NUS), res * res)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 def leg(n_long, reps=4, patch_range=(0, -1, 1), skip_bulk=False):
     images._DEV_SKIP_BULK = skip_bulk
@@ -31,7 +33,7 @@ def leg(n_long, reps=4, patch_range=(0, -1, 1), skip_bulk=False):
         shared.reset(); dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        images.render(m, resolution=res, image_out=shared.image_ptr, queue=shared.queue_ptr, long_queue=shared.ring_queue_ptr,
+        images.render(m, resolution=res, observing_frequencies=NUS, mass_scale=MS, image_out=shared.image_ptr, queue=shared.queue_ptr, long_queue=shared.ring_queue_ptr,
                       participants=world, long_patches=n_long, patch_range=patch_range)
         e1.record(); torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -43,7 +45,7 @@ for thr in (None, 0.3, 0.25):
     n_long = 0 if thr is None else min(int((L >= thr * L[0]).sum()), world * 148)
     r = leg(n_long)
     if rank == 0:
-        print(f"[{world} GPUs, {res}^2, exclusive={images._LONG_EXCLUSIVE}] threshold {thr}: {n_long:5d} long patches: min {r[0]:.2f} ms mean {r[1]:.2f} ms identical {r[2]}", flush=True)
+        print(f"[{world} GPUs, {res}^2, {len(NUS)} frequencies, exclusive={images._LONG_EXCLUSIVE}] threshold {thr}: {n_long:5d} long patches: min {r[0]:.2f} ms mean {r[1]:.2f} ms identical {r[2]}", flush=True)
 n_long = min(int((L >= 0.3 * L[0]).sum()), world * 148)
 r = leg(n_long, skip_bulk=True)
 if rank == 0: print(f"[{world} GPUs] long-patch launch alone ({n_long} patches): min {r[0]:.2f} ms mean {r[1]:.2f}", flush=True)

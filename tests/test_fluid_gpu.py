@@ -291,6 +291,14 @@ def test_long_patch_pipeline_is_bit_identical(setup, exclusive, monkeypatch):
             img, c = images.render(dm, want_counters=True, patch_order=order, long_patches=n_long, **kw)
             assert torch.equal(img, ref), (kw, n_long, float((img - ref).abs().max()))
             assert torch.equal(c, cref), (kw, n_long, c, cref)
+    # several frequencies: the consumers evaluate all of them per sample and fold each into its own (I_f, T_f)
+    for nus in ((86e9, 230e9), (43e9, 86e9, 230e9, 345e9, 690e9), (43e9, 86e9, 130e9, 230e9, 345e9, 460e9, 690e9, 870e9)):
+        kw = dict(resolution=24, observing_frequencies=nus, mass_scale=2e24)
+        ref, cref = images.render(dm, want_counters=True, patch_order="centre_out", **kw)
+        order = images.centre_out_patch_order(24, ref.device)
+        for n_long in (18, 7):
+            img, c = images.render(dm, want_counters=True, patch_order=order, long_patches=n_long, **kw)
+            assert torch.equal(img, ref) and torch.equal(c, cref), (len(nus), n_long, float((img - ref).abs().max()))
     # learned order: 'auto' sends the photon-ring patches to the pipeline kernel
     ref = images.render(dm, resolution=48)
     images.learn_patch_order(A, resolution=48)
