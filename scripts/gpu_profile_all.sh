@@ -1,5 +1,6 @@
 #!/bin/bash
-# Run on a B200 (gpurun): collects everything scripts/refresh_profiles.sh turns into profiles/.
+# Run on a B200: collects everything scripts/refresh_profiles.sh turns into profiles/.  Under gpurun use
+# scripts/gpu_profile_part.sh A and B instead: the four .ncu-rep files together exceed the 64 MiB gpurun brings back.
 mkdir -p gpurun_out
 R=${ROUND:-r02}
 python bench.py > gpurun_out/bench_${R}_n1.json 2> gpurun_out/bench_n1.err
