@@ -21,8 +21,11 @@ namespace mk {
 #ifndef MK_INT_CTAS           // experiment knob: resident CTAs of the final / padded modes (1 -> 255 registers)
 #define MK_INT_CTAS 4
 #endif
+#ifndef MK_INT_THREADS        // experiment knob: threads per CTA (192 x 3 CTAs = 18 warps per SM at <= 112 registers)
+#define MK_INT_THREADS 128
+#endif
 template <class Metric, int MODE, bool SHARED = false>
-__global__ void __launch_bounds__(128, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : MK_INT_CTAS)) integrate_kernel(const Metric g, const IntegrateArgs A)
+__global__ void __launch_bounds__(Metric::kHeavy ? 128 : MK_INT_THREADS, Metric::kHeavy ? 2 : ((MODE == MODE_PAGED) ? MK_PAGED_CTAS : MK_INT_CTAS)) integrate_kernel(const Metric g, const IntegrateArgs A)
 {
     integrate_body<Metric, MODE, SHARED>(g, A);
 }
@@ -85,17 +88,19 @@ static int launch_integrate(const Metric& g, const IntegrateArgs& A, cudaStream_
     auto kern = A.pages ? (shared ? integrate_kernel<Metric, MODE_PAGED, true> : integrate_kernel<Metric, MODE_PAGED>)
                         : (A.S ? integrate_kernel<Metric, MODE_PADDED> : integrate_kernel<Metric, MODE_FINAL>);
     const size_t dyn_smem = (A.pages && MK_DUMP_TMA) ? 4 * DUMP_SMEM_PER_WARP : 0;      // TMA dump staging, 4 warps
-    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, dyn_smem));
+    const int threads = Metric::kHeavy ? 128 : MK_INT_THREADS;
+    const int wpc = threads / 32;                                            // warps per CTA
+    MK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, dyn_smem));
     if (per_sm < 1) per_sm = 1;
     long warps_needed = (A.npx + 31) / 32;
     long blocks = (long)sm_count() * per_sm;
-    long need = (warps_needed + 3) / 4;
+    long need = (warps_needed + wpc - 1) / wpc;
     if (need < blocks) blocks = need;
     if (blocks < 1) blocks = 1;
     IntegrateArgs B = A;
-    B.chunk_div = (int)(4 * 4 * blocks) * (shared ? A.chunk_div : 1);     // 4 x warps x participating GPUs
+    B.chunk_div = (int)(4 * wpc * blocks) * (shared ? A.chunk_div : 1);     // 4 x warps x participating GPUs
     B.chunk_mul = (unsigned)(0x100000000ULL / (unsigned long long)B.chunk_div);
-    kern<<<(unsigned)blocks, 128, dyn_smem, stream>>>(g, B);
+    kern<<<(unsigned)blocks, threads, dyn_smem, stream>>>(g, B);
     MK_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
