@@ -177,8 +177,9 @@ def render(fluid_model, camera_inclination=60, camera_distance=1000, mass_scale=
 
     ``s0`` (npx, 8) replaces the grid camera by explicit rays.  ``image_out`` / ``queue`` may be tensors
     or raw device pointers (possibly in a peer GPU's memory) — see ``mahakala_b200.multigpu``.
-    ``patch_order``: 'auto' = the order learned for this camera by ``learn_patch_order`` if there is one, else
-    'centre_out'; 'centre_out'; None = row-major; or an int32 device tensor.
+    ``patch_order``: 'auto' = the order learned for this camera by ``learn_patch_order`` if there is one, else -- when
+    several GPUs share the frame (``participants`` > 1 with both queues) -- the order of ``quick_patch_order``, computed
+    here once per camera, else 'centre_out'; 'centre_out'; None = row-major; or an int32 device tensor.
     ``long_patches``: how many patches at the head of ``patch_order`` run through the warp-specialised long-patch kernel
     (``mk_render_long``: the sample leaves the critical path of the ray's dependent RK4 steps) on a high-priority
     stream next to the bulk launch; 'auto' = ``long_patch_count`` of the learned order (0 without one); built-in
