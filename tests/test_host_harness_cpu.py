@@ -150,6 +150,34 @@ def test_adaptive_integrator_option(hk):
     assert (ns == 0).all() and np.array_equal(fin, far)
 
 
+def test_adaptive_integrator_against_an_independent_solver(hk):
+    """Accuracy pin of the adaptive option by a solver that shares nothing with it: SciPy's DOP853 (8th order, rtol
+    1e-12) on the ORACLE's literal right-hand side (jets + 4x4 inverse, geodesics.py:294-309), stopped by an event at the
+    coordinate time at which the adaptive run (rtol 1e-10, closed-form acceleration) froze.  Escaped rays agree to 1e-9 of
+    the state, captured ones -- whose wavevector blue-shifts by orders of magnitude near the horizon -- to 1e-7."""
+    from scipy.integrate import solve_ivp
+    from oracle import c_oracle, mahakala_oracle as onp
+    s0 = np.ascontiguousarray(onp.initialize_geodesics_at_camera(A, 60, 1000, -10, 10, 64))
+    idx = [0, 700, 1500, 2079, 2080, 2111, 3000, 4095]
+    sub = np.ascontiguousarray(s0[idx])
+    fin, ns, nr, rl = _adaptive(hk, sub, 1e-10)
+    captured = rl < 100
+    assert captured.sum() == 3 and nr.sum() == 0
+
+    def f(lam, y):
+        return c_oracle.rhs(y[None, :].copy(), A)[0]
+
+    for k in range(len(idx)):
+        def reached(lam, y, t_end=fin[k, 0]):
+            return y[0] - t_end
+        reached.terminal = True
+        sol = solve_ivp(f, (0.0, -1e6), sub[k], method="DOP853", rtol=1e-12, atol=1e-14, events=reached, max_step=50.0)
+        assert sol.status == 1 and len(sol.y_events[0]) == 1
+        ye = sol.y_events[0][0]
+        err = np.abs(ye - fin[k]) / np.maximum(np.abs(fin[k]), 1e-3 * np.abs(fin[k]).max())
+        assert err.max() < (1e-7 if captured[k] else 1e-9), (idx[k], err.max())
+
+
 def test_fused_emission_chain_on_adversarial_inputs(hk, monkeypatch):
     """The adversarial cases of tests/test_emission_gpu.py (sigma cut, Theta_e floor, X range, Planck switch, aligned /
     reversed / null wavevectors, degenerate primitives, exp underflow) run through the HOST build of emission_fast."""
