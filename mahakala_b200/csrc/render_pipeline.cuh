@@ -101,9 +101,10 @@ __device__ __forceinline__ unsigned pipe_lds32(unsigned addr)
 // conservative "could this point be sampled?" (a superset of the exact membership test the consumer applies)
 __device__ __forceinline__ bool pipe_maybe_inside(const SnapshotView& sn, const double s[8])
 {
-    if (sn.source != 0) return true;
-    return (sn.bbox_lo[0] <= s[1]) & (s[1] <= sn.bbox_hi[0]) & (sn.bbox_lo[1] <= s[2]) & (s[2] <= sn.bbox_hi[1]) &
-           (sn.bbox_lo[2] <= s[3]) & (s[3] <= sn.bbox_hi[2]);
+    // branch-free: every divergent region between the first RK4 stage and the rest of the step costs the lone producer
+    // its reconvergence
+    return (sn.source != 0) | ((sn.bbox_lo[0] <= s[1]) & (s[1] <= sn.bbox_hi[0]) & (sn.bbox_lo[1] <= s[2]) &
+                               (s[2] <= sn.bbox_hi[1]) & (sn.bbox_lo[2] <= s[3]) & (s[3] <= sn.bbox_hi[2]));
 }
 
 template <int NF, int KIND, int GROUPS>
@@ -210,7 +211,7 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
         if (A.patch_order) patch = A.patch_order[patch];
 
         long ray;
-        double s[8];
+        double s[8] = {0.0, 100.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0};       // lanes without a ray step on this (discarded)
         bool active;
         if (A.s0) {
             ray = patch * 32 + lane;
@@ -237,7 +238,8 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
         int it = 0;
         double dt = 0.0;
         KerrSchild::Cache cache;
-        if (active) dt = A.rule(G.radius(s, cache));
+        const double dt_first = A.rule(G.radius(s, cache));
+        if (active) dt = dt_first;
         if (dt == 0.0) active = false;
         double wdt = 0.0;
         bool pending = false;
@@ -251,16 +253,18 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
             const unsigned old_bar = sh + PIPE_OFF_DONE + 8 * (done_ptr % PIPE_RING), old_par = (done_ptr / PIPE_RING) & 1u;
             unsigned room_ok = 1u;
             if (need_room) room_ok = pipe_mbar_test(old_bar, old_par);
-            if (active) G.accel(s, s + 4, a1, &cache, &mf);
-            if (need_room) {
-                if (!room_ok) pipe_mbar_wait(old_bar, old_par);
-                done_ptr++;
-            }
+            // No divergent regions in this loop: every lane executes the step, finished lanes on whatever their registers
+            // hold (no memory access depends on it, nothing of theirs is kept) -- a lone producer pays for every
+            // reconvergence point between the first RK4 stage, the push and the rest of the step (measured: 0.85 ->
+            // 0.80 us per step for the branch-free bounding-box test alone).
+            G.accel(s, s + 4, a1, &cache, &mf);
+            if (need_room & (room_ok == 0u)) pipe_mbar_wait(old_bar, old_par);       // rare: the consumers are behind
+            done_ptr += need_room ? 1u : 0u;
             // hand the state to the consumers (render_body samples it here)
 #ifdef MK_PIPE_NOPUSH          // experiment: the producer alone (no slot is ever pushed; pixels are wrong)
             const bool want = false;
 #else
-            const bool want = active && pending && pipe_maybe_inside(A.sn, s);
+            const bool want = active & pending & pipe_maybe_inside(A.sn, s);
 #endif
             const unsigned pm = __ballot_sync(FULL_MASK, want);
             if (pm) {
@@ -279,19 +283,15 @@ __device__ __forceinline__ void render_pipeline_body(const KerrSchild& G, const 
                 pipe_mbar_arrive(sh + PIPE_OFF_FULL + 8 * k);
                 push_ptr++;
             }
-            if (active) {
-                rk4_rest(G, s, a1, dt, s);
-                const double dtn = A.rule(G.radius(s, cache));
-                if (dtn == 0.0) {
-                    active = false;             // step rejected; ray frozen (geodesics.py:264-267)
-                } else {
-                    wdt = -dt * A.P.L_unit;     // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
-                    dt = dtn;
-                    it++;
-                    pending = true;
-                    if (it == A.N) active = false;      // row N is not part of the reference's scan output
-                }
-            }
+            rk4_rest(G, s, a1, dt, s);
+            const double dtn = A.rule(G.radius(s, cache));
+            // geodesics.py:264-267: a step whose end point fails the rule is rejected and the ray is frozen
+            const bool moved = active & (dtn != 0.0);
+            wdt = moved ? -dt * A.P.L_unit : wdt;       // -dt[i-1] * L_unit  (> 0): weight of the sample at the new state
+            dt = moved ? dtn : dt;
+            it += moved ? 1 : 0;
+            pending = pending | moved;
+            active = moved & (it != A.N);               // row N is not part of the reference's scan output
         }
         while (done_ptr != push_ptr) {
             pipe_mbar_wait(sh + PIPE_OFF_DONE + 8 * (done_ptr % PIPE_RING), (done_ptr / PIPE_RING) & 1u);
