@@ -19,7 +19,7 @@
 // Every number is produced by the same device functions with the same operands in the same order as in render_body, so
 // the pixels are bit-identical to the fused kernel's (tests/test_fluid_gpu.py::test_long_patch_pipeline_is_bit_identical).
 // With 16 warps resident per SM the producer advances at its share of the FP64 pipe (455 instead of 795 FP64 instructions
-// per step on its chain), and once the GPU drains at 0.64 us per step.
+// per step on its chain), and once the GPU drains at 0.73 us per step (0.645 for the geodesic alone).
 //
 // Built-in Kerr-Schild spacetime, 1 to 8 observing frequencies (the consumers evaluate all of them for a sample and
 // fold each into its own (I_f, T_f)); registered spacetimes go through render_body.  Replaces nothing new in the reference: same contract as render_kernel.cuh
