@@ -300,7 +300,7 @@ int mk_render(double bhspin, double cos_i, double sin_i, double distance, double
               long patch_stride, const int* patch_order, void* stream);
 /* The same contract through the warp-specialised LONG-PATCH kernel (csrc/render_pipeline.cuh): one CTA per patch, a
    producer warp integrates the geodesics and hands every state to three consumer warps (sample + emission) through a
-   shared-memory ring, so that the snapshot sample leaves the critical path of the dependent RK4 steps (0.64 instead of
+   shared-memory ring, so that the snapshot sample leaves the critical path of the dependent RK4 steps (0.73 instead of
    1.95 us per step for a lone patch on B200).  Pixels are bit-identical to mk_render's.  Meant for the few hundred
    patches that contain photon-ring rays (patch_begin .. patch_end of a longest-first patch_order), launched on a
    high-priority stream next to an mk_render launch for the rest; nfreq <= 8 like mk_render.
